@@ -1,0 +1,340 @@
+"""Oracle-side problem fabrication (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Restates the callers on the input side of the boundary so tests can build (Z, G, options):
+  functions/create_coupled_data.m:55-183 (Frobenius / Gaussian noise; couplings 0,1,3,4 and 2),
+  functions/init_coupled_AOADMM_CMTF.m:37-169 (random init, nvecs=0),
+  functions_for_example_scripts/create_CP_data_example10piecewiseconstant.m:77-92,
+and the configuration sections of example_script6 (:25-133), example_script1 (:21-123),
+example_script10 (:23-122).  MATLAB's randn/randi streams cannot be reproduced from NumPy
+(SURVEY.md 8c RNG note) so seeds here are our own.
+"""
+import numpy as np
+
+from .prox import constraints_to_prox
+from .tensor_ops import full_ktensor
+
+
+def _size1(s):
+    return int(s[0]) if isinstance(s, (list, tuple, np.ndarray)) else int(s)
+
+
+def create_coupled_data(model, sz, modes, lambdas, noise, coupling, normalize_columns, distr_data, rng,
+                        piecewise_constant_mode1=False):
+    """create_coupled_data.m:48-183.  distr_data[n](rows, cols, rng) -> ndarray."""
+    P = len(modes)
+    nb_modes = len(sz)
+    lin = coupling['lin_coupled_modes']
+    ctype_l = coupling.get('coupling_type', [])
+    trafo = coupling.get('coupl_trafo_matrices') or [None] * nb_modes
+    A = [None] * nb_modes
+    Delta = [None] * nb_modes
+
+    def normcols(M):
+        return M / np.sqrt(np.sum(M * M, axis=0))[None, :]
+
+    for p in range(P):
+        for n in modes[p]:
+            if lin[n - 1] == 0:
+                A[n - 1] = distr_data[n - 1](_size1(sz[n - 1]), len(lambdas[p]), rng)
+                if normalize_columns:
+                    A[n - 1] = normcols(A[n - 1])
+                if model[p] == 'PAR2' and modes[p].index(n) == 1:
+                    AA = A[n - 1]
+                    A[n - 1] = [np.roll(AA, k, axis=0) for k in range(len(sz[n - 1]))]   # circshift (:64-72)
+    if piecewise_constant_mode1:                                                    # example10 generator :77-92
+        I = _size1(sz[0])
+        for r in range(len(lambdas[0])):
+            jumps = np.concatenate(([1], np.sort(rng.randint(1, I + 1, size=4)), [I]))
+            values = -1 + 2 * rng.rand(5)
+            for i in range(5):
+                A[0][jumps[i] - 1:jumps[i + 1], r] = values[i]
+        if normalize_columns:
+            A[0] = normcols(A[0])
+    nb_c = max(lin) if len(lin) else 0
+    for i in range(1, nb_c + 1):
+        ct = ctype_l[i - 1]
+        cp_modes = [m for m in range(1, nb_modes + 1) if lin[m - 1] == i]
+        mode1 = cp_modes[0]
+        p1 = [p for p in range(P) if mode1 in modes[p]][0]
+        R1 = len(lambdas[p1])
+        if ct == 0:
+            A[mode1 - 1] = distr_data[mode1 - 1](_size1(sz[mode1 - 1]), R1, rng)
+            if normalize_columns:
+                A[mode1 - 1] = normcols(A[mode1 - 1])
+            for j in cp_modes[1:]:
+                A[j - 1] = A[mode1 - 1].copy()
+        elif ct == 1:
+            mode1 = cp_modes[int(np.argmax([_size1(sz[m - 1]) for m in cp_modes]))]
+            A[mode1 - 1] = distr_data[mode1 - 1](_size1(sz[mode1 - 1]), R1, rng)
+            if normalize_columns:
+                A[mode1 - 1] = normcols(A[mode1 - 1])
+            Delta[i - 1] = trafo[mode1 - 1] @ A[mode1 - 1]
+            for j in cp_modes:
+                if j != mode1:
+                    A[j - 1] = np.linalg.pinv(trafo[j - 1]) @ Delta[i - 1]
+        elif ct == 2:
+            Delta[i - 1] = distr_data[mode1 - 1](_size1(sz[mode1 - 1]), trafo[mode1 - 1].shape[1], rng)
+            if normalize_columns:
+                Delta[i - 1] = normcols(Delta[i - 1])
+            for j in cp_modes:
+                A[j - 1] = np.linalg.lstsq(trafo[j - 1].T, Delta[i - 1].T, rcond=None)[0].T
+        elif ct == 3:
+            Delta[i - 1] = distr_data[mode1 - 1](trafo[mode1 - 1].shape[1], R1, rng)
+            if normalize_columns:
+                Delta[i - 1] = normcols(Delta[i - 1])
+            for j in cp_modes:
+                A[j - 1] = trafo[j - 1] @ Delta[i - 1]
+        elif ct == 4:
+            Delta[i - 1] = distr_data[mode1 - 1](_size1(sz[mode1 - 1]), trafo[mode1 - 1].shape[0], rng)
+            if normalize_columns:
+                Delta[i - 1] = normcols(Delta[i - 1])
+            for j in cp_modes:
+                A[j - 1] = Delta[i - 1] @ trafo[j - 1]
+    X = [None] * P
+    for p in range(P):
+        if model[p] == 'CP':
+            Xp = full_ktensor([A[m - 1] for m in modes[p]], lambdas[p])
+            N = rng.randn(*Xp.shape)
+            sigma = noise[p] * np.sqrt(np.sum(Xp ** 2)) / np.sqrt(np.sum(N ** 2))
+            X[p] = np.asfortranarray(Xp + sigma * N)
+        else:
+            m1, m2, m3 = modes[p]
+            Cf = A[m3 - 1]
+            Xp = []
+            for k in range(Cf.shape[0]):
+                Xk = A[m1 - 1] @ np.diag(np.asarray(lambdas[p], dtype=float)) @ np.diag(Cf[k, :]) @ A[m2 - 1][k].T
+                Nk = rng.randn(*Xk.shape)
+                sigma = noise[p] * np.sqrt(np.sum(Xk ** 2)) / np.sqrt(np.sum(Nk ** 2))
+                Xp.append(np.asfortranarray(Xk + sigma * Nk))
+            X[p] = Xp
+    return X, A, Delta
+
+
+def normalize_objects(X, model):
+    """example_script6...m:97-113: divide every data set by its Frobenius norm."""
+    out = []
+    norms = []
+    for p, Xp in enumerate(X):
+        if model[p] == 'CP':
+            nz = np.sqrt(np.sum(Xp ** 2))
+            out.append(np.asfortranarray(Xp / nz))
+        else:
+            nz = np.sqrt(sum(np.sum(Xk ** 2) for Xk in Xp))
+            out.append([np.asfortranarray(Xk / nz) for Xk in Xp])
+        norms.append(nz)
+    return out, norms
+
+
+def znorm_const(Z):
+    """cmtf_AOADMM.m:124-156 (Frobenius, no missing data)."""
+    out = []
+    for p, Xp in enumerate(Z['object']):
+        if Z['model'][p] == 'CP':
+            out.append(float(np.sqrt(np.sum(Xp ** 2)) ** 2))
+        else:
+            out.append(float(sum(np.sqrt(np.sum(Xk ** 2)) ** 2 for Xk in Xp)))
+    return out
+
+
+def init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=None):
+    """init_coupled_AOADMM_CMTF.m:37-169 with nvecs = 0."""
+    sz = Z['size']
+    lambdas = init_options['lambdas_init']
+    distr = init_options['distr']
+    normalize = init_options['normalize']
+    modes = Z['modes']
+    model = Z['model']
+    lin = Z['coupling']['lin_coupled_modes']
+    ctype_l = Z['coupling'].get('coupling_type', [])
+    trafo = Z['coupling'].get('coupl_trafo_matrices') or [None] * len(sz)
+    constrained = Z['constrained_modes']
+    constraints = Z['constraints']
+    P = len(modes)
+    nb_modes = len(sz)
+    nb_c = max(lin) if len(lin) else 0
+    G = {'fac': [None] * nb_modes, 'coupling_fac': [None] * nb_c, 'constraint_fac': [None] * nb_modes,
+         'coupling_dual_fac': [None] * nb_modes, 'constraint_dual_fac': [None] * nb_modes,
+         'P': [None] * P, 'DeltaB': [None] * P, 'mu_DeltaB': [None] * P}
+
+    def normcols(M):
+        return M / np.sqrt(np.sum(M * M, axis=0))[None, :]
+
+    for p in range(P):
+        R = len(lambdas[p])
+        for n in modes[p]:
+            if model[p] == 'PAR2' and modes[p].index(n) == 1:
+                G['DeltaB'][p] = rng.rand(R, R)
+                G['fac'][n - 1] = []
+                G['P'][p] = []
+                G['mu_DeltaB'][p] = []
+                for k in range(len(sz[n - 1])):
+                    Fk = distr[n - 1](int(sz[n - 1][k]), R, rng)
+                    G['P'][p].append(np.eye(int(sz[n - 1][k]), R))
+                    G['mu_DeltaB'][p].append(rng.rand(int(sz[n - 1][k]), R))
+                    if normalize:
+                        Fk = normcols(Fk)
+                    G['fac'][n - 1].append(Fk)
+            else:
+                F = distr[n - 1](_size1(sz[n - 1]), R, rng)
+                if normalize:
+                    F = normcols(F)
+                G['fac'][n - 1] = F
+    if any(constrained):
+        prox_ops, _ = constraints_to_prox(constrained, constraints, sz)
+        for p in range(P):
+            for n in modes[p]:
+                if not constrained[n - 1]:
+                    continue
+                if model[p] == 'PAR2' and modes[p].index(n) == 1:
+                    G['constraint_fac'][n - 1] = []
+                    G['constraint_dual_fac'][n - 1] = []
+                    for k in range(len(sz[n - 1])):
+                        Zk = distr[n - 1](*G['fac'][n - 1][k].shape, rng)
+                        if constraints[n - 1][0] != 'tPARAFAC2':
+                            Zk = prox_ops[n - 1](Zk, 1.0)
+                        G['constraint_fac'][n - 1].append(Zk)
+                        G['constraint_dual_fac'][n - 1].append(rng.rand(*G['fac'][n - 1][k].shape))
+                else:
+                    Zc = distr[n - 1](*G['fac'][n - 1].shape, rng)
+                    G['constraint_fac'][n - 1] = prox_ops[n - 1](Zc, 1.0)
+                    G['constraint_dual_fac'][n - 1] = rng.rand(*G['fac'][n - 1].shape)
+    for n in range(1, nb_c + 1):
+        cmodes = [m for m in range(1, nb_modes + 1) if lin[m - 1] == n]
+        mode1 = cmodes[0]
+        ct = ctype_l[n - 1]
+        F1 = G['fac'][mode1 - 1]
+        H1 = trafo[mode1 - 1]
+        if ct == 0:
+            G['coupling_fac'][n - 1] = rng.rand(*F1.shape)
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['coupling_fac'][n - 1].shape)
+        elif ct == 1:
+            G['coupling_fac'][n - 1] = rng.rand(H1.shape[0], F1.shape[1])
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['coupling_fac'][n - 1].shape)
+        elif ct == 2:
+            G['coupling_fac'][n - 1] = rng.rand(F1.shape[0], H1.shape[1])
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['coupling_fac'][n - 1].shape)
+        elif ct == 3:
+            G['coupling_fac'][n - 1] = rng.rand(H1.shape[1], F1.shape[1])
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['fac'][m - 1].shape)
+        elif ct == 4:
+            G['coupling_fac'][n - 1] = rng.rand(F1.shape[0], H1.shape[0])
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['fac'][m - 1].shape)
+        elif ct == 5:
+            G['coupling_fac'][n - 1] = rng.rand(*Delta[n - 1].shape)
+            for m in cmodes:
+                G['coupling_dual_fac'][m - 1] = rng.rand(G['coupling_fac'][n - 1].shape[0], G['fac'][m - 1].shape[1])
+    return G
+
+
+# ----------------------------------------------------------------------------------------------
+# configuration builders
+# ----------------------------------------------------------------------------------------------
+def d_rand(r, c, rng):
+    return rng.rand(r, c)
+
+
+def d_randn(r, c, rng):
+    return rng.randn(r, c)
+
+
+def d_rand01(r, c, rng):
+    return rng.rand(r, c) + 0.1
+
+
+def default_options(**kw):
+    """example_script6...m:120-132."""
+    o = dict(Display='no', DisplayIters=10, MaxOuterIters=4000, MaxInnerIters=5, AbsFuncTol=1e-4,
+             OuterRelTol=1e-8, innerRelPrTol_coupl=1e-3, innerRelPrTol_constr=1e-3,
+             innerRelDualTol_coupl=1e-3, innerRelDualTol_constr=1e-3, bsum=0, eps_log=1e-10)
+    o.update(kw)
+    return o
+
+
+def _finish(model, sz, modes, lambdas, noise, coupling, distr, constrained_modes, constraints, weights, rng,
+            normalize_columns=0, init_normalize=1, piecewise=False, Delta_shapes=None):
+    X, Atrue, Delta = create_coupled_data(model, sz, modes, lambdas, noise, coupling, normalize_columns, distr, rng,
+                                          piecewise_constant_mode1=piecewise)
+    obj, norms = normalize_objects(X, model)
+    Z = {'loss_function': ['Frobenius'] * len(modes), 'model': model, 'modes': modes, 'size': sz,
+         'coupling': coupling, 'constrained_modes': constrained_modes, 'constraints': constraints,
+         'weights': weights, 'object': obj}
+    init_options = {'lambdas_init': lambdas, 'nvecs': 0, 'distr': distr, 'normalize': init_normalize}
+    G = init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=Delta_shapes)
+    return Z, G, {'Atrue': Atrue, 'norms': norms, 'Delta': Delta}
+
+
+def config_script6(seed=0, sz=(50, 60, 40, 50, 70, 60, 80), R=3, noise=0.2):
+    """C1: example_script6_matrix_matrix_CP_nonneg.m:25-92 (3-way CP + two coupled matrices, nonneg)."""
+    rng = np.random.RandomState(seed)
+    sz = list(sz)
+    modes = [[1, 2, 3], [4, 5], [6, 7]]
+    lambdas = [[1.0] * R] * 3
+    distr = [d_rand, d_rand, d_randn, d_rand, d_rand, d_rand, d_rand]
+    coupling = {'lin_coupled_modes': [1, 2, 0, 1, 0, 2, 0], 'coupling_type': [0, 0],
+                'coupl_trafo_matrices': [None] * 7}
+    constrained = [1, 0, 0, 1, 1, 1, 1]          # mode 2 unconstrained although a constraint is listed (quirk 9)
+    nn = ('non-negativity',)
+    constraints = [nn, nn, None, nn, nn, nn, nn]
+    return _finish(['CP', 'CP', 'CP'], sz, modes, lambdas, [noise] * 3, coupling, distr, constrained, constraints,
+                   [1 / 3, 1 / 3, 1 / 3], rng)
+
+
+def config_cp_matrix(I, J, K, M, R, seed=0, noise=0.2):
+    """C2/C3 family: 3-way CP I x J x K coupled in mode 1 with an I x M matrix, all modes nonneg
+    (modes={[1 2 3],[4 5]}, lin_coupled_modes=[1 0 0 1 0], weights [1/2 1/2])."""
+    rng = np.random.RandomState(seed)
+    sz = [I, J, K, I, M]
+    modes = [[1, 2, 3], [4, 5]]
+    lambdas = [[1.0] * R] * 2
+    distr = [d_rand] * 5
+    coupling = {'lin_coupled_modes': [1, 0, 0, 1, 0], 'coupling_type': [0], 'coupl_trafo_matrices': [None] * 5}
+    nn = ('non-negativity',)
+    return _finish(['CP', 'CP'], sz, modes, lambdas, [noise] * 2, coupling, distr, [1] * 5, [nn] * 5,
+                   [0.5, 0.5], rng)
+
+
+def config_cp_par2(I=20, J=30, K=40, Jk=30, Kp=20, R=3, seed=0, noise=0.0):
+    """C4 family: example_script1_CP_PAR2_nonneg.m:21-63 (CP coupled in mode 1 with a regular PARAFAC2)."""
+    rng = np.random.RandomState(seed)
+    sz = [I, J, K, I, [Jk] * Kp, Kp]
+    modes = [[1, 2, 3], [4, 5, 6]]
+    lambdas = [[1.0] * R] * 2
+    distr = [d_rand, d_randn, d_randn, d_rand, d_rand, d_rand01]
+    coupling = {'lin_coupled_modes': [1, 0, 0, 1, 0, 0], 'coupling_type': [0], 'coupl_trafo_matrices': [None] * 6}
+    nn = ('non-negativity',)
+    constrained = [1, 0, 0, 1, 1, 1]
+    constraints = [nn, None, None, nn, nn, nn]
+    return _finish(['CP', 'PAR2'], sz, modes, lambdas, [noise] * 2, coupling, distr, constrained, constraints,
+                   [0.5, 0.5], rng)
+
+
+def config_cp_tv(I=60, J=50, K=70, R=3, seed=0, noise=0.8, eta=1e-3, mode1=('TV regularization',)):
+    """C5 family: example_script10_CP_TVreg.m:23-57 (TV on a piecewise-constant mode 1, l2-ball on 2,3)."""
+    rng = np.random.RandomState(seed)
+    sz = [I, J, K]
+    modes = [[1, 2, 3]]
+    lambdas = [[1.0] * R]
+    distr = [d_randn] * 3
+    coupling = {'lin_coupled_modes': [0, 0, 0], 'coupling_type': [], 'coupl_trafo_matrices': [None] * 3}
+    c1 = tuple(mode1) + ((eta,) if len(mode1) == 1 else ())
+    constraints = [c1, ('l2-ball', 1.0), ('l2-ball', 1.0)]
+    return _finish(['CP'], sz, modes, lambdas, [noise], coupling, distr, [1, 1, 1], constraints, [1.0], rng,
+                   normalize_columns=1, piecewise=True)
+
+
+def config_single_cp(sz=(12, 10, 8), R=3, seed=0, noise=0.1, constraints=None, constrained=None, distr=None):
+    """Single uncoupled 3-way (or N-way) CP tensor with arbitrary per-mode constraints."""
+    rng = np.random.RandomState(seed)
+    n = len(sz)
+    sz = list(sz)
+    modes = [list(range(1, n + 1))]
+    coupling = {'lin_coupled_modes': [0] * n, 'coupling_type': [], 'coupl_trafo_matrices': [None] * n}
+    constraints = constraints if constraints is not None else [None] * n
+    constrained = constrained if constrained is not None else [1 if c else 0 for c in constraints]
+    return _finish(['CP'], sz, modes, [[1.0] * R], [noise], coupling, distr or [d_rand] * n, constrained,
+                   constraints, [1.0], rng)
