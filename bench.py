@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py - AO-ADMM outer iterations/s on B200 (metric of BASELINE.json), driver contract in the task prompt.
+
+  python bench.py --gpus N --steps K --warmup W            our engine (CUDA, C ABI of include/aoadmm.h)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's algorithm on the host cores
+                                                           (NumPy/OpenBLAS oracle port: MATLAB cannot run offline)
+
+A "step" is one outer AO-ADMM iteration (one sweep over all modes: 3 tensor MTTKRPs + 2 matrix products + every
+inner ADMM loop with all tolerances 0, i.e. MaxInnerIters=5 inner iterations per mode group) of the workload below.
+
+Workload (same for every N so that the 1->8 curve is a strong-scaling curve): the C3 family of SURVEY.md 8d,
+a 4096 x 4096 x K3 nonneg CP tensor (R=64) coupled in mode 1 with a 4096 x 8192 matrix, K3 = 1024 so that the
+FP64 tensor (137.4 GB) fits ONE B200; the tensor is generated on device (it cannot exist in host memory at that
+size) and sharded along mode 3 across the N ranks.  BENCH_WORKLOAD=c2 selects configs[1] (1000^3, R=32, 1000x5000).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'matlab-code_b200'))
+
+WORKLOADS = {
+    # name: (I, J, K, M, R, cpu_sample_dims)
+    'c3k1024': dict(I=4096, J=4096, K=1024, M=8192, R=64, sample=dict(I=1024, J=1024, K=256, M=2048)),
+    'c2': dict(I=1000, J=1000, K=1000, M=5000, R=32, sample=dict(I=1000, J=1000, K=1000, M=5000)),
+    'tiny': dict(I=64, J=48, K=40, M=80, R=8, sample=dict(I=64, J=48, K=40, M=80)),
+}
+FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool: profiles/r01_fp64_probe.log (DMMA.8x8x4 issue-rate probe)
+
+
+def zero_tol_options(iters):
+    return dict(MaxOuterIters=iters, MaxInnerIters=5, AbsFuncTol=0.0, OuterRelTol=0.0, innerRelPrTol_coupl=0.0,
+                innerRelPrTol_constr=0.0, innerRelDualTol_coupl=0.0, innerRelDualTol_constr=0.0, bsum=0)
+
+
+def make_problem(I, J, K, M, R, seed=0, with_tensor=False):
+    """C2/C3 construction of SURVEY.md 8d: X = [[A,B,C]] + noise (level 0.2), Y = A V' + noise, all nonneg, w=[1/2 1/2].
+    Factors are host-side (small); the tensor itself is only built on the host when with_tensor=True."""
+    rng = np.random.RandomState(seed)
+    A, B, C, V = rng.rand(I, R), rng.rand(J, R), rng.rand(K, R), rng.rand(M, R)
+    Y = A @ V.T
+    N = rng.standard_normal((I, M))
+    Y = Y + 0.2 * np.linalg.norm(Y) / np.linalg.norm(N) * N
+    Y = np.asfortranarray(Y / np.linalg.norm(Y))
+    X = None
+    if with_tensor:
+        X = np.empty((I, J, K), order='F')
+        KR = (C[:, None, :] * B[None, :, :]).reshape(-1, R) if I * J * K <= 2 ** 27 else None
+        nrm2_x = 0.0
+        nrm2_n = 0.0
+        noise = np.empty((I, J, K), order='F', dtype=np.float32)
+        for k in range(K):   # slab-wise to bound temporaries
+            slab = (A * C[k, :]) @ B.T
+            X[:, :, k] = slab
+            nrm2_x += float(np.sum(slab * slab))
+            nz = rng.standard_normal((I, J), dtype=np.float32)
+            noise[:, :, k] = nz
+            nrm2_n += float(np.sum(nz.astype(np.float64) ** 2))
+        del KR
+        sigma = 0.2 * np.sqrt(nrm2_x) / np.sqrt(nrm2_n)
+        for k in range(K):
+            X[:, :, k] += sigma * noise[:, :, k]
+        del noise
+        X /= np.sqrt(float(np.sum(X * X)))
+    nn = ('non-negativity',)
+    sz = [I, J, K, I, M]
+    Z = {'loss_function': ['Frobenius'] * 2, 'model': ['CP', 'CP'], 'modes': [[1, 2, 3], [4, 5]], 'size': sz,
+         'coupling': {'lin_coupled_modes': [1, 0, 0, 1, 0], 'coupling_type': [0], 'coupl_trafo_matrices': [None] * 5},
+         'constrained_modes': [1] * 5, 'constraints': [nn] * 5, 'weights': [0.5, 0.5], 'object': [X, Y], 'rank': [R, R]}
+
+    def normc(F):
+        return F / np.linalg.norm(F, axis=0)
+    G = {'fac': [normc(rng.rand(s, R)) for s in sz], 'constraint_fac': [rng.rand(s, R) for s in sz],
+         'constraint_dual_fac': [rng.rand(s, R) for s in sz],
+         'coupling_dual_fac': [rng.rand(I, R), None, None, rng.rand(I, R), None], 'coupling_fac': [rng.rand(I, R)],
+         'P': [None, None], 'DeltaB': [None, None], 'mu_DeltaB': [None, None]}
+    return Z, G, (A, B, C)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(',')]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], p[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_baseline_run(wl, steps, warmup):
+    """The oracle (NumPy restatement of cmtf_fun_AOADMM.m, Tensor-Toolbox-style MTTKRP = unfold + Khatri-Rao + DGEMM)
+    on the host cores, on a bounded sample of the workload; flop-proportional extrapolation to the full size."""
+    sys.path.insert(0, ROOT)
+    from oracle.cmtf_fun_aoadmm import cmtf_fun_AOADMM as oracle_solve
+    sm = wl['sample']
+    Z, G, _ = make_problem(sm['I'], sm['J'], sm['K'], sm['M'], wl['R'], seed=0, with_tensor=True)
+    zn = [float(np.sum(Z['object'][0] ** 2)), float(np.sum(Z['object'][1] ** 2))]
+    if warmup > 0:
+        oracle_solve(Z, zn, G, options=zero_tol_options(min(warmup, 1)))
+    t = time.perf_counter()
+    _, out = oracle_solve(Z, zn, G, options=zero_tol_options(steps))
+    dt = time.perf_counter() - t
+    per_iter = (out['time_at_it'][-1] - out['time_at_it'][0]) / steps   # excludes the iteration-0 objective
+    scale = (wl['I'] * wl['J'] * wl['K']) / float(sm['I'] * sm['J'] * sm['K'])
+    full = (scale == 1.0)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count()
+    sample = '%d outer iterations of %dx%dx%d R=%d + %dx%d matrix (%s)' % (
+        steps, sm['I'], sm['J'], sm['K'], wl['R'], sm['I'], sm['M'],
+        'full workload' if full else 'tensor sample, it/s scaled by 1/%g ~ flops' % scale)
+    return {'value': 1.0 / (per_iter * scale), 'unit': 'outer_iters/s', 'cores': cores, 'kind': 'port',
+            'sample': sample, 'sample_s_per_iter': per_iter, 'wall_s': dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=os.environ.get('BENCH_WORKLOAD', 'c3k1024'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    I, J, K, M, R = wl['I'], wl['J'], wl['K'], wl['M'], wl['R']
+    config = {'workload': 'CP %dx%dx%d R=%d nonneg + coupled %dx%d matrix (SURVEY 8d C3 family, K=%d so the FP64 tensor '
+                          'fits one GPU), MaxInnerIters=5, all tolerances 0' % (I, J, K, R, I, M, K),
+              'name': args.workload, 'sharding': 'mode-3 slabs over %d rank(s)' % world,
+              'l2_policy': 'inputs (%.1f GB tensor) far larger than the 126 MB L2' % (8.0 * I * J * K / 1e9)}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5))
+        cb = cpu_baseline_run(wl, steps, args.warmup)
+        line = {'impl': 'reference', 'metric': 'ao_admm_outer_iters_per_s', 'value': cb['value'], 'unit': 'outer_iters/s',
+                'n_gpus': args.gpus, 'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 / cb['value'],
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': config, 'cpu_baseline': cb,
+                'e2e': {'value': cb['value'], 'unit': 'outer_iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'note': 'MATLAB/Octave + Tensor Toolbox are not available offline: this is the NumPy/OpenBLAS port of '
+                        'cmtf_fun_AOADMM.m (oracle/), timed on the host cores'}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import aoadmm_b200 as ab
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the engine has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        t = torch.zeros(128, dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            t.copy_(torch.tensor(list(ab.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Z, G, facs = make_problem(I, J, K, M, R, seed=0, with_tensor=False)
+    lo, hi = ab.shard_range(K, rank, world)
+    solver = ab.Solver(Z, [1.0, float(np.sum(Z['object'][1] ** 2))], rank=rank, world_size=world, device=local_rank,
+                       unique_id=uid, shard=[(lo, hi), None])
+    solver.generate_cp_data(1, facs, 0.2, 20261018)
+    solver.set_state(G)
+
+    # ---- device-resident throughput (`value`) ----
+    solver.run(zero_tol_options(max(args.warmup, 3)))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = solver.launch_count()
+    ph0 = solver.phase_ms().copy()
+    barrier()
+    t0 = time.perf_counter()
+    out = solver.run(zero_tol_options(args.steps))
+    dev_ms = solver.last_run_ms()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = solver.launch_count() - l0
+    ph = solver.phase_ms() - ph0
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    assert out['OuterIterations'] == args.steps
+
+    # ---- per-mode MTTKRP kernel times (CUDA events on the engine's stream) for the roofline ----
+    Kloc = hi - lo
+    flops_mode = 2.0 * I * J * Kloc * R
+    bytes_mode = 8.0 * I * J * Kloc
+    mode_ms = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
+    tsum = sum(mode_ms)
+    achieved = 3 * flops_mode / (tsum * 1e-3) / 1e12
+    hbm_peak = 6557.1
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            hbm_peak = float(json.load(f)['hbm_gbs'])
+    except Exception:
+        pass
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                'frac': achieved / FP64_DMMA_PEAK_TFLOPS, 'traffic': None,
+                'kernel': 'mttkrp_lead_kernel / mttkrp_inner_kernel (FP64 DMMA.8x8x4 + TMA), 3 modes',
+                'per_mode_ms': mode_ms, 'per_mode_tflops': [flops_mode / (m * 1e-3) / 1e12 for m in mode_ms],
+                'per_mode_hbm_gbs': [bytes_mode / (m * 1e-3) / 1e9 for m in mode_ms], 'hbm_peak_gbs_measured': hbm_peak,
+                'hbm_frac': (3 * bytes_mode / (tsum * 1e-3) / 1e9) / hbm_peak,
+                'peak_source': 'FP64 tensor peak measured with a DMMA.8x8x4 issue-rate probe on this pool '
+                               '(profiles/r01_fp64_probe.log; MEASURED_PEAKS.json has no FP64 entry); cuBLAS DGEMM '
+                               'reaches 34.2-35.8 TFLOP/s on the same box',
+                'algorithmic_flops_per_launch': flops_mode, 'algorithmic_bytes_per_launch': bytes_mode,
+                'mttkrp_share_of_step': float(ph[0] / dev_ms) if dev_ms > 0 else None}
+
+    # ---- end-to-end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        # The coupled matrix, the full state (5 factors, 5 Z, 5 mu_Z, Delta, 2 mu_Delta) go host->device, the state comes
+        # back device->host, inside the timed region.  The tensor is device-generated at this size (137 GB cannot exist
+        # on the host), so it is re-created on device inside the timed region instead of copied.
+        barrier()
+        t0 = time.perf_counter()
+        s2 = ab.Solver(Z, [1.0, float(np.sum(Z['object'][1] ** 2))], rank=rank, world_size=world, device=local_rank,
+                       unique_id=None if world == 1 else _fresh_uid(ab, dist, torch, rank), shard=[(lo, hi), None])
+        s2.generate_cp_data(1, facs, 0.2, 20261018)
+        s2.set_state(G)
+        o2 = s2.run(zero_tol_options(args.steps))
+        G2 = s2.get_state()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        s2.close()
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+        state_bytes = sum(a.nbytes for k in ('fac', 'constraint_fac', 'constraint_dual_fac', 'coupling_dual_fac', 'coupling_fac')
+                          for a in G[k] if a is not None)
+        h2d = state_bytes + Z['object'][1].nbytes + sum(f.nbytes for f in facs)
+        e2e = {'value': args.steps / e2e_s, 'unit': 'outer_iters/s', 'h2d_bytes_per_step': h2d / args.steps,
+               'd2h_bytes_per_step': state_bytes / args.steps,
+               'note': 'one cmtf_fun_AOADMM call of %d outer iterations through the C ABI (create + generate tensor on '
+                       'device + set_state + run + get_state + destroy), host wall clock, max over ranks' % args.steps}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline_run(wl, 3, 1)
+
+    if rank == 0:
+        line = {'metric': 'ao_admm_outer_iters_per_s', 'value': args.steps / (dev_ms * 1e-3), 'unit': 'outer_iters/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps,
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+                'cpu_baseline': cb, 'wall_ms_per_step': wall_ms / args.steps,
+                'final_f_tensors': out['f_tensors'],
+                'timing': 'CUDA events on the engine stream around the whole run (includes the one-off iteration-0 '
+                          'objective of cmtf_fun_AOADMM.m:32), max over ranks'}
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _fresh_uid(ab, dist, torch, rank):
+    t = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    if rank == 0:
+        t.copy_(torch.tensor(list(ab.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
+
+
+if __name__ == '__main__':
+    sys.exit(main())

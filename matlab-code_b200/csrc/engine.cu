@@ -1,0 +1,1145 @@
+// engine.cu - the AO-ADMM outer loop on device-resident state.
+//
+// Control flow mirrors functions/cmtf_fun_AOADMM.m:
+//   :10        couplings = unique(lin_coupled_modes)  (0 = uncoupled modes first)
+//   :62-81     initial Grams
+//   :87-476    outer loop: per coupling id -> per object -> per mode precompute (MTTKRP, Hadamard, rho, B, chol),
+//              uncoupled modes updated immediately (LS :134 or ADMM_constrained_only :144), coupled groups
+//              updated jointly after all their precomputes (ADMM_coupled_case0 :277)
+//   :447-456   objective (shortcut :1235-1241) + evaluate_stopping_conditions.m:8-44
+//   :478       make_exit_flag.m:4-29
+// All numerics run in the kernels of mttkrp.cu / smallops.cu / prox.cu; this file only sequences launches and
+// does the scalar bookkeeping the reference does in MATLAB scalars.
+#include "engine.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+
+namespace aoadmm {
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL through dlopen (only needed when world_size > 1)
+// ---------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* load_nccl() {
+  static NcclApi api;
+  if (api.lib != nullptr) return &api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) throw CudaError(6, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
+    throw CudaError(6, "libnccl.so.2 lacks required symbols");
+  return &api;
+}
+
+void nccl_unique_id(uint8_t id[128]) {
+  NcclApi* api = load_nccl();
+  ncclUniqueId uid;
+  ncclResult_t r = api->GetUniqueId(&uid);
+  if (r != ncclSuccess) throw CudaError(6, "ncclGetUniqueId failed");
+  std::memcpy(id, uid.internal, 128);
+}
+
+#define AO_NCCL(expr)                                                                                 \
+  do {                                                                                                \
+    ncclResult_t _r = (expr);                                                                         \
+    if (_r != ncclSuccess)                                                                            \
+      throw CudaError(6, std::string(#expr) + ": " +                                                 \
+                             (nccl_->GetErrorString ? nccl_->GetErrorString(_r) : "nccl error"));     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, double alpha, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = y[i] + alpha * x[i];
+}
+
+// dense Khatri-Rao: out(a + rows_a*b, r) = Fa(a,r) * Fb(b,r); rows a >= valid_a are zero
+__global__ void kr_dense_kernel(double* __restrict__ out, const double* __restrict__ Fa, long long rows_a,
+                                long long valid_a, long long lda, const double* __restrict__ Fb, long long rows_b,
+                                long long ldb, int R) {
+  const long long rows = rows_a * rows_b, n = rows * R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / rows, row = idx % rows;
+    const long long a = row % rows_a, b = row / rows_a;
+    out[idx] = (a < valid_a) ? Fa[r * lda + a] * Fb[r * ldb + b] : 0.0;
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// counter-based N(0,1): hash(seed, global element index) -> Box-Muller
+__device__ __forceinline__ double normal_at(uint64_t seed, uint64_t idx) {
+  const uint64_t h1 = splitmix64(seed ^ (idx * 0xD1342543DE82EF95ull));
+  const uint64_t h2 = splitmix64(h1 ^ 0xA5A5A5A5A5A5A5A5ull);
+  const double u1 = ((double)(h1 >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+  const double u2 = (double)(h2 >> 11) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+struct GenArgs {
+  int order, R;
+  long long dims[8];        // local dims
+  long long full_last;      // unsharded extent of the last mode
+  long long shard_offset;
+  long long ld0;
+  const double* fac[8];     // device factor matrices (full rows), leading dimension = rows
+  long long fld[8];
+};
+
+// mode 0: sums[0] += x0^2, sums[1] += n^2 ; mode 1: x = x0 + sigma*n, sums[2] += x^2 ; mode 2: x *= scale
+__global__ void gen_cp_kernel(GenArgs g, double* __restrict__ X, uint64_t seed, int pass, double sigma, double scale,
+                              double* __restrict__ sums) {
+  __shared__ double red[32];
+  long long n = 1;
+  for (int d = 0; d < g.order; ++d) n *= g.dims[d];
+  double s0 = 0.0, s1 = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long rem = idx, sub[8];
+    for (int d = 0; d < g.order; ++d) {
+      sub[d] = rem % g.dims[d];
+      rem /= g.dims[d];
+    }
+    long long addr = sub[0], mult = g.ld0, gidx = sub[0], gmult = g.dims[0];
+    for (int d = 1; d < g.order; ++d) {
+      addr += sub[d] * mult;
+      mult *= g.dims[d];
+      const long long gs = (d == g.order - 1) ? sub[d] + g.shard_offset : sub[d];
+      gidx += gs * gmult;
+      gmult *= (d == g.order - 1) ? g.full_last : g.dims[d];
+    }
+    if (pass == 2) {
+      X[addr] *= scale;
+      continue;
+    }
+    double x0 = 0.0;
+    for (int r = 0; r < g.R; ++r) {
+      double t = 1.0;
+      for (int d = 0; d < g.order; ++d) {
+        const long long row = (d == g.order - 1) ? sub[d] + g.shard_offset : sub[d];
+        t *= g.fac[d][(long long)r * g.fld[d] + row];
+      }
+      x0 += t;
+    }
+    const double nz = normal_at(seed, (uint64_t)gidx);
+    if (pass == 0) {
+      s0 = fma(x0, x0, s0);
+      s1 = fma(nz, nz, s1);
+    } else {
+      const double x = x0 + sigma * nz;
+      X[addr] = x;
+      s0 = fma(x, x, s0);
+    }
+  }
+  if (pass == 2) return;
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    if (pass == 0) {
+      atomicAdd(&sums[0], s0);
+      atomicAdd(&sums[1], s1);
+    } else {
+      atomicAdd(&sums[2], s0);
+    }
+  }
+}
+
+double now_s() {
+  using namespace std::chrono;
+  return duration_cast<duration<double>>(steady_clock::now().time_since_epoch()).count();
+}
+
+void dev_alloc(DevMat& m, int64_t rows, int64_t cols) {
+  m.rows = rows;
+  m.cols = cols;
+  if (rows * cols > 0) {
+    AO_CUDA(cudaMalloc(&m.p, m.bytes()));
+    AO_CUDA(cudaMemset(m.p, 0, m.bytes()));
+    // the engine stream is non-blocking: legacy-stream memsets must have landed before it touches the buffer
+    AO_CUDA(cudaStreamSynchronize(0));
+  }
+}
+void dev_free(DevMat& m) {
+  if (m.p) cudaFree(m.p);
+  m.p = nullptr;
+}
+
+bool constraint_supported(int kind) {
+  switch (kind) {
+    case AOADMM_CON_NONE:
+    case AOADMM_CON_NONNEG:
+    case AOADMM_CON_BOX:
+    case AOADMM_CON_SIMPLEX_COL:
+    case AOADMM_CON_SIMPLEX_ROW:
+    case AOADMM_CON_NONDECREASING:
+    case AOADMM_CON_NONINCREASING:
+    case AOADMM_CON_UNIMODAL:
+    case AOADMM_CON_L1_BALL:
+    case AOADMM_CON_L2_BALL:
+    case AOADMM_CON_NONNEG_L2_BALL:
+    case AOADMM_CON_NONNEG_L2_SPHERE:
+    case AOADMM_CON_L1_REG:
+    case AOADMM_CON_L0_REG:
+    case AOADMM_CON_L2_REG:
+    case AOADMM_CON_RIDGE:
+    case AOADMM_CON_GL_SMOOTH:
+    case AOADMM_CON_TV: return true;
+    default: return false;
+  }
+}
+
+}  // namespace
+
+struct Engine::ObjTerms {
+  struct PerObject {
+    int idx_dot = -1, idx_had = -1;
+  };
+  struct PerMode {
+    int idx_norm2 = -1, idx_diffZ = -1, idx_diffD = -1, idx_reg = -1;
+  };
+  std::vector<PerObject> obj;
+  std::vector<PerMode> mode;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------------
+Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
+  if (prob == nullptr) throw CudaError(1, "problem is NULL");
+  if (dist != nullptr) {
+    rank_ = dist->rank;
+    world_ = dist->world_size;
+    device_ = dist->device;
+    if (world_ < 1 || rank_ < 0 || rank_ >= world_) throw CudaError(1, "invalid rank/world_size");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(8, "no CUDA device available");
+  if (device_ >= ndev) throw CudaError(1, "device ordinal out of range");
+  AO_CUDA(cudaSetDevice(device_));
+  AO_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+
+  nb_modes_ = prob->nb_modes;
+  n_objects_ = prob->n_objects;
+  n_couplings_ = prob->n_couplings;
+  if (nb_modes_ <= 0 || n_objects_ <= 0) throw CudaError(1, "empty problem");
+  has_ridge_ = prob->ridge != nullptr;
+  coupling_type_.assign(prob->coupling_type, prob->coupling_type + n_couplings_);
+  for (int c = 0; c < n_couplings_; ++c)
+    if (coupling_type_[c] != 0)
+      throw CudaError(2, "coupling type " + std::to_string(coupling_type_[c]) + " is not supported by this build");
+
+  modes_.resize(nb_modes_);
+  for (int i = 0; i < nb_modes_; ++i) {
+    ModeState& m = modes_[i];
+    m.id = i + 1;
+    m.rows = prob->mode_rows[i];
+    m.R = prob->mode_rank[i];
+    m.coupling = prob->lin_coupled_modes[i];
+    m.constrained = prob->constrained_modes[i] != 0;
+    m.con = prob->constraints[i];
+    if (!m.constrained) m.con.kind = AOADMM_CON_NONE;
+    m.ridge = has_ridge_ ? prob->ridge[i] : 0.0;
+    if (m.coupling < 0 || m.coupling > n_couplings_) throw CudaError(1, "lin_coupled_modes out of range");
+    if (m.constrained && !constraint_supported(m.con.kind))
+      throw CudaError(2, "constraint kind " + std::to_string(m.con.kind) + " of mode " + std::to_string(m.id) +
+                             " is not supported on device");
+    if (m.R <= 0 || m.R > 256) throw CudaError(1, "rank must be in 1..256");
+    if (prob->n_slices != nullptr && prob->n_slices[i] > 0) throw CudaError(2, "PARAFAC2 objects are not supported by this build");
+  }
+
+  objects_.resize(n_objects_);
+  for (int p = 0; p < n_objects_; ++p) {
+    const aoadmm_object& src = prob->objects[p];
+    ObjectState& o = objects_[p];
+    o.model = src.model;
+    o.order = src.order;
+    if (o.model != AOADMM_MODEL_CP) throw CudaError(2, "PARAFAC2 objects are not supported by this build");
+    if (o.order < 2 || o.order > 8) throw CudaError(1, "object order must be in 2..8");
+    o.modes.assign(src.modes, src.modes + o.order);
+    o.weight = src.weight;
+    o.znorm = src.znorm_const;
+    int R = 0;
+    for (int d = 0; d < o.order; ++d) {
+      const int mid = o.modes[d];
+      if (mid < 1 || mid > nb_modes_) throw CudaError(1, "mode id out of range");
+      ModeState& m = mode(mid);
+      if (m.p != -1) throw CudaError(1, "mode " + std::to_string(mid) + " belongs to two objects");
+      m.p = p;
+      m.pos = d;
+      if (d == 0) R = m.R;
+      if (m.R != R) throw CudaError(1, "all modes of a CP object need the same rank");
+      o.dims.push_back(m.rows);
+    }
+    o.last_full = o.dims.back();
+    o.sharded = (world_ > 1 && o.order >= 3);
+    if (o.sharded) {
+      o.shard_offset = src.shard_offset;
+      o.shard_extent = src.shard_extent;
+      if (o.shard_offset < 0 || o.shard_extent < 0 || o.shard_offset + o.shard_extent > o.last_full)
+        throw CudaError(1, "invalid shard range");
+    } else {
+      o.shard_offset = 0;
+      o.shard_extent = o.last_full;
+    }
+    o.dims.back() = o.shard_extent;
+    o.ld0 = round_up(o.dims[0], 2);
+    size_t slab = 1;
+    for (int d = 1; d < o.order; ++d) slab *= (size_t)o.dims[d];
+    const size_t bytes = std::max<size_t>((size_t)o.ld0 * slab * sizeof(double), 256);
+    AO_CUDA(cudaMalloc(&o.data, bytes));
+    if (o.ld0 != o.dims[0] || src.data == nullptr) AO_CUDA(cudaMemset(o.data, 0, bytes));
+    if (src.data != nullptr && slab > 0)
+      AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
+                           cudaMemcpyHostToDevice));
+    AO_CUDA(cudaDeviceSynchronize());  // pageable H2D copies return before the DMA has finished
+  }
+  for (auto& m : modes_)
+    if (m.p < 0) throw CudaError(1, "mode " + std::to_string(m.id) + " belongs to no object");
+
+  // couplings: exact coupling needs identical shapes
+  delta_.resize(n_couplings_);
+  for (int c = 1; c <= n_couplings_; ++c) {
+    int first = -1;
+    for (auto& m : modes_)
+      if (m.coupling == c) {
+        if (first < 0) first = m.id;
+        if (m.rows != mode(first).rows || m.R != mode(first).R)
+          throw CudaError(1, "exactly coupled modes need identical factor shapes");
+      }
+    if (first < 0) throw CudaError(1, "coupling id without modes");
+    dev_alloc(delta_[c - 1], mode(first).rows, mode(first).R);
+  }
+
+  // per-mode buffers
+  size_t gram_ws = 0, admm_ws = 0, prox_bytes = 0;
+  for (auto& m : modes_) {
+    dev_alloc(m.fac, m.rows, m.R);
+    if (m.constrained) {
+      dev_alloc(m.Z, m.rows, m.R);
+      dev_alloc(m.muZ, m.rows, m.R);
+      if (!prox_is_elementwise(m.con.kind)) {
+        dev_alloc(m.Znew, m.rows, m.R);
+        dev_alloc(m.V, m.rows, m.R);
+        prox_bytes = std::max(prox_bytes, prox_scratch_bytes(m.con.kind, m.rows, m.R));
+      }
+    }
+    if (m.coupling != 0) dev_alloc(m.muD, m.rows, m.R);
+    dev_alloc(m.A, m.rows, m.R);
+    dev_alloc(m.Alast, m.rows, m.R);
+    dev_alloc(m.C, m.R, m.R);
+    dev_alloc(m.B, m.R, m.R);
+    dev_alloc(m.L, m.R, m.R);
+    dev_alloc(m.GtG, m.R, m.R);
+    AO_CUDA(cudaMalloc(&m.invdiag, sizeof(double) * m.R));
+    AO_CUDA(cudaMalloc(&m.rho, sizeof(double)));
+    AO_CUDA(cudaMemset(m.rho, 0, sizeof(double)));
+    gram_ws = std::max(gram_ws, gram_ws_doubles(m.rows, m.R));
+    admm_ws = std::max(admm_ws, admm_ws_doubles(m.rows, m.R, kMaxGroup));
+  }
+  AO_CUDA(cudaMalloc(&gram_ws_, gram_ws * sizeof(double)));
+  AO_CUDA(cudaMalloc(&admm_partials_, admm_ws * sizeof(double)));
+  AO_CUDA(cudaMalloc(&admm_sums_, (6 * kMaxGroup + 1) * sizeof(double)));
+  AO_CUDA(cudaMemset(admm_sums_, 0, (6 * kMaxGroup + 1) * sizeof(double)));
+  AO_CUDA(cudaMalloc(&admm_counter_, sizeof(unsigned)));
+  AO_CUDA(cudaMemset(admm_counter_, 0, sizeof(unsigned)));
+  if (prox_bytes > 0) AO_CUDA(cudaMalloc(&prox_scratch_, prox_bytes));
+
+  // control blocks: one per mode (a coupled group uses the block of its first mode)
+  n_ctl_ = nb_modes_;
+  AO_CUDA(cudaMalloc(&ctl_dev_, sizeof(InnerCtl) * n_ctl_));
+  AO_CUDA(cudaMemset(ctl_dev_, 0, sizeof(InnerCtl) * n_ctl_));
+  AO_CUDA(cudaMallocHost(&ctl_host_, sizeof(InnerCtl) * n_ctl_));
+  std::memset(ctl_host_, 0, sizeof(InnerCtl) * n_ctl_);
+  for (auto& m : modes_) {
+    int owner = m.id;
+    if (m.coupling != 0)
+      for (auto& q : modes_)
+        if (q.coupling == m.coupling) {
+          owner = q.id;
+          break;
+        }
+    m.ctl_index = owner - 1;
+    m.ctl = ctl_dev_ + m.ctl_index;
+  }
+
+  // views + workspaces
+  size_t ws_bytes = 0, kr_doubles = 0;
+  size_t cp0 = 0;
+  for (auto& o : objects_) {
+    build_views(o);
+    for (auto& v : o.views) {
+      ws_bytes = std::max(ws_bytes, mttkrp_workspace_bytes(v.t, mode(o.modes[0]).R));
+      if (v.f0_modes.size() >= 2) kr_doubles = std::max(kr_doubles, (size_t)v.f0_rows * mode(o.modes[0]).R);
+      if (v.f1_modes.size() >= 2) kr_doubles = std::max(kr_doubles, (size_t)v.f1_rows * mode(o.modes[0]).R);
+    }
+    cp0 = std::max(cp0, (size_t)mode(o.modes[0]).rows * mode(o.modes[0]).R);
+  }
+  mws_.ws_bytes = ws_bytes;
+  AO_CUDA(cudaMalloc(&mws_.ws, ws_bytes));
+  if (kr_doubles > 0) {
+    krtmp_doubles_ = kr_doubles;
+    AO_CUDA(cudaMalloc(&krtmp_[0], kr_doubles * sizeof(double)));
+    AO_CUDA(cudaMalloc(&krtmp_[1], kr_doubles * sizeof(double)));
+  }
+  AO_CUDA(cudaMalloc(&cp0_tmp_, (cp0 + 4 * 256 * 256 + 512) * sizeof(double)));
+  AO_CUDA(cudaDeviceSynchronize());
+
+  // static sweep order -> last updated mode of every object (cmtf_fun_AOADMM.m:121-123)
+  {
+    std::set<int> cset;
+    for (auto& m : modes_) cset.insert(m.coupling);
+    for (int cid : cset) {
+      std::set<int> ps;
+      for (auto& m : modes_)
+        if (m.coupling == cid) ps.insert(m.p);
+      for (int p : ps)
+        for (auto& m : modes_)
+          if (m.coupling == cid && m.p == p) objects_[p].last_m = m.id;
+    }
+  }
+  build_objective_jobs();
+
+  if (world_ > 1) {
+    nccl_ = load_nccl();
+    ncclUniqueId uid;
+    std::memcpy(uid.internal, dist->nccl_unique_id, 128);
+    ncclComm_t comm;
+    AO_NCCL(nccl_->CommInitRank(&comm, world_, uid, rank_));
+    comm_ = comm;
+  }
+  AO_CUDA(cudaDeviceSynchronize());
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (st_) cudaStreamSynchronize(st_);
+  if (comm_ && nccl_) nccl_->CommDestroy(static_cast<ncclComm_t>(comm_));
+  for (auto& m : modes_) {
+    for (DevMat* d : {&m.fac, &m.Z, &m.muZ, &m.muD, &m.A, &m.Alast, &m.C, &m.B, &m.L, &m.GtG, &m.Znew, &m.V}) dev_free(*d);
+    if (m.invdiag) cudaFree(m.invdiag);
+    if (m.rho) cudaFree(m.rho);
+  }
+  for (auto& o : objects_) {
+    if (o.data) cudaFree(o.data);
+    for (auto& v : o.views) {
+      if (v.f0_own) packed_factor_free(v.f0);
+      if (v.f1_own) packed_factor_free(v.f1);
+    }
+  }
+  for (auto& d : delta_) dev_free(d);
+  for (void* p : {(void*)mws_.ws, (void*)gram_ws_, (void*)admm_partials_, (void*)admm_sums_, (void*)admm_counter_,
+                  prox_scratch_, (void*)krtmp_[0], (void*)krtmp_[1], (void*)ctl_dev_, (void*)jobs_dev_,
+                  (void*)red_dev_, (void*)cp0_tmp_})
+    if (p) cudaFree(p);
+  if (ctl_host_) cudaFreeHost(ctl_host_);
+  if (red_host_) cudaFreeHost(red_host_);
+  if (run_ev_[0]) cudaEventDestroy(run_ev_[0]);
+  if (run_ev_[1]) cudaEventDestroy(run_ev_[1]);
+  for (auto& e : ev_pool_) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  if (st_) cudaStreamDestroy(st_);
+}
+
+void Engine::build_views(ObjectState& o) {
+  const int N = o.order;
+  const int R = mode(o.modes[0]).R;
+  o.views.resize(N);
+  auto prod = [&](int a, int b) {  // product of local dims[a..b]
+    int64_t v = 1;
+    for (int d = a; d <= b; ++d) v *= o.dims[d];
+    return v;
+  };
+  for (int n = 0; n < N; ++n) {
+    View3& v = o.views[n];
+    int64_t I, J, K, ldI;
+    if (N == 2) {
+      I = o.dims[0];
+      J = o.dims[1];
+      K = 1;
+      ldI = o.ld0;
+      v.kernel_pos = (n == 0) ? 0 : 1;
+      v.f0_modes = {o.modes[n == 0 ? 1 : 0]};
+      v.f1_modes = {};
+    } else if (n == 0 || n == N - 1) {
+      I = o.dims[0];
+      J = prod(1, N - 2);
+      K = o.dims[N - 1];
+      ldI = o.ld0;
+      v.kernel_pos = (n == 0) ? 0 : 2;
+      std::vector<int> mid(o.modes.begin() + 1, o.modes.begin() + N - 1);
+      if (n == 0) {
+        v.f0_modes = mid;
+        v.f1_modes = {o.modes[N - 1]};
+      } else {
+        v.f0_modes = {o.modes[0]};
+        v.f1_modes = mid;
+      }
+    } else {
+      I = (n == 1) ? o.dims[0] : o.ld0 * prod(1, n - 1);
+      ldI = (n == 1) ? o.ld0 : I;
+      J = o.dims[n];
+      K = prod(n + 1, N - 1);
+      v.kernel_pos = 1;
+      v.f0_modes.assign(o.modes.begin(), o.modes.begin() + n);
+      v.f1_modes.assign(o.modes.begin() + n + 1, o.modes.end());
+    }
+    make_tensor3(v.t, o.data, I, J, K, ldI);
+    auto rows_of = [&](const std::vector<int>& ms, bool padded_first) {
+      int64_t r = 1;
+      for (size_t q = 0; q < ms.size(); ++q) {
+        const ModeState& mm = mode(ms[q]);
+        int64_t rr = o.dims[mm.pos];
+        if (q == 0 && padded_first && mm.pos == 0 && ms.size() > 1) rr = o.ld0;
+        r *= rr;
+      }
+      return r;
+    };
+    v.f0_rows = rows_of(v.f0_modes, true);
+    v.f1_rows = rows_of(v.f1_modes, false);
+    packed_factor_alloc(v.f0, v.f0_rows, R);
+    v.f0_own = true;
+    packed_factor_alloc(v.f1, v.f1_rows, R);
+    v.f1_own = true;
+    if (v.f1_modes.empty()) {
+      packed_factor_pack(v.f1, nullptr, 1, st_, nullptr);  // ones row (matrices: K = 1)
+      ++launches_;
+    }
+    const bool last = (N >= 3 && n == N - 1);
+    v.out_rows = last ? o.shard_extent : mode(o.modes[n]).rows;
+    v.out_offset = last ? o.shard_offset : 0;
+    v.needs_allreduce = o.sharded;
+  }
+}
+
+// pack operand `which` (0/1) of a view from the current factor matrices
+void Engine::pack_operand(View3& v, int which) {
+  const std::vector<int>& ms = which == 0 ? v.f0_modes : v.f1_modes;
+  PackedFactor& pf = which == 0 ? v.f0 : v.f1;
+  if (ms.empty()) return;  // ones, packed once
+  ObjectState& o = objects_[mode(ms[0]).p];
+  auto fac_ptr = [&](const ModeState& mm) {  // local slice of the (possibly sharded) last mode
+    return (mm.pos == o.order - 1) ? mm.fac.p + o.shard_offset : mm.fac.p;
+  };
+  auto local_rows = [&](const ModeState& mm) { return o.dims[mm.pos]; };
+  if (ms.size() == 1) {
+    const ModeState& mm = mode(ms[0]);
+    packed_factor_pack(pf, fac_ptr(mm), mm.rows, st_, nullptr);
+    ++launches_;
+    return;
+  }
+  // Khatri-Rao chain, first listed mode varies fastest
+  const ModeState& m0 = mode(ms[0]);
+  const bool pad0 = (which == 0 && m0.pos == 0);
+  int64_t rows_a = pad0 ? o.ld0 : local_rows(m0);
+  int64_t valid_a = local_rows(m0);
+  const double* Fa = fac_ptr(m0);
+  int64_t lda = m0.rows;
+  const int R = m0.R;
+  for (size_t q = 1; q < ms.size(); ++q) {
+    const ModeState& mb = mode(ms[q]);
+    const bool final_step = (q + 1 == ms.size());
+    if (final_step && q == 1 && !pad0) {
+      packed_factor_pack_kr(pf, Fa, rows_a, lda, fac_ptr(mb), local_rows(mb), mb.rows, st_, nullptr);
+      ++launches_;
+      return;
+    }
+    double* dst = krtmp_[(q - 1) & 1];
+    const int64_t rows_b = local_rows(mb);
+    const long long n = rows_a * rows_b * R;
+    const unsigned ctas = (unsigned)std::min<long long>(ceil_div(n, 256), 148 * 8);
+    kr_dense_kernel<<<ctas, 256, 0, st_>>>(dst, Fa, rows_a, valid_a, lda, fac_ptr(mb), rows_b, mb.rows, R);
+    AO_CHECK_LAUNCH();
+    ++launches_;
+    Fa = dst;
+    rows_a = rows_a * rows_b;
+    valid_a = rows_a;
+    lda = rows_a;
+  }
+  packed_factor_pack(pf, Fa, lda, st_, nullptr);
+  ++launches_;
+}
+
+void Engine::allreduce(double* buf, size_t count) {
+  if (world_ <= 1) return;
+  AO_NCCL(nccl_->AllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm_), st_));
+}
+
+void Engine::compute_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout) {
+  View3& v = o.views[pos];
+  const int R = mode(o.modes[0]).R;
+  pack_operand(v, 0);
+  pack_operand(v, 1);
+  phase_begin(o.order >= 3 ? 0 : 1);
+  const bool last_sharded = o.sharded && o.order >= 3 && pos == o.order - 1;
+  if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr);
+  if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
+  phase_end();
+}
+
+void Engine::refresh_gram(ModeState& m) {
+  launches_ += gram(m.fac.p, m.rows, m.rows, m.R, m.GtG.p, gram_ws_, st_, nullptr);
+}
+
+void Engine::precompute_mode(ModeState& m, int n_rho_terms, bool do_chol) {
+  ObjectState& o = objects_[m.p];
+  compute_mttkrp(o, m.pos, o.weight, m.A.p, m.rows);  // A{m} = w * mttkrp (:97, :108, :111)
+  PrepArgs a{};
+  a.nhad = 0;
+  for (int d = 0; d < o.order; ++d)
+    if (o.modes[d] != m.id) a.had[a.nhad++] = mode(o.modes[d]).GtG.p;  // :98-103, :109, :112
+  a.R = m.R;
+  a.weight = o.weight;
+  a.ridge = m.ridge;
+  a.bsum_half = opt_.bsum ? opt_.bsum_weight / 2.0 : 0.0;
+  a.n_rho_terms = n_rho_terms;
+  a.rho_scale = 1.0;
+  a.HHt = nullptr;
+  a.do_chol = do_chol ? 1 : 0;
+  a.C = m.C.p;
+  a.B = m.B.p;
+  a.L = m.L.p;
+  a.invdiag = m.invdiag;
+  a.rho = m.rho;
+  a.ctl = m.ctl;
+  launches_ += prep_system(a, st_, nullptr);
+  if (opt_.bsum) {  // :124-127 (last_mttkrp keeps the value before the BSUM term, :121)
+    AO_CUDA(cudaMemcpyAsync(m.Alast.p, m.A.p, m.A.bytes(), cudaMemcpyDeviceToDevice, st_));
+    const long long n = m.rows * m.R;
+    axpy_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), 148 * 8), 256, 0, st_>>>(m.A.p, m.fac.p,
+                                                                                           opt_.bsum_weight / 2.0, n);
+    AO_CHECK_LAUNCH();
+    ++launches_;
+  }
+}
+
+void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt) {
+  if ((int)group.size() > kMaxGroup) throw CudaError(2, "more than 8 modes in one coupling group");
+  AdmmGroup g{};
+  g.nmodes = (int)group.size();
+  g.Delta = Delta;
+  g.rows = group[0]->rows;
+  g.R = group[0]->R;
+  std::vector<int> deferred;
+  for (int i = 0; i < g.nmodes; ++i) {
+    ModeState& m = *group[i];
+    AdmmMode& am = g.m[i];
+    am.A = m.A.p;
+    am.L = m.L.p;
+    am.invdiag = m.invdiag;
+    am.rho = m.rho;
+    am.F = m.fac.p;
+    am.Z = m.Z.p;
+    am.muZ = m.muZ.p;
+    am.muD = m.muD.p;
+    am.ldA = m.rows;
+    am.ldF = m.rows;
+    am.constrained = m.constrained ? 1 : 0;
+    am.prox_kind = m.con.kind;
+    am.p0 = m.con.p0;
+    am.p1 = m.con.p1;
+    if (m.constrained && !prox_is_elementwise(m.con.kind)) deferred.push_back(i);
+  }
+  InnerCtl* ctl = group[0]->ctl;
+  InnerTol tol{opt.innerRelPrTol_coupl, opt.innerRelDualTol_coupl, opt.innerRelPrTol_constr, opt.innerRelDualTol_constr};
+  for (int it = 0; it < opt.MaxInnerIters; ++it) {
+    launches_ += admm_iteration(g, tol, ctl, admm_sums_, admm_partials_, admm_counter_, deferred.empty() ? 1 : 0, st_);
+    for (size_t d = 0; d < deferred.size(); ++d) {
+      ModeState& m = *group[deferred[d]];
+      launches_ += admm_form_prox_input(g, deferred[d], m.V.p, ctl, st_);
+      launches_ += prox_apply(m.con.kind, m.con.p0, m.con.p1, m.V.p, m.rows, m.Znew.p, m.rows, m.rows, m.R, m.rho, 0.0,
+                              prox_scratch_, st_, &ctl->done);
+      launches_ += admm_constraint_update(g, deferred[d], m.Znew.p, tol, ctl, admm_sums_, admm_partials_, admm_counter_,
+                                          (d + 1 == deferred.size()) ? 1 : 0, st_);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// objective (cmtf_fun_AOADMM.m:1213-1363)
+// ---------------------------------------------------------------------------------------------------
+void Engine::build_objective_jobs() {
+  terms_.reset(new ObjTerms());
+  terms_->obj.resize(n_objects_);
+  terms_->mode.resize(nb_modes_);
+  jobs_host_.clear();
+  auto add = [&](int kind, const double* a, const double* b, int64_t rows, int cols) {
+    RedJob j{};
+    j.kind = kind;
+    j.cols = cols;
+    j.rows = rows;
+    j.lda = rows;
+    j.ldb = rows;
+    j.a = a;
+    j.b = b;
+    jobs_host_.push_back(j);
+    return (int)jobs_host_.size() - 1;
+  };
+  for (int p = 0; p < n_objects_; ++p) {
+    ModeState& lm = mode(objects_[p].last_m);
+    // Alast holds last_mttkrp when BSUM is on; decided at run time by swapping the pointer (see eval_objective)
+    terms_->obj[p].idx_dot = add(RED_DOT, lm.A.p, lm.fac.p, lm.rows, lm.R);
+    terms_->obj[p].idx_had = add(RED_DOT, lm.C.p, lm.GtG.p, lm.R, lm.R);
+  }
+  for (int i = 0; i < nb_modes_; ++i) {
+    ModeState& m = modes_[i];
+    auto& t = terms_->mode[i];
+    t.idx_norm2 = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R);
+    if (m.constrained) t.idx_diffZ = add(RED_DIFF2, m.fac.p, m.Z.p, m.rows, m.R);
+    if (m.coupling != 0) t.idx_diffD = add(RED_DIFF2, m.fac.p, delta_[m.coupling - 1].p, m.rows, m.R);
+    if (m.constrained) {
+      switch (m.con.kind) {  // reg_func of constraints_to_prox.m:49,:53,:57,:61,:77,:81
+        case AOADMM_CON_L1_REG: t.idx_reg = add(RED_L1, m.fac.p, nullptr, m.rows, m.R); break;
+        case AOADMM_CON_L0_REG: t.idx_reg = add(RED_NNZ, m.fac.p, nullptr, m.rows, m.R); break;
+        case AOADMM_CON_L2_REG: t.idx_reg = add(RED_COLNORM, m.fac.p, nullptr, m.rows, m.R); break;
+        case AOADMM_CON_RIDGE: t.idx_reg = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R); break;
+        case AOADMM_CON_GL_SMOOTH: t.idx_reg = add(RED_GLQUAD, m.fac.p, nullptr, m.rows, m.R); break;
+        case AOADMM_CON_TV: t.idx_reg = add(RED_TVSUM, m.fac.p, nullptr, m.rows, m.R); break;
+        default: break;
+      }
+    }
+  }
+  const size_t nj = jobs_host_.size();
+  AO_CUDA(cudaMalloc(&jobs_dev_, sizeof(RedJob) * (nj + 8)));
+  AO_CUDA(cudaMemcpy(jobs_dev_, jobs_host_.data(), sizeof(RedJob) * nj, cudaMemcpyHostToDevice));
+  AO_CUDA(cudaMalloc(&red_dev_, sizeof(double) * (nj + 8)));
+  AO_CUDA(cudaMallocHost(&red_host_, sizeof(double) * (nj + 8)));
+}
+
+void Engine::eval_objective(bool first, double f[4]) {
+  const int nj = (int)jobs_host_.size();
+  std::vector<double> f_obj(n_objects_, 0.0);
+  if (first) {
+    // cp_func.m:47-56 / pca_func.m:29-40: f = w*(||X||^2 - 2*sum(A1 .* mttkrp(X,A,1)) + sum(prod of all Grams))
+    for (int p = 0; p < n_objects_; ++p) {
+      ObjectState& o = objects_[p];
+      ModeState& m0 = mode(o.modes[0]);
+      double* M = cp0_tmp_;
+      double* scr = cp0_tmp_ + (size_t)m0.rows * m0.R;  // C | B | L | invdiag | rho
+      const size_t RR = (size_t)256 * 256;
+      compute_mttkrp(o, 0, 1.0, M, m0.rows);
+      PrepArgs a{};
+      a.nhad = 0;
+      for (int d = 0; d < o.order; ++d) a.had[a.nhad++] = mode(o.modes[d]).GtG.p;
+      a.R = m0.R;
+      a.weight = 1.0;
+      a.rho_scale = 1.0;
+      a.do_chol = 0;
+      a.C = scr;
+      a.B = scr + RR;
+      a.L = scr + 2 * RR;
+      a.invdiag = scr + 3 * RR;
+      a.rho = scr + 3 * RR + 256;
+      a.ctl = nullptr;
+      launches_ += prep_system(a, st_, nullptr);
+      RedJob jb[2]{};
+      jb[0].kind = RED_DOT;
+      jb[0].cols = m0.R;
+      jb[0].rows = jb[0].lda = jb[0].ldb = m0.rows;
+      jb[0].a = M;
+      jb[0].b = m0.fac.p;
+      jb[1].kind = RED_SUM;  // f_3 = sum(W(:)) (cp_func.m:52)
+      jb[1].cols = 1;
+      jb[1].rows = jb[1].lda = jb[1].ldb = (long long)m0.R * m0.R;
+      jb[1].a = scr;
+      jb[1].b = nullptr;
+      AO_CUDA(cudaMemcpyAsync(jobs_dev_ + nj, jb, sizeof(jb), cudaMemcpyHostToDevice, st_));
+      launches_ += reduce_jobs(jobs_dev_ + nj, 2, red_dev_ + nj, st_, nullptr);
+      double r2[2];
+      AO_CUDA(cudaMemcpyAsync(r2, red_dev_ + nj, sizeof(r2), cudaMemcpyDeviceToHost, st_));
+      AO_CUDA(cudaStreamSynchronize(st_));
+      f_obj[p] = o.weight * (o.znorm - 2.0 * r2[0] + r2[1]);
+    }
+  }
+  launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, st_, nullptr);
+  AO_CUDA(cudaMemcpyAsync(red_host_, red_dev_, sizeof(double) * nj, cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaMemcpyAsync(ctl_host_, ctl_dev_, sizeof(InnerCtl) * n_ctl_, cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+  phase_collect();
+  const double* r = red_host_;
+  double f_tensors = 0.0;
+  for (int p = 0; p < n_objects_; ++p) {
+    if (!first) {
+      ObjectState& o = objects_[p];
+      // f_2 = sum(last_mttkrp .* fac) with last_mttkrp = A/w (:121, :1236-1237)
+      const double f2 = r[terms_->obj[p].idx_dot] / o.weight;
+      const double f3 = r[terms_->obj[p].idx_had];
+      f_obj[p] = o.weight * (o.znorm - 2.0 * f2 + f3);
+    }
+    f_tensors += f_obj[p];
+  }
+  for (int i = 0; i < nb_modes_; ++i) {  // :1272-1288 regularisers
+    const ModeState& m = modes_[i];
+    const int ir = terms_->mode[i].idx_reg;
+    if (ir >= 0) f_tensors += m.con.p0 * r[ir];
+  }
+  if (has_ridge_)  // :1290-1300
+    for (int i = 0; i < nb_modes_; ++i) f_tensors += modes_[i].ridge * r[terms_->mode[i].idx_norm2];
+  double f_coupl = 0.0;
+  int nz = 0;
+  for (int c = 1; c <= n_couplings_; ++c) {  // :1303-1329
+    double cp = 0.0;
+    for (int i = 0; i < nb_modes_; ++i)
+      if (modes_[i].coupling == c)
+        cp += std::sqrt(r[terms_->mode[i].idx_diffD]) / std::sqrt(r[terms_->mode[i].idx_norm2]);
+    f_coupl += cp;
+    if (cp != 0.0) ++nz;
+  }
+  if (f_coupl > 0.0) f_coupl /= (double)nz;
+  double f_con = 0.0;
+  nz = 0;
+  for (int i = 0; i < nb_modes_; ++i) {  // :1332-1348
+    if (!modes_[i].constrained) continue;
+    const double v = std::sqrt(r[terms_->mode[i].idx_diffZ]) / std::sqrt(r[terms_->mode[i].idx_norm2]);
+    f_con += v;
+    if (v != 0.0) ++nz;
+  }
+  if (f_con > 0.0) f_con /= (double)nz;
+  f[0] = f_tensors;
+  f[1] = f_coupl;
+  f[2] = f_con;
+  f[3] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// state exchange
+// ---------------------------------------------------------------------------------------------------
+static DevMat* field_ptr(std::vector<ModeState>& modes, std::vector<DevMat>& delta, int field, int index) {
+  switch (field) {
+    case AOADMM_FIELD_FAC: return &modes.at(index - 1).fac;
+    case AOADMM_FIELD_CONSTRAINT_FAC: return &modes.at(index - 1).Z;
+    case AOADMM_FIELD_CONSTRAINT_DUAL: return &modes.at(index - 1).muZ;
+    case AOADMM_FIELD_COUPLING_DUAL: return &modes.at(index - 1).muD;
+    case AOADMM_FIELD_COUPLING_FAC: return &delta.at(index - 1);
+    default: return nullptr;
+  }
+}
+
+void Engine::set_state(int field, int index, int slice, const double* data, int64_t rows, int64_t cols) {
+  (void)slice;
+  AO_CUDA(cudaSetDevice(device_));
+  if (data == nullptr) throw CudaError(1, "set_state: NULL data");
+  DevMat* d = nullptr;
+  try {
+    d = field_ptr(modes_, delta_, field, index);
+  } catch (const std::out_of_range&) {
+    throw CudaError(1, "set_state: index out of range");
+  }
+  if (d == nullptr) throw CudaError(2, "set_state: field not supported by this build");
+  if (d->p == nullptr) throw CudaError(1, "set_state: field " + std::to_string(field) + " does not exist for index " + std::to_string(index));
+  if (d->rows != rows || d->cols != cols)
+    throw CudaError(1, "set_state: shape mismatch for field " + std::to_string(field) + " index " +
+                           std::to_string(index) + ": expected " + std::to_string(d->rows) + "x" +
+                           std::to_string(d->cols));
+  AO_CUDA(cudaMemcpyAsync(d->p, data, d->bytes(), cudaMemcpyHostToDevice, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+}
+
+void Engine::get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols) {
+  (void)slice;
+  AO_CUDA(cudaSetDevice(device_));
+  if (data == nullptr) throw CudaError(1, "get_state: NULL data");
+  DevMat* d = nullptr;
+  try {
+    d = field_ptr(modes_, delta_, field, index);
+  } catch (const std::out_of_range&) {
+    throw CudaError(1, "get_state: index out of range");
+  }
+  if (d == nullptr) throw CudaError(2, "get_state: field not supported by this build");
+  if (d->p == nullptr) throw CudaError(1, "get_state: field does not exist for this index");
+  if (d->rows != rows || d->cols != cols) throw CudaError(1, "get_state: shape mismatch");
+  AO_CUDA(cudaMemcpyAsync(data, d->p, d->bytes(), cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// timing helpers
+// ---------------------------------------------------------------------------------------------------
+void Engine::phase_begin(int phase) {
+  if (ev_used_ == ev_pool_.size()) {
+    cudaEvent_t a, b;
+    AO_CUDA(cudaEventCreate(&a));
+    AO_CUDA(cudaEventCreate(&b));
+    ev_pool_.push_back({a, b});
+    ev_phase_.push_back(0);
+  }
+  ev_phase_[ev_used_] = phase;
+  AO_CUDA(cudaEventRecord(ev_pool_[ev_used_].first, st_));
+}
+void Engine::phase_end() {
+  AO_CUDA(cudaEventRecord(ev_pool_[ev_used_].second, st_));
+  ++ev_used_;
+}
+void Engine::phase_collect() {  // call only after a stream synchronisation
+  for (size_t i = 0; i < ev_used_; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_pool_[i].first, ev_pool_[i].second) == cudaSuccess) phase_ms_[ev_phase_[i]] += ms;
+  }
+  ev_used_ = 0;
+}
+void Engine::phase_ms(double ms[3]) {
+  ms[0] = phase_ms_[0];
+  ms[1] = phase_ms_[1];
+  ms[2] = phase_ms_[2];
+}
+
+void Engine::check_errors(aoadmm_out* out) {
+  for (int i = 0; i < n_ctl_; ++i) {
+    if (ctl_host_[i].err != 0) {
+      if (out) out->error_mode = i + 1;
+      const int code = ctl_host_[i].err;
+      throw CudaError(code, code == 3 ? "system matrix of mode " + std::to_string(i + 1) +
+                                            " is not positive definite (chol would fail, cmtf_fun_AOADMM.m:142)"
+                                      : "non-finite residual in the ADMM loop of mode " + std::to_string(i + 1));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------------
+static bool stop_one(double f, double f_old, double abs_tol, double rel_tol) {  // evaluate_stopping_conditions.m:8-15
+  const double rel = (f_old > 0.0) ? std::fabs(f_old - f) / f_old : std::fabs(f_old - f);
+  return (f < abs_tol) || (rel < rel_tol);
+}
+
+void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
+  if (opt == nullptr || out == nullptr) throw CudaError(1, "run: NULL options/out");
+  AO_CUDA(cudaSetDevice(device_));
+  opt_ = *opt;
+  if (opt_.MaxInnerIters < 1) throw CudaError(1, "MaxInnerIters must be >= 1");
+  out->error_mode = 0;
+  if (run_ev_[0] == nullptr) {
+    AO_CUDA(cudaEventCreate(&run_ev_[0]));
+    AO_CUDA(cudaEventCreate(&run_ev_[1]));
+  }
+  AO_CUDA(cudaEventRecord(run_ev_[0], st_));
+  AO_CUDA(cudaMemsetAsync(ctl_dev_, 0, sizeof(InnerCtl) * n_ctl_, st_));
+  const double t_start = now_s();
+
+  // BSUM: the objective dot product uses last_mttkrp = A before the BSUM term (:121)
+  {
+    bool changed = false;
+    for (int p = 0; p < n_objects_; ++p) {
+      ModeState& lm = mode(objects_[p].last_m);
+      const double* want = opt_.bsum ? lm.Alast.p : lm.A.p;
+      RedJob& j = jobs_host_[terms_->obj[p].idx_dot];
+      if (j.a != want) {
+        j.a = want;
+        changed = true;
+      }
+    }
+    if (changed)
+      AO_CUDA(cudaMemcpyAsync(jobs_dev_, jobs_host_.data(), sizeof(RedJob) * jobs_host_.size(), cudaMemcpyHostToDevice, st_));
+  }
+
+  for (auto& m : modes_) refresh_gram(m);  // :62-81
+  double f[4];
+  eval_objective(true, f);                  // :32
+  if (out->func_val_conv) out->func_val_conv[0] = f[0];
+  if (out->func_coupl_conv) out->func_coupl_conv[0] = f[1];
+  if (out->func_constr_conv) out->func_constr_conv[0] = f[2];
+  if (out->func_PAR2_coupl) out->func_PAR2_coupl[0] = f[3];
+  if (out->time_at_it) out->time_at_it[0] = 0.0;
+
+  std::set<int> cset;
+  for (auto& m : modes_) cset.insert(m.coupling);
+  std::vector<int> inner_fixed(nb_modes_, 0);
+
+  int iter = 1;
+  bool stop = false;
+  while (iter <= opt_.MaxOuterIters && !stop) {
+    std::fill(inner_fixed.begin(), inner_fixed.end(), 0);
+    for (int coupl_id : cset) {                                      // :89
+      std::vector<ModeState*> cm;
+      std::set<int> ps;
+      for (auto& m : modes_)
+        if (m.coupling == coupl_id) {
+          cm.push_back(&m);
+          ps.insert(m.p);
+        }
+      for (int p : ps) {                                             // :91
+        for (ModeState* mp : cm) {                                   // :93
+          ModeState& m = *mp;
+          if (m.p != p) continue;
+          if (coupl_id == 0) {
+            if (!m.constrained) {
+              precompute_mode(m, 0, true);
+              launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :134
+              inner_fixed[m.id - 1] = 1;
+            } else {
+              precompute_mode(m, 1, true);                           // :141-142
+              std::vector<ModeState*> g1{&m};
+              run_admm(g1, nullptr, opt_);                           // :144
+            }
+            refresh_gram(m);                                         // :148
+          } else {
+            precompute_mode(m, 1 + (m.constrained ? 1 : 0), true);  // :269-273
+          }
+        }
+      }
+      if (coupl_id != 0) {                                           // :253
+        run_admm(cm, delta_[coupl_id - 1].p, opt_);                  // :277
+        for (ModeState* mp : cm) refresh_gram(*mp);                  // :393-403
+      }
+    }
+    const double f_old[4] = {f[0], f[1], f[2], f[3]};
+    eval_objective(false, f);                                        // :447 (synchronises)
+    check_errors(out);
+    if (out->func_val_conv) out->func_val_conv[iter] = f[0];
+    if (out->func_coupl_conv) out->func_coupl_conv[iter] = f[1];
+    if (out->func_constr_conv) out->func_constr_conv[iter] = f[2];
+    if (out->func_PAR2_coupl) out->func_PAR2_coupl[iter] = f[3];
+    if (out->time_at_it) out->time_at_it[iter] = now_s() - t_start;
+    if (out->inner_iters)
+      for (int i = 0; i < nb_modes_; ++i)
+        out->inner_iters[(size_t)(iter - 1) * nb_modes_ + i] =
+            inner_fixed[i] ? inner_fixed[i] : ctl_host_[modes_[i].ctl_index].iters;
+    stop = stop_one(f[0], f_old[0], opt_.AbsFuncTol, opt_.OuterRelTol) &&
+           stop_one(f[1], f_old[1], opt_.AbsFuncTol, opt_.OuterRelTol) &&
+           stop_one(f[2], f_old[2], opt_.AbsFuncTol, opt_.OuterRelTol) &&
+           stop_one(f[3], f_old[3], opt_.AbsFuncTol, opt_.OuterRelTol);   // evaluate_stopping_conditions.m:44
+    ++iter;
+  }
+  AO_CUDA(cudaEventRecord(run_ev_[1], st_));
+  AO_CUDA(cudaEventSynchronize(run_ev_[1]));
+  {
+    float ms = 0.f;
+    AO_CUDA(cudaEventElapsedTime(&ms, run_ev_[0], run_ev_[1]));
+    last_run_ms_ = ms;
+  }
+  out->f_tensors = f[0];
+  out->f_couplings = f[1];
+  out->f_constraints = f[2];
+  out->f_PAR2_couplings = f[3];
+  out->OuterIterations = iter - 1;
+  if (iter > opt_.MaxOuterIters) {                                   // make_exit_flag.m:4-5
+    out->exit_flag = 0;
+  } else {
+    int fl = 1 << 8;
+    for (int q = 0; q < 4; ++q)
+      if (f[q] < opt_.AbsFuncTol) fl |= (1 << q);
+    out->exit_flag = fl;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// benchmark helpers
+// ---------------------------------------------------------------------------------------------------
+void Engine::generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed) {
+  AO_CUDA(cudaSetDevice(device_));
+  if (object < 1 || object > n_objects_) throw CudaError(1, "generate_cp_data: object out of range");
+  ObjectState& o = objects_[object - 1];
+  const int R = mode(o.modes[0]).R;
+  GenArgs g{};
+  g.order = o.order;
+  g.R = R;
+  std::vector<double*> tmp(o.order, nullptr);
+  for (int d = 0; d < o.order; ++d) {
+    const ModeState& mm = mode(o.modes[d]);
+    g.dims[d] = o.dims[d];
+    AO_CUDA(cudaMalloc(&tmp[d], (size_t)mm.rows * R * sizeof(double)));
+    AO_CUDA(cudaMemcpyAsync(tmp[d], factors[d], (size_t)mm.rows * R * sizeof(double), cudaMemcpyHostToDevice, st_));
+    g.fac[d] = tmp[d];
+    g.fld[d] = mm.rows;
+  }
+  g.full_last = o.last_full;
+  g.shard_offset = o.shard_offset;
+  g.ld0 = o.ld0;
+  double* sums = nullptr;
+  AO_CUDA(cudaMalloc(&sums, 4 * sizeof(double)));
+  AO_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), st_));
+  const int ctas = 148 * 8;
+  double h[4];
+  gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 0, 0.0, 1.0, sums);
+  AO_CHECK_LAUNCH();
+  if (o.sharded) allreduce(sums, 2);
+  AO_CUDA(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+  const double sigma = (noise > 0.0) ? noise * std::sqrt(h[0]) / std::sqrt(h[1]) : 0.0;  // create_coupled_data.m:161
+  gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 1, sigma, 1.0, sums);
+  AO_CHECK_LAUNCH();
+  if (o.sharded) allreduce(sums + 2, 1);
+  AO_CUDA(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+  gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 2, 0.0, 1.0 / std::sqrt(h[2]), sums);  // script6 :101-102
+  AO_CHECK_LAUNCH();
+  AO_CUDA(cudaStreamSynchronize(st_));
+  launches_ += 3;
+  o.znorm = 1.0;
+  for (auto p : tmp) cudaFree(p);
+  cudaFree(sums);
+}
+
+void Engine::mttkrp_to_host(int object, int pos, double* out) {
+  AO_CUDA(cudaSetDevice(device_));
+  if (object < 1 || object > n_objects_) throw CudaError(1, "mttkrp: object out of range");
+  ObjectState& o = objects_[object - 1];
+  if (pos < 1 || pos > o.order) throw CudaError(1, "mttkrp: position out of range");
+  ModeState& m = mode(o.modes[pos - 1]);
+  compute_mttkrp(o, pos - 1, 1.0, m.A.p, m.rows);
+  AO_CUDA(cudaMemcpyAsync(out, m.A.p, m.A.bytes(), cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+  phase_collect();
+}
+
+float Engine::time_mttkrp(int object, int pos, int reps) {
+  AO_CUDA(cudaSetDevice(device_));
+  if (object < 1 || object > n_objects_) throw CudaError(1, "time_mttkrp: object out of range");
+  ObjectState& o = objects_[object - 1];
+  if (pos < 1 || pos > o.order) throw CudaError(1, "time_mttkrp: position out of range");
+  ModeState& m = mode(o.modes[pos - 1]);
+  View3& v = o.views[pos - 1];
+  pack_operand(v, 0);
+  pack_operand(v, 1);
+  cudaEvent_t a, b;
+  AO_CUDA(cudaEventCreate(&a));
+  AO_CUDA(cudaEventCreate(&b));
+  const int R = m.R;
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr);  // warm-up
+  AO_CUDA(cudaEventRecord(a, st_));
+  for (int r = 0; r < reps; ++r)
+    launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr);
+  AO_CUDA(cudaEventRecord(b, st_));
+  AO_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  AO_CUDA(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return ms / (float)std::max(reps, 1);
+}
+
+}  // namespace aoadmm

@@ -1,0 +1,145 @@
+// engine.h - host-side driver of the AO-ADMM sweep: owns all device state, mirrors the control flow of
+// functions/cmtf_fun_AOADMM.m:87-476 and launches the sm_100a kernels.
+#pragma once
+#include <chrono>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/aoadmm.h"
+#include "mttkrp.cuh"
+#include "smallops.cuh"
+
+namespace aoadmm {
+
+struct DevMat {
+  double* p = nullptr;
+  int64_t rows = 0, cols = 0;
+  size_t bytes() const { return (size_t)rows * cols * sizeof(double); }
+};
+
+struct NcclApi;  // dlopen'ed NCCL entry points (multi-GPU only)
+
+struct ModeState {
+  int id = 0;                 // 1-based global mode id
+  int p = -1;                 // owning object
+  int pos = 0;                // 0-based position inside the object
+  int64_t rows = 0;
+  int R = 0;
+  int coupling = 0;           // lin_coupled_modes(m)
+  bool constrained = false;
+  aoadmm_constraint con{};
+  double ridge = 0.0;
+  DevMat fac, Z, muZ, muD;    // G.fac, G.constraint_fac, G.constraint_dual_fac, G.coupling_dual_fac
+  DevMat A, Alast, C, B, L, GtG, Znew, V;
+  double* invdiag = nullptr;
+  double* rho = nullptr;      // device scalar
+  PackedFactor packed;        // transposed copy used as DMMA B operand
+  InnerCtl* ctl = nullptr;    // device; for coupled modes all modes of the group share the group's block
+  int ctl_index = -1;
+};
+
+struct View3 {                // how mode position n of an object is computed
+  Tensor3 t;
+  int kernel_pos = 0;         // 0 lead, 1 inner/epilogue0, 2 inner/epilogue1
+  std::vector<int> f0_modes, f1_modes;  // global mode ids whose Khatri-Rao product forms operand 0 / 1 (empty = ones)
+  int64_t f0_rows = 0, f1_rows = 0;
+  PackedFactor f0, f1;        // packed operands (allocated when a KR product or ones are needed)
+  bool f0_own = false, f1_own = false;
+  int64_t out_rows = 0;       // rows produced by this rank (== rows of the factor unless sharded last mode)
+  int64_t out_offset = 0;
+  bool needs_allreduce = false;
+};
+
+struct ObjectState {
+  int model = 0, order = 0;
+  std::vector<int> modes;     // global mode ids (1-based)
+  std::vector<int64_t> dims;  // local dims (last one = shard extent)
+  double weight = 1.0, znorm = 0.0;
+  double* data = nullptr;     // device, leading dimension ld0
+  int64_t ld0 = 0;
+  int64_t shard_offset = 0, shard_extent = 0, last_full = 0;
+  bool sharded = false;
+  std::vector<View3> views;   // one per mode position
+  int last_m = 0;             // global id of the mode updated last in a sweep (static)
+};
+
+class Engine {
+ public:
+  Engine(const aoadmm_problem* prob, const aoadmm_dist* dist);
+  ~Engine();
+  void set_state(int field, int index, int slice, const double* data, int64_t rows, int64_t cols);
+  void get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols);
+  void run(const aoadmm_options* opt, aoadmm_out* out);
+  void generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed);
+  float time_mttkrp(int object, int pos, int reps);
+  void mttkrp_to_host(int object, int pos, double* out);  // unweighted MTTKRP of the resident factors
+  int64_t launches() const { return launches_; }
+  void phase_ms(double ms[3]);
+  double last_run_ms() const { return last_run_ms_; }
+  std::string last_error;
+
+ private:
+  // setup
+  void build_views(ObjectState& o);
+  void build_objective_jobs();
+  // sweep pieces
+  void refresh_gram(ModeState& m);
+  void compute_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout);
+  void pack_operand(View3& v, int which);
+  void precompute_mode(ModeState& m, int n_rho_terms, bool do_chol);
+  void run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt);
+  void eval_objective(bool first, double f[4]);
+  void check_errors(aoadmm_out* out);
+  void allreduce(double* buf, size_t count);
+
+  ModeState& mode(int id) { return modes_[id - 1]; }
+
+  int nb_modes_ = 0, n_objects_ = 0, n_couplings_ = 0;
+  std::vector<ModeState> modes_;
+  std::vector<ObjectState> objects_;
+  std::vector<int> coupling_type_;
+  std::vector<DevMat> delta_;  // coupling_fac per coupling id
+  bool has_ridge_ = false;
+
+  // distributed
+  int rank_ = 0, world_ = 1, device_ = 0;
+  NcclApi* nccl_ = nullptr;
+  void* comm_ = nullptr;
+
+  // scratch
+  cudaStream_t st_ = nullptr;
+  MttkrpWorkspace mws_;
+  double* gram_ws_ = nullptr;
+  double* admm_partials_ = nullptr;
+  double* admm_sums_ = nullptr;
+  unsigned* admm_counter_ = nullptr;
+  void* prox_scratch_ = nullptr;
+  double* krtmp_[2] = {nullptr, nullptr};
+  size_t krtmp_doubles_ = 0;
+  InnerCtl* ctl_dev_ = nullptr;
+  InnerCtl* ctl_host_ = nullptr;  // pinned
+  int n_ctl_ = 0;
+  // objective
+  std::vector<RedJob> jobs_host_;
+  RedJob* jobs_dev_ = nullptr;
+  double* red_dev_ = nullptr;
+  double* red_host_ = nullptr;  // pinned
+  struct ObjTerms;
+  std::unique_ptr<ObjTerms> terms_;
+  double* cp0_tmp_ = nullptr;     // iteration-0 MTTKRP / Hadamard scratch
+  int64_t launches_ = 0;
+  // timing
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool_;
+  std::vector<int> ev_phase_;
+  size_t ev_used_ = 0;
+  double phase_ms_[3] = {0, 0, 0};
+  void phase_begin(int phase);
+  void phase_end();
+  void phase_collect();
+  aoadmm_options opt_{};
+  cudaEvent_t run_ev_[2] = {nullptr, nullptr};
+  double last_run_ms_ = 0.0;
+};
+
+}  // namespace aoadmm

@@ -1,0 +1,638 @@
+// smallops.cu - Gram / system preparation / fused ADMM iteration / reductions (sm_100a).
+//
+// Reference lines replaced (functions/cmtf_fun_AOADMM.m):
+//   gram                 :66, :148, :190, :396           G_transp_G{m} = fac'*fac
+//   prep_system          :98-103, :115-119, :124-127, :141-142, :257-276 (Hadamard, rho, B, chol)
+//   admm_iteration       :591-623 (ADMM_constrained_only), :625-695 (ADMM_coupled_case0),
+//                        :1420-1429 (update_constraint), :1079-1115 (eval_res_*), element-wise prox of
+//                        functions/constraints_to_prox.m:13-18,:46-61
+//   ls_solve             :134  fac = A/B
+//   reduce_jobs          :1235-1241, :1272-1300, :1311, :1341 (objective reductions)
+#include "smallops.cuh"
+
+#include <algorithm>
+
+namespace aoadmm {
+
+namespace {
+
+// =====================================================================================================
+// Gram
+// =====================================================================================================
+constexpr int kGramChunk = 2048;
+
+__global__ void gram_partial_kernel(const double* __restrict__ F, long long rows, long long ld, int R,
+                                    double* __restrict__ ws, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  __shared__ double As[32][33];
+  __shared__ double Bs[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+  const int bi = blockIdx.y, bj = blockIdx.z;
+  const long long r0 = (long long)blockIdx.x * kGramChunk;
+  const long long r1 = min(rows, r0 + (long long)kGramChunk);
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (long long rb = r0; rb < r1; rb += 32) {
+    for (int e = tid; e < 1024; e += 256) {
+      const int rr = e & 31, c = e >> 5;
+      const long long row = rb + rr;
+      const int ca = bi * 32 + c, cb = bj * 32 + c;
+      As[rr][c] = (row < r1 && ca < R) ? F[(long long)ca * ld + row] : 0.0;
+      Bs[rr][c] = (row < r1 && cb < R) ? F[(long long)cb * ld + row] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const double a0 = As[rr][2 * ty], a1 = As[rr][2 * ty + 1];
+      const double b0 = Bs[rr][2 * tx], b1 = Bs[rr][2 * tx + 1];
+      acc[0][0] = fma(a0, b0, acc[0][0]);
+      acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]);
+      acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  double* out = ws + (long long)blockIdx.x * R * R;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ia = bi * 32 + 2 * ty + a, ib = bj * 32 + 2 * tx + b;
+      if (ia < R && ib < R) out[(long long)ib * R + ia] = acc[a][b];
+    }
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ ws, int nchunks, int RR, double* __restrict__ G,
+                                   const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= RR) return;
+  double v = 0.0;
+  for (int c = 0; c < nchunks; ++c) v += ws[(long long)c * RR + e];
+  G[e] = v;
+}
+
+// =====================================================================================================
+// prep_system: C = prod(had), rho = trace(C)/R, B = w*C + shifts, L = chol(B)
+// =====================================================================================================
+__global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ double S[];  // R*R when R <= 64, else unused (factorisation runs in global memory)
+  __shared__ double red[32];
+  __shared__ double s_rho;
+  __shared__ int s_err;
+  const int R = a.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const bool use_smem = (R <= 64);
+  double* W = use_smem ? S : a.L;
+  if (tid == 0) s_err = 0;
+  // Hadamard product and trace
+  double tr = 0.0;
+  for (int e = tid; e < RR; e += nt) {
+    double c = a.had[0][e];
+    for (int h = 1; h < a.nhad; ++h) c *= a.had[h][e];
+    a.C[e] = c;
+    if (e % (R + 1) == 0) tr += c;
+  }
+  tr = block_sum(tr, red);
+  if (tid == 0) {
+    s_rho = tr / (double)R * a.rho_scale;
+    *a.rho = s_rho;
+  }
+  __syncthreads();
+  const double half = s_rho / 2.0;
+  for (int e = tid; e < RR; e += nt) {
+    double b = a.weight * a.C[e];
+    if (e % (R + 1) == 0) {
+      if (a.ridge != 0.0) b += a.ridge;
+      if (a.bsum_half != 0.0) b += a.bsum_half;
+      for (int q = 0; q < a.n_rho_terms; ++q) b += half;
+    }
+    if (a.HHt != nullptr) b += half * a.HHt[e];
+    a.B[e] = b;
+    W[e] = b;
+  }
+  __syncthreads();
+  if (a.do_chol) {
+    // right-looking Cholesky on the lower triangle of W (column-major, ld = R)
+    for (int j = 0; j < R; ++j) {
+      const double d = W[j * R + j];
+      if (!(d > 0.0) || !isfinite(d)) {
+        if (tid == 0) s_err = 3;
+        break;  // uniform: every thread read the same d
+      }
+      const double s = sqrt(d);
+      __syncthreads();
+      for (int i = j + 1 + tid; i < R; i += nt) W[j * R + i] = W[j * R + i] / s;
+      if (tid == 0) W[j * R + j] = s;
+      __syncthreads();
+      const int n = R - j - 1;
+      for (int e = tid; e < n * n; e += nt) {
+        const int ci = e / n, ri = e % n;  // trailing block column ci, row ri (0-based inside the block)
+        if (ri >= ci) W[(j + 1 + ci) * R + (j + 1 + ri)] -= W[j * R + (j + 1 + ri)] * W[j * R + (j + 1 + ci)];
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int e = tid; e < RR; e += nt) {
+      const int ci = e / R, ri = e % R;
+      const double v = (ri >= ci) ? W[e] : 0.0;
+      a.L[e] = v;
+      if (ri == ci) a.invdiag[ri] = 1.0 / v;
+    }
+  }
+  if (tid == 0 && a.ctl != nullptr) {
+    a.ctl->done = 0;
+    a.ctl->iters = 0;
+    if (s_err != 0) a.ctl->err = s_err;
+    a.ctl->res[0] = a.ctl->res[1] = a.ctl->res[2] = a.ctl->res[3] = 0.0;
+  }
+}
+
+// =====================================================================================================
+// element-wise prox (constraints_to_prox.m:13-18, :46-61)
+// =====================================================================================================
+__device__ __forceinline__ double prox_elem(int kind, double v, double p0, double p1, double rho) {
+  switch (kind) {
+    case PROX_NONNEG: return fmax(v, 0.0);
+    case PROX_BOX: return fmin(fmax(v, p0), p1);
+    case PROX_L1_REG: {
+      const double g = p0 / rho;
+      const double mag = fmax(fabs(v) - g, 0.0);
+      return (v > 0.0) ? mag : ((v < 0.0) ? -mag : 0.0);
+    }
+    case PROX_L0_REG: {
+      const double g = p0 / rho;
+      return (fabs(v) > sqrt(2.0 * g)) ? v : 0.0;
+    }
+    case PROX_RIDGE: return 1.0 / (2.0 * (p0 / rho) + 1.0) * v;
+    default: return v;
+  }
+}
+
+// =====================================================================================================
+// fused ADMM iteration (row-parallel)
+// =====================================================================================================
+struct FinInfo {
+  int nmodes;
+  int coupled;
+  int constrained[kMaxGroup];
+};
+
+__device__ void finalize_ctl(const double* sums, const FinInfo& fin, const InnerTol& tol, InnerCtl* ctl) {
+  double rpk = 0.0, rdk = 0.0, rpc = 0.0, rdc = 0.0;
+  int nc = 0;
+  const double dd = sqrt(sums[6 * fin.nmodes]);
+  for (int mi = 0; mi < fin.nmodes; ++mi) {
+    const double* s = sums + 6 * mi;
+    const double nF = sqrt(s[0]);
+    if (fin.coupled) {
+      rpk += sqrt(s[1]) / nF;
+      const double sc = sqrt(s[2]);
+      rdk += (sc > 0.0) ? dd / sc : dd;
+    }
+    if (fin.constrained[mi]) {
+      ++nc;
+      rpc += sqrt(s[3]) / nF;
+      const double sc = sqrt(s[5]);
+      const double zz = sqrt(s[4]);
+      rdc += (sc > 0.0) ? zz / sc : zz;
+    }
+  }
+  if (fin.coupled) {
+    rpk /= (double)fin.nmodes;
+    rdk /= (double)fin.nmodes;
+  }
+  if (nc > 0) {
+    rpc /= (double)nc;
+    rdc /= (double)nc;
+  }
+  ctl->res[0] = rpk;
+  ctl->res[1] = rdk;
+  ctl->res[2] = rpc;
+  ctl->res[3] = rdc;
+  ctl->iters += 1;
+  const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
+  if (!cont) ctl->done = 1;
+  if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+}
+
+// Solves x * (L L') = a in place for one row held in shared memory (element e at row_s[e*BT]).
+__device__ __forceinline__ void solve_row(double* row_s, int BT, int R, const double* __restrict__ L,
+                                          const double* __restrict__ invd) {
+  for (int j = 0; j < R; ++j) {
+    const double yj = row_s[j * BT] * invd[j];
+    row_s[j * BT] = yj;
+    const double* Lj = L + (long long)j * R;
+    for (int e = j + 1; e < R; ++e) row_s[e * BT] = fma(-yj, Lj[e], row_s[e * BT]);
+  }
+  for (int j = R - 1; j >= 0; --j) {
+    const double xj = row_s[j * BT] * invd[j];
+    row_s[j * BT] = xj;
+    for (int e = 0; e < j; ++e) row_s[e * BT] = fma(-xj, L[(long long)e * R + j], row_s[e * BT]);
+  }
+}
+
+template <bool LSMEM>
+__global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl* ctl, double* sums, double* partials,
+                                unsigned* counter, int finalize) {
+  if (ctl->done != 0) return;
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  __shared__ bool s_last;
+  const int BT = blockDim.x, tid = threadIdx.x, R = g.R;
+  double* row_s = sm + tid;              // [R][BT]
+  double* dsum_s = sm + (size_t)R * BT + tid;  // [R][BT]
+  double* Ls = sm + (size_t)2 * R * BT;  // [R*R] (LSMEM)
+  double* invd_s = Ls + (LSMEM ? R * R : 0);
+  const long long i = (long long)blockIdx.x * BT + tid;
+  const bool active = i < g.rows;
+  const int NS = 6 * g.nmodes + 1;
+  double lsum[6 * kMaxGroup + 1];
+  for (int s = 0; s < NS; ++s) lsum[s] = 0.0;
+  const bool coupled = g.Delta != nullptr;
+  double sum_rho = 0.0;
+
+  if (coupled)
+    for (int e = 0; e < R; ++e) dsum_s[e * BT] = 0.0;
+
+  for (int mi = 0; mi < g.nmodes; ++mi) {
+    const AdmmMode& md = g.m[mi];
+    const double rho = *md.rho;
+    const double half = rho / 2.0;
+    sum_rho += rho;
+    const double* L = md.L;
+    const double* invd = md.invdiag;
+    if (LSMEM) {
+      __syncthreads();
+      for (int e = tid; e < R * R; e += BT) Ls[e] = md.L[e];
+      for (int e = tid; e < R; e += BT) invd_s[e] = md.invdiag[e];
+      __syncthreads();
+      L = Ls;
+      invd = invd_s;
+    }
+    if (active) {
+      for (int e = 0; e < R; ++e) {
+        double a = md.A[(long long)e * md.ldA + i];
+        if (coupled) a += half * (g.Delta[(long long)e * g.rows + i] - md.muD[(long long)e * g.rows + i]);
+        if (md.constrained) a += half * (md.Z[(long long)e * g.rows + i] - md.muZ[(long long)e * g.rows + i]);
+        row_s[e * BT] = a;
+      }
+      solve_row(row_s, BT, R, L, invd);
+      double sF2 = 0.0;
+      for (int e = 0; e < R; ++e) {
+        const double x = row_s[e * BT];
+        md.F[(long long)e * md.ldF + i] = x;
+        sF2 = fma(x, x, sF2);
+        if (coupled) dsum_s[e * BT] += rho * (x + md.muD[(long long)e * g.rows + i]);
+      }
+      lsum[6 * mi + 0] = sF2;
+    }
+  }
+
+  if (active) {
+    if (coupled) {
+      const double inv = 1.0 / sum_rho;
+      double sDD = 0.0;
+      for (int e = 0; e < R; ++e) {
+        const double dn = inv * dsum_s[e * BT];
+        const double dold = g.Delta[(long long)e * g.rows + i];
+        g.Delta[(long long)e * g.rows + i] = dn;
+        dsum_s[e * BT] = dn;
+        const double df = dn - dold;
+        sDD = fma(df, df, sDD);
+      }
+      lsum[6 * g.nmodes] = sDD;
+    }
+    for (int mi = 0; mi < g.nmodes; ++mi) {
+      const AdmmMode& md = g.m[mi];
+      const double rho = *md.rho;
+      double sFD = 0.0, sMuD = 0.0, sFZ = 0.0, sZZ = 0.0, sMuZ = 0.0;
+      const bool do_con = md.constrained && prox_is_elementwise(md.prox_kind);
+      for (int e = 0; e < R; ++e) {
+        const double x = md.F[(long long)e * md.ldF + i];
+        if (coupled) {
+          const double dn = dsum_s[e * BT];
+          const double mu = md.muD[(long long)e * g.rows + i] + x - dn;
+          md.muD[(long long)e * g.rows + i] = mu;
+          const double fd = x - dn;
+          sFD = fma(fd, fd, sFD);
+          sMuD = fma(mu, mu, sMuD);
+        }
+        if (do_con) {
+          const long long idx = (long long)e * g.rows + i;
+          const double muz = md.muZ[idx];
+          const double zold = md.Z[idx];
+          const double z = prox_elem(md.prox_kind, x + muz, md.p0, md.p1, rho);
+          const double munew = muz + x - z;
+          md.Z[idx] = z;
+          md.muZ[idx] = munew;
+          const double fz = x - z, zz = z - zold;
+          sFZ = fma(fz, fz, sFZ);
+          sZZ = fma(zz, zz, sZZ);
+          sMuZ = fma(munew, munew, sMuZ);
+        }
+      }
+      lsum[6 * mi + 1] = sFD;
+      lsum[6 * mi + 2] = sMuD;
+      lsum[6 * mi + 3] = sFZ;
+      lsum[6 * mi + 4] = sZZ;
+      lsum[6 * mi + 5] = sMuZ;
+    }
+  }
+
+  // deterministic two-level reduction: per-CTA partials, then the last CTA sums them in CTA order
+  for (int s = 0; s < NS; ++s) {
+    const double v = block_sum(lsum[s], red);
+    if (tid == 0) partials[(long long)blockIdx.x * NS + s] = v;
+  }
+  __threadfence();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int s = tid; s < NS; s += BT) {
+      const int mi = s / 6, w = s % 6;
+      // sums owned by a deferred (non element-wise) constraint update are left untouched
+      const bool deferred = (s < 6 * g.nmodes) && (w >= 3) && g.m[mi].constrained &&
+                            !prox_is_elementwise(g.m[mi].prox_kind);
+      if (deferred) continue;
+      double v = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) v += partials[(long long)b * NS + s];
+      sums[s] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      *counter = 0u;
+      if (finalize) finalize_ctl(sums, fin, tol, ctl);
+    }
+  }
+}
+
+
+// deferred constraint update for a mode whose prox is not element-wise
+__global__ void admm_constraint_update_kernel(AdmmGroup g, int which, const double* __restrict__ Znew, FinInfo fin,
+                                              InnerTol tol, InnerCtl* ctl, double* sums, double* partials,
+                                              unsigned* counter, int finalize) {
+  if (ctl->done != 0) return;
+  __shared__ double red[32];
+  __shared__ bool s_last;
+  const AdmmMode& md = g.m[which];
+  const long long n = g.rows * g.R;
+  double sFZ = 0.0, sZZ = 0.0, sMuZ = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / g.rows, i = idx % g.rows;
+    const double x = md.F[e * md.ldF + i];
+    const double z = Znew[idx];
+    const double zold = md.Z[idx];
+    const double munew = md.muZ[idx] + x - z;
+    md.Z[idx] = z;
+    md.muZ[idx] = munew;
+    const double fz = x - z, zz = z - zold;
+    sFZ = fma(fz, fz, sFZ);
+    sZZ = fma(zz, zz, sZZ);
+    sMuZ = fma(munew, munew, sMuZ);
+  }
+  double v;
+  v = block_sum(sFZ, red);
+  if (threadIdx.x == 0) partials[blockIdx.x * 3 + 0] = v;
+  v = block_sum(sZZ, red);
+  if (threadIdx.x == 0) partials[blockIdx.x * 3 + 1] = v;
+  v = block_sum(sMuZ, red);
+  if (threadIdx.x == 0) partials[blockIdx.x * 3 + 2] = v;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += partials[b * 3 + threadIdx.x];
+      sums[6 * which + 3 + threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *counter = 0u;
+      if (finalize) finalize_ctl(sums, fin, tol, ctl);
+    }
+  }
+}
+
+__global__ void admm_form_prox_input_kernel(AdmmGroup g, int which, double* __restrict__ V, const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  const AdmmMode& md = g.m[which];
+  const long long n = g.rows * g.R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / g.rows, i = idx % g.rows;
+    V[idx] = md.F[e * md.ldF + i] + md.muZ[idx];
+  }
+}
+
+template <bool LSMEM>
+__global__ void ls_solve_kernel(const double* __restrict__ A, long long ldA, const double* __restrict__ Lg,
+                                const double* __restrict__ invdg, double* __restrict__ F, long long ldF,
+                                long long rows, int R, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ double sm[];
+  const int BT = blockDim.x, tid = threadIdx.x;
+  double* row_s = sm + tid;
+  double* Ls = sm + (size_t)R * BT;
+  double* invd_s = Ls + (LSMEM ? R * R : 0);
+  const double* L = Lg;
+  const double* invd = invdg;
+  if (LSMEM) {
+    for (int e = tid; e < R * R; e += BT) Ls[e] = Lg[e];
+    for (int e = tid; e < R; e += BT) invd_s[e] = invdg[e];
+    __syncthreads();
+    L = Ls;
+    invd = invd_s;
+  }
+  const long long i = (long long)blockIdx.x * BT + tid;
+  if (i >= rows) return;
+  for (int e = 0; e < R; ++e) row_s[e * BT] = A[(long long)e * ldA + i];
+  solve_row(row_s, BT, R, L, invd);
+  for (int e = 0; e < R; ++e) F[(long long)e * ldF + i] = row_s[e * BT];
+}
+
+// =====================================================================================================
+// reductions: one CTA per job
+// =====================================================================================================
+__global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __restrict__ results,
+                                   const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  __shared__ double red[32];
+  const RedJob jb = jobs[blockIdx.x];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double acc = 0.0;
+  if (jb.kind == RED_COLNORM) {
+    for (int c = 0; c < jb.cols; ++c) {
+      double s = 0.0;
+      for (long long i = tid; i < jb.rows; i += nt) {
+        const double v = jb.a[(long long)c * jb.lda + i];
+        s = fma(v, v, s);
+      }
+      s = block_sum(s, red);
+      if (tid == 0) acc += sqrt(s);
+    }
+    if (tid == 0) results[blockIdx.x] = acc;
+    return;
+  }
+  for (int c = 0; c < jb.cols; ++c) {
+    const double* a = jb.a + (long long)c * jb.lda;
+    const double* b = (jb.b != nullptr) ? jb.b + (long long)c * jb.ldb : nullptr;
+    for (long long i = tid; i < jb.rows; i += nt) {
+      const double v = a[i];
+      switch (jb.kind) {
+        case RED_DOT: acc = fma(v, b[i], acc); break;
+        case RED_NORM2: acc = fma(v, v, acc); break;
+        case RED_DIFF2: {
+          const double d = v - b[i];
+          acc = fma(d, d, acc);
+          break;
+        }
+        case RED_L1: acc += fabs(v); break;
+        case RED_SUM: acc += v; break;
+        case RED_NNZ: acc += (v != 0.0) ? 1.0 : 0.0; break;
+        case RED_TVSUM:
+          if (i + 1 < jb.rows) acc += a[i + 1] - v;
+          break;
+        case RED_GLQUAD: {
+          // (L x)_i with L = tridiag(-1, 2, -1), corners 1
+          double lx = 0.0;
+          if (jb.rows > 1) {
+            if (i == 0) lx = v - a[1];
+            else if (i == jb.rows - 1) lx = v - a[i - 1];
+            else lx = 2.0 * v - a[i - 1] - a[i + 1];
+          }
+          acc = fma(v, lx, acc);
+          break;
+        }
+        default: break;
+      }
+    }
+  }
+  acc = block_sum(acc, red);
+  if (tid == 0) results[blockIdx.x] = acc;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// host wrappers
+// =====================================================================================================
+size_t gram_ws_doubles(int64_t rows, int R) { return (size_t)ceil_div(std::max<int64_t>(rows, 1), kGramChunk) * R * R; }
+
+int gram(const double* F, int64_t rows, int64_t ld, int R, double* G, double* ws, cudaStream_t st, const int* skip) {
+  const int nchunks = (int)ceil_div(std::max<int64_t>(rows, 1), kGramChunk);
+  const int nb = (int)ceil_div(R, 32);
+  dim3 grid(nchunks, nb, nb), block(16, 16);
+  gram_partial_kernel<<<grid, block, 0, st>>>(F, rows, ld, R, ws, skip);
+  AO_CHECK_LAUNCH();
+  gram_reduce_kernel<<<(unsigned)ceil_div(R * R, 256), 256, 0, st>>>(ws, nchunks, R * R, G, skip);
+  AO_CHECK_LAUNCH();
+  return 2;
+}
+
+int prep_system(const PrepArgs& a, cudaStream_t st, const int* skip) {
+  const size_t smem = (a.R <= 64) ? (size_t)a.R * a.R * sizeof(double) : 0;
+  prep_system_kernel<<<1, 256, smem, st>>>(a, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+namespace {
+struct RowLaunch {
+  int BT;
+  bool lsmem;
+  size_t smem;
+};
+RowLaunch row_launch_cfg(int R, int nrowbuf) {
+  RowLaunch c;
+  c.BT = (R <= 32) ? 128 : ((R <= 64) ? 64 : 32);
+  c.lsmem = (R <= 64);
+  c.smem = ((size_t)nrowbuf * R * c.BT + (c.lsmem ? (size_t)R * R + R : 0)) * sizeof(double);
+  return c;
+}
+FinInfo make_fin(const AdmmGroup& g) {
+  FinInfo f;
+  f.nmodes = g.nmodes;
+  f.coupled = g.Delta != nullptr;
+  for (int i = 0; i < kMaxGroup; ++i) f.constrained[i] = (i < g.nmodes) ? g.m[i].constrained : 0;
+  return f;
+}
+template <typename K>
+void set_smem(K kern, size_t smem) {
+  if (smem > 48 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+}  // namespace
+
+size_t admm_ws_doubles(long long rows, int R, int nmodes) {
+  const RowLaunch c = row_launch_cfg(R, 2);
+  const size_t ctas_row = (size_t)ceil_div(std::max<long long>(rows, 1), c.BT);
+  return std::max<size_t>(ctas_row * (6 * nmodes + 1), (size_t)148 * 8 * 3) + 16;
+}
+
+int admm_iteration(const AdmmGroup& g, const InnerTol& tol, InnerCtl* ctl, double* sums, double* partials,
+                   unsigned* counter, int finalize, cudaStream_t st) {
+  const RowLaunch c = row_launch_cfg(g.R, 2);
+  const unsigned ctas = (unsigned)ceil_div(std::max<long long>(g.rows, 1), c.BT);
+  const FinInfo fin = make_fin(g);
+  if (c.lsmem) {
+    set_smem(admm_row_kernel<true>, c.smem);
+    admm_row_kernel<true><<<ctas, c.BT, c.smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
+  } else {
+    set_smem(admm_row_kernel<false>, c.smem);
+    admm_row_kernel<false><<<ctas, c.BT, c.smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
+  }
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int admm_constraint_update(const AdmmGroup& g, int which, const double* Znew, const InnerTol& tol, InnerCtl* ctl,
+                           double* sums, double* partials, unsigned* counter, int finalize, cudaStream_t st) {
+  const long long n = g.rows * g.R;
+  const unsigned ctas = (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8);
+  admm_constraint_update_kernel<<<ctas, 256, 0, st>>>(g, which, Znew, make_fin(g), tol, ctl, sums, partials, counter,
+                                                      finalize);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int admm_form_prox_input(const AdmmGroup& g, int which, double* V, const InnerCtl* ctl, cudaStream_t st) {
+  const long long n = g.rows * g.R;
+  const unsigned ctas = (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8);
+  admm_form_prox_input_kernel<<<ctas, 256, 0, st>>>(g, which, V, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int ls_solve(const double* A, long long ldA, const double* L, const double* invdiag, double* F, long long ldF,
+             long long rows, int R, InnerCtl* ctl, cudaStream_t st, const int* skip) {
+  (void)ctl;
+  const RowLaunch c = row_launch_cfg(R, 1);
+  const unsigned ctas = (unsigned)ceil_div(std::max<long long>(rows, 1), c.BT);
+  if (c.lsmem) {
+    set_smem(ls_solve_kernel<true>, c.smem);
+    ls_solve_kernel<true><<<ctas, c.BT, c.smem, st>>>(A, ldA, L, invdiag, F, ldF, rows, R, skip);
+  } else {
+    set_smem(ls_solve_kernel<false>, c.smem);
+    ls_solve_kernel<false><<<ctas, c.BT, c.smem, st>>>(A, ldA, L, invdiag, F, ldF, rows, R, skip);
+  }
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int reduce_jobs(const RedJob* jobs_dev, int njobs, double* results_dev, cudaStream_t st, const int* skip) {
+  if (njobs <= 0) return 0;
+  reduce_jobs_kernel<<<njobs, 512, 0, st>>>(jobs_dev, results_dev, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+}  // namespace aoadmm

@@ -1,0 +1,121 @@
+"""CPU: the C-ABI library loads, exports every symbol include/aoadmm.h declares, and the host-side mirror behaves
+(no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'aoadmm.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(aoadmm_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol(ab):
+    names = header_functions()
+    assert 'aoadmm_run' in names and 'aoadmm_create' in names and len(names) >= 17
+    for n in names:
+        assert hasattr(ab._capi.lib, n), n
+    assert sorted(ab._capi.EXPORTS) == names
+    assert ab._capi.lib.aoadmm_abi_version() == 1
+
+
+def test_struct_layouts_match_header(ab, tmp_path):
+    """compile include/aoadmm.h with gcc and compare sizeof/offsetof with the ctypes mirror."""
+    import subprocess
+    c = ab._capi
+    structs = {'aoadmm_constraint': c.Constraint, 'aoadmm_object': c.Object, 'aoadmm_problem': c.Problem,
+               'aoadmm_dist': c.Dist, 'aoadmm_options': c.Options, 'aoadmm_out': c.Out}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aoadmm.h"', 'int main(void){']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('return 0;}')
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_no_device_is_an_error_not_a_fallback(ab):
+    if ab.device_count() > 0:
+        pytest.skip('a GPU is present')
+    X = np.zeros((4, 3, 2))
+    U = [np.ones((s, 2)) for s in X.shape]
+    with pytest.raises(ab.AoadmmError) as e:
+        ab.mttkrp(X, U, 1)
+    assert e.value.status_name == 'NO_DEVICE'
+    with pytest.raises(ab.AoadmmError):
+        ab.prox(('non-negativity',), np.zeros((3, 2)))
+
+
+def test_invalid_arguments_rejected_without_device(ab):
+    c = ab._capi
+    assert c.lib.aoadmm_create(None, None, None) == 1
+    h = c.HandleP()
+    assert c.lib.aoadmm_create(None, None, ctypes.byref(h)) != 0
+    assert b'NULL' in c.lib.aoadmm_last_error(None)
+    assert c.lib.aoadmm_run(None, None, None) == 1
+    assert c.lib.aoadmm_destroy(None) == 0
+
+
+def test_constraint_spec_mapping(ab):
+    spec, _ = ab.constraint_spec(('box', -1.0, 2.0))
+    assert (spec.kind, spec.p0, spec.p1) == (2, -1.0, 2.0)
+    spec, _ = ab.constraint_spec(('unimodality', True))
+    assert (spec.kind, spec.p0) == (7, 1.0)
+    spec, _ = ab.constraint_spec(('TV regularization', 1e-3))
+    assert (spec.kind, spec.p0) == (19, 1e-3)
+    spec, keep = ab.constraint_spec(('quadratic regularization', 0.5, np.eye(3)))
+    assert spec.kind == 17 and spec.matrix_n == 3 and keep is not None
+    assert ab.constraint_spec(None)[0].kind == 0
+    with pytest.raises(ValueError):
+        ab.constraint_spec(('no such constraint',))
+    # every named spec of constraints_to_prox.m is known
+    ref = open('/root/reference/functions/constraints_to_prox.m').read() if os.path.exists(
+        '/root/reference/functions/constraints_to_prox.m') else None
+    if ref:
+        for name in re.findall(r"strcmp\(constraints\{m\}\{1\},'([^']+)'\)", ref):
+            assert name in ab._capi.CONSTRAINT_KINDS, name
+
+
+def test_shard_range_partitions(ab):
+    for extent in (1, 7, 256, 1000, 2048):
+        for world in (1, 2, 3, 4, 8):
+            parts = [ab.shard_range(extent, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == extent
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_unsupported_inputs_raise_before_touching_the_device(ab):
+    from oracle import problem_gen as pg
+    Z, G, _ = pg.config_script6(seed=0, sz=(6, 7, 5, 6, 8, 7, 9))
+    Zk = dict(Z, loss_function=['KL', 'Frobenius', 'Frobenius'])
+    with pytest.raises(ab.AoadmmError) as e:
+        ab.cmtf_fun_AOADMM(Zk, pg.znorm_const(Z), G, None, None, None, None, pg.default_options())
+    assert e.value.status_name == 'UNSUPPORTED'
+    Zm = dict(Z, miss=[np.ones_like(Z['object'][0]), None, None])
+    with pytest.raises(ab.AoadmmError):
+        ab.cmtf_fun_AOADMM(Zm, pg.znorm_const(Z), G, None, None, None, None, pg.default_options())
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'matlab-code_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp', '.m')):
+                txt = open(os.path.join(dp, f), errors='replace').read()
+                assert 'import oracle' not in txt and 'from oracle' not in txt, os.path.join(dp, f)

@@ -1,0 +1,256 @@
+"""GPU (-m gpu): parity of the CUDA engine with the CPU oracle THROUGH THE C ABI, on identical seeded inputs.
+
+Tolerances (north_star): factor matrices 1e-8 relative Frobenius error, objective/fit 1e-10; operator-level
+checks are held to rounding level (1e-12)."""
+import numpy as np
+import pytest
+
+from oracle import problem_gen as pg
+from oracle import prox as P
+from oracle.cmtf_fun_aoadmm import cmtf_fun_AOADMM as oracle_solve
+from oracle.tensor_ops import mttkrp as oracle_mttkrp
+from _cases import FAC_TOL, FIT_TOL, ZERO_TOL, assert_state_close, golden_case, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_gpu(ab):
+    assert ab.device_count() >= 1, 'GPU tests need a CUDA device (the engine has no CPU fallback)'
+
+
+# ---------------------------------------------------------------------------------------------- MTTKRP
+@pytest.mark.parametrize('shape,R', [
+    ((50, 60, 40), 3),            # example_script6 sizes
+    ((1, 1, 1), 1), ((2, 3, 4), 2), ((3, 129, 5), 7),   # degenerate / ragged
+    ((130, 70, 33), 8), ((64, 64, 64), 16), ((200, 150, 90), 32), ((129, 257, 65), 64),
+    ((96, 80, 72), 100), ((40, 36, 30), 256),           # multi-chunk ranks, maximum rank
+    ((51, 61, 41), 5),            # odd leading dimension (padded on upload)
+    ((40, 30), 4), ((300, 500), 32), ((7, 1), 3),       # matrices (cmtf_fun_AOADMM.m:106-113)
+    ((20, 12, 10, 8), 6), ((9, 8, 7, 6, 5), 4),         # N-way tensors
+])
+def test_mttkrp_all_modes(ab, shape, R):
+    rng = np.random.RandomState(sum(shape) + R)
+    X = np.asfortranarray(rng.randn(*shape))
+    U = [rng.randn(s, R) for s in shape]
+    for n in range(1, len(shape) + 1):
+        got = ab.mttkrp(X, U, n)
+        assert rel(got, oracle_mttkrp(X, U, n - 1)) < 1e-12, (shape, R, n)
+
+
+def test_mttkrp_linearity_and_scaling_large(ab):
+    """size-independent properties at a size the oracle would not finish quickly: linearity in X and in a factor."""
+    rng = np.random.RandomState(0)
+    shape, R = (384, 320, 256), 32
+    X1 = np.asfortranarray(rng.randn(*shape))
+    X2 = np.asfortranarray(rng.randn(*shape))
+    U = [rng.randn(s, R) for s in shape]
+    for n in (1, 2, 3):
+        a = ab.mttkrp(X1, U, n)
+        b = ab.mttkrp(X2, U, n)
+        c = ab.mttkrp(X1 + 2.0 * X2, U, n)
+        assert rel(c, a + 2.0 * b) < 1e-12
+    # rank-one tensor: closed form  M1 = a * (b'B .* c'C)
+    a_, b_, c_ = rng.randn(shape[0]), rng.randn(shape[1]), rng.randn(shape[2])
+    Xr = np.asfortranarray(np.einsum('i,j,k->ijk', a_, b_, c_))
+    M1 = ab.mttkrp(Xr, U, 1)
+    assert rel(M1, np.outer(a_, (b_ @ U[1]) * (c_ @ U[2]))) < 1e-12
+
+
+def test_mttkrp_deterministic(ab):
+    rng = np.random.RandomState(1)
+    X = np.asfortranarray(rng.randn(150, 140, 130))
+    U = [rng.randn(s, 16) for s in X.shape]
+    for n in (1, 2, 3):
+        assert np.array_equal(ab.mttkrp(X, U, n), ab.mttkrp(X, U, n))
+
+
+# ---------------------------------------------------------------------------------------------- small ops
+@pytest.mark.parametrize('rows,R', [(1, 1), (5, 3), (500, 7), (4097, 32), (3000, 64), (700, 100), (300, 256)])
+def test_gram_and_chol_solve(ab, rows, R):
+    rng = np.random.RandomState(rows + R)
+    F = rng.randn(rows, R)
+    G = ab.gram(F)
+    assert rel(G, F.T @ F) < 1e-13
+    B = F.T @ F / max(rows, 1) + (np.trace(F.T @ F) / rows / R + 0.1) * np.eye(R)
+    A = rng.randn(max(rows // 3, 1), R)
+    X = ab.chol_solve(B, A)
+    assert rel(X @ B, A) < 1e-11
+    assert rel(X, np.linalg.solve(B.T, A.T).T) < 1e-10
+
+
+def test_chol_failure_is_reported(ab):
+    B = np.array([[1.0, 2.0], [2.0, 1.0]])   # indefinite: chol() throws in the reference (cmtf_fun_AOADMM.m:142)
+    with pytest.raises(ab.AoadmmError) as e:
+        ab.chol_solve(B, np.ones((3, 2)))
+    assert e.value.status_name == 'NOT_POSITIVE_DEFINITE'
+
+
+CONSTRAINTS = [('non-negativity',), ('box', -0.3, 0.5), ('simplex column-wise', 1.0), ('simplex row-wise', 2.0),
+               ('non-decreasing',), ('non-increasing',), ('unimodality', True), ('unimodality', False), ('l1-ball', 3.0),
+               ('l2-ball', 1.0), ('non-negative l2-ball', 1.0), ('non-negative l2-sphere', 1.0), ('l1 regularization', 0.2),
+               ('l0 regularization', 0.2), ('l2 regularization', 2.0), ('ridge', 0.3), ('GL smoothness', 0.5),
+               ('TV regularization', 0.7)]
+
+
+@pytest.mark.parametrize('con', CONSTRAINTS, ids=[c[0] + str(c[1:]) for c in CONSTRAINTS])
+@pytest.mark.parametrize('rows,cols', [(1, 1), (2, 3), (200, 6), (2049, 8)])
+def test_prox_matches_oracle(ab, con, rows, cols):
+    rng = np.random.RandomState(rows * 7 + cols)
+    V = rng.randn(rows, cols)
+    if rows > 100:
+        V[:, 0] = -np.abs(V[:, 0])         # an all-negative column (the non-negative sphere special case)
+        V[rows // 2:, 1] = V[rows // 2, 1]  # ties / plateaus
+    ops, _ = P.constraints_to_prox([1], [con], [rows])
+    for rho in (1.0, 0.37):
+        assert rel(ab.prox(con, V, rho=rho), ops[0](V, rho)) < 1e-12, (con, rows, cols, rho)
+
+
+def test_prox_large_column_uses_global_scratch(ab):
+    rng = np.random.RandomState(2)
+    V = np.cumsum(rng.randn(20000, 2), axis=0) * 0.05
+    for con in [('TV regularization', 0.5), ('non-decreasing',)]:
+        ops, _ = P.constraints_to_prox([1], [con], [V.shape[0]])
+        assert rel(ab.prox(con, V, rho=1.0), ops[0](V, 1.0)) < 1e-12
+    Y = ab.prox(('simplex column-wise', 1.0), V)
+    assert np.allclose(Y.sum(axis=0), 1.0) and Y.min() >= 0
+
+
+def test_prox_idempotent_projections(ab):
+    rng = np.random.RandomState(3)
+    V = rng.randn(300, 5)
+    for con in [('non-negativity',), ('simplex column-wise', 1.0), ('l2-ball', 1.0), ('unimodality', True),
+                ('non-decreasing',), ('l1-ball', 2.0), ('non-negative l2-sphere', 1.0)]:
+        once = ab.prox(con, V)
+        assert rel(ab.prox(con, once), once) < 1e-12, con
+
+
+def test_custom_constraint_is_unsupported(ab):
+    with pytest.raises(ab.AoadmmError) as e:
+        ab.prox(('custom', None), np.zeros((3, 2)))
+    assert e.value.status_name == 'UNSUPPORTED'
+
+
+# ---------------------------------------------------------------------------------------------- solver
+def _both(ab, Z, G, opts):
+    zn = pg.znorm_const(Z)
+    Go, oo = oracle_solve(Z, zn, G, options=opts)
+    Gd, od = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts)
+    return Go, oo, Gd, od
+
+
+def _assert_out_close(od, oo):
+    assert od['OuterIterations'] == oo['OuterIterations']
+    n = oo['OuterIterations'] + 1
+    for key in ('func_val_conv', 'func_coupl_conv', 'func_constr_conv'):
+        assert np.max(np.abs(od[key][:n] - oo[key][:n])) < FIT_TOL, key
+    assert np.array_equal(od['innerIters'], oo['innerIters'])
+    assert od['exit_flag'] == oo['exit_flag']
+    for key in ('f_tensors', 'f_couplings', 'f_constraints'):
+        assert abs(od[key] - oo[key]) < FIT_TOL
+
+
+def test_config1_example_script6_full_run(ab):
+    """C1: example_script6 at the script's own sizes and options (runs to convergence: 102 outer iterations)."""
+    Z, G, _ = pg.config_script6(seed=0)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options())
+    assert oo['OuterIterations'] == 102
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_config1_fixed_iterations_zero_tolerances(ab):
+    Z, G, _ = pg.config_script6(seed=2)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=40, **ZERO_TOL))
+    assert np.all(oo['innerIters'][[0, 1, 3, 4, 5, 6], :] == 5) and np.all(oo['innerIters'][2, :] == 1)
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+@pytest.mark.parametrize('dims', [(120, 90, 70, 200, 8), (64, 48, 40, 80, 32), (33, 21, 17, 50, 3), (40, 36, 30, 64, 64)])
+def test_config2_family_cp_coupled_matrix(ab, dims):
+    Z, G, _ = pg.config_cp_matrix(*dims, seed=1)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=25))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+@pytest.mark.parametrize('mode1', [('TV regularization',), ('l1 regularization',), ('unimodality', False),
+                                   ('non-negative l2-sphere', 1.0), ('simplex column-wise', 1.0), ('GL smoothness',),
+                                   ('l2 regularization',), ('box', -0.2, 0.2), ('non-decreasing',), ('l1-ball', 2.0)])
+def test_config5_family_prox_kernels_in_the_loop(ab, mode1):
+    """C5 (example_script10 style): regulariser / constraint on mode 1, l2-ball on modes 2,3."""
+    Z, G, _ = pg.config_cp_tv(I=40, J=30, K=26, R=3, seed=4, mode1=mode1, eta=1e-3 if len(mode1) == 1 else 1.0)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=30, AbsFuncTol=1e-7))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_rank_sweep_small(ab):
+    for R in (8, 16, 40, 128):
+        Z, G, _ = pg.config_cp_tv(I=48, J=40, K=36, R=R, seed=R, mode1=('l1 regularization',), eta=1e-3)
+        Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=6, **ZERO_TOL))
+        _assert_out_close(od, oo)
+        assert_state_close(Gd, Go)
+
+
+def test_unconstrained_als_and_ridge_and_bsum(ab):
+    Z, G, _ = pg.config_single_cp(sz=(24, 20, 18), R=3, seed=7, noise=0.1,
+                                  constraints=[None, ('non-negativity',), None])
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=15))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+    Zr = dict(Z, ridge=[1e-3, 2e-3, 1e-3])
+    Go, oo, Gd, od = _both(ab, Zr, G, pg.default_options(MaxOuterIters=15, bsum=1, bsum_weight=1e-2))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_four_way_tensor(ab):
+    Z, G, _ = pg.config_single_cp(sz=(12, 10, 9, 8), R=3, seed=9, noise=0.1, constraints=[('non-negativity',)] * 4)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=20))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_warm_restart_equals_continuous_run(ab):
+    """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
+    Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
+    zn = pg.znorm_const(Z)
+    o10 = pg.default_options(MaxOuterIters=10, **ZERO_TOL)
+    o20 = pg.default_options(MaxOuterIters=20, **ZERO_TOL)
+    Ga, _ = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, o10)
+    Gb, _ = ab.cmtf_fun_AOADMM(Z, zn, Ga, None, None, None, None, o10)
+    Gc, _ = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, o20)
+    for m in range(5):
+        assert np.array_equal(Gb['fac'][m], Gc['fac'][m])
+
+
+@pytest.mark.parametrize('name', ['script6_small', 'cp_matrix_small', 'cp_tv_small'])
+def test_engine_reproduces_committed_golden_vectors(ab, name):
+    Z, G, opts, gold = golden_case(name)
+    Gd, od = ab.cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, None, None, None, None, opts)
+    assert od['OuterIterations'] == int(gold['OuterIterations'])
+    assert np.max(np.abs(od['func_val_conv'] - gold['func_val_conv'])) < FIT_TOL
+    for i, F in enumerate(Gd['fac']):
+        assert rel(F, gold['out_fac_%d' % i]) < FAC_TOL
+    assert np.array_equal(od['innerIters'], gold['innerIters'])
+
+
+def test_front_end_cmtf_AOADMM(ab):
+    Z, G, _ = pg.config_script6(seed=0, sz=(20, 24, 16, 20, 28, 24, 32))
+    Zhat, Fac, Ginit, out = ab.cmtf_AOADMM(Z, G, pg.default_options(MaxOuterIters=30))
+    assert len(Zhat) == 3 and Zhat[0][0].shape == (20, 3) and out['OuterIterations'] <= 30
+    fit = 100 * (1 - np.sum((Z['object'][1] - Zhat[1][0] @ Zhat[1][1].T) ** 2) / np.sum(Z['object'][1] ** 2))
+    assert fit > 90
+
+
+def test_solver_reports_launches_and_times(ab):
+    Z, G, _ = pg.config_cp_matrix(64, 48, 40, 80, 8, seed=1)
+    Z = dict(Z, rank=[8, 8])
+    with ab.Solver(Z, pg.znorm_const(Z)) as s:
+        s.set_state(G)
+        out = s.run(pg.default_options(MaxOuterIters=3, **ZERO_TOL))
+        assert out['OuterIterations'] == 3
+        assert s.launch_count() > 50 and s.last_run_ms() > 0
+        assert s.time_mttkrp(1, 2, 2) > 0

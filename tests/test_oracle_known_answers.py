@@ -1,0 +1,189 @@
+"""CPU: the oracle is validated by known-answer checks; the reference ships no
+golden vectors (parity unpinned), so these are what pins the oracle."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import problem_gen as pg
+from oracle import prox as P
+from oracle.cmtf_fun_aoadmm import cmtf_fun_AOADMM, evaluate_stopping_conditions, make_exit_flag
+from oracle.tensor_ops import full_ktensor, khatrirao, mttkrp
+from _cases import golden_case, rel
+
+
+def test_mttkrp_vs_einsum():
+    rng = np.random.RandomState(0)
+    X = np.asfortranarray(rng.randn(7, 6, 5))
+    U = [rng.randn(s, 3) for s in X.shape]
+    assert rel(mttkrp(X, U, 0), np.einsum('ijk,jr,kr->ir', X, U[1], U[2])) < 1e-14
+    assert rel(mttkrp(X, U, 1), np.einsum('ijk,ir,kr->jr', X, U[0], U[2])) < 1e-14
+    assert rel(mttkrp(X, U, 2), np.einsum('ijk,ir,jr->kr', X, U[0], U[1])) < 1e-14
+    X4 = rng.randn(3, 4, 5, 6)
+    U4 = [rng.randn(s, 2) for s in X4.shape]
+    assert rel(mttkrp(X4, U4, 1), np.einsum('ijkl,ir,kr,lr->jr', X4, U4[0], U4[2], U4[3])) < 1e-14
+
+
+def test_full_ktensor_and_khatrirao():
+    rng = np.random.RandomState(1)
+    U = [rng.randn(4, 3), rng.randn(5, 3), rng.randn(6, 3)]
+    assert rel(full_ktensor(U, [2.0, 1.0, 0.5]), np.einsum('r,ir,jr,kr->ijk', [2.0, 1.0, 0.5], *U)) < 1e-14
+    kr = khatrirao([U[0], U[1]])
+    assert kr.shape == (20, 3) and abs(kr[1 + 4 * 2, 1] - U[0][1, 1] * U[1][2, 1]) < 1e-15
+
+
+def test_shortcut_objective_equals_explicit_residual():
+    Z, G, _ = pg.config_script6(seed=0, sz=(12, 14, 10, 12, 16, 14, 18))
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=15))
+    f = 0.0
+    for p, X in enumerate(Z['object']):
+        f += Z['weights'][p] * np.sum((X - full_ktensor([Gout['fac'][m - 1] for m in Z['modes'][p]])) ** 2)
+    assert abs(f - out['f_tensors']) < 1e-13
+
+
+def test_noise_free_recovery_and_attainable_fit():
+    Z, G, info = pg.config_script6(seed=1, noise=0.0, sz=(15, 16, 14, 15, 18, 16, 20))
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=2000, AbsFuncTol=1e-10))
+    assert out['f_tensors'] < 1e-5
+    Z, G, info = pg.config_script6(seed=0)   # noise 0.2 -> attainable fit ~ 100/(1+0.04) = 96.15 %
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options())
+    assert out['OuterIterations'] == 102     # the value the survey probe measured with RandomState(0)
+    for p, X in enumerate(Z['object']):
+        fit = 100 * (1 - np.sum((X - full_ktensor([Gout['fac'][m - 1] for m in Z['modes'][p]])) ** 2) / np.sum(X ** 2))
+        assert 95.5 < fit < 97.0
+
+
+def test_ordering_quirks():
+    """uncoupled modes first; mixed constrained/unconstrained group (script 6: mode 2 unconstrained, mode 6 constrained)."""
+    Z, G, _ = pg.config_script6(seed=0, sz=(10, 12, 8, 10, 14, 12, 16))
+    tr = []
+    cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=1), trace=tr)
+    assert [t[1] for t in tr] == [3, 5, 7, 1, 4, 2, 6]
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=3))
+    assert Gout['constraint_fac'][1] is None and Gout['constraint_fac'][5] is not None
+    assert out['innerIters'][2, 0] == 1      # unconstrained least-squares update counts one inner iteration
+
+
+def _brute_force_projection(v, feasible_grid):
+    best, bx = np.inf, None
+    for x in feasible_grid:
+        d = np.sum((np.asarray(x) - v) ** 2)
+        if d < best:
+            best, bx = d, np.asarray(x)
+    return bx
+
+
+def test_simplex_and_l1_projection_kkt():
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        v = rng.randn(9) * 2
+        w = P._project_simplex_vec(v, 1.5)
+        assert abs(w.sum() - 1.5) < 1e-12 and w.min() >= 0
+        theta = (v - w)[w > 0]
+        assert np.ptp(theta) < 1e-12 and np.all((v - theta[0])[w == 0] <= 1e-12)   # KKT
+    X = rng.randn(11, 4) * 3
+    Y = P.project_L1(X, 2.0)
+    assert np.all(np.abs(Y).sum(axis=0) <= 2.0 + 1e-12)
+    small = rng.randn(5, 2) * 0.01
+    assert np.array_equal(P.project_L1(small, 2.0), small)
+    assert rel(P.project_simplex(X.T, 1.0, 2), P.project_simplex(X, 1.0, 1).T) < 1e-15
+
+
+def test_tv_prox_optimality():
+    """Condat's output must satisfy the TV-prox optimality conditions: x = y - D'u, |u|<=lam, u_i = lam*sign(dx_i)."""
+    rng = np.random.RandomState(3)
+    for n, lam in [(1, 0.5), (2, 0.3), (17, 0.4), (64, 1.5), (200, 0.05)]:
+        y = np.cumsum(rng.randn(n)) * 0.3 + rng.randn(n) * 0.2
+        x = P.tv_condat(y, lam)
+        u = np.cumsum(y - x)[:-1]            # dual variable
+        assert abs(np.sum(y - x)) < 1e-10
+        if n > 1:
+            assert np.all(np.abs(u) <= lam + 1e-10)
+            dx = np.diff(x)
+            assert np.all(np.abs(u[dx > 1e-12] + lam) < 1e-9) or np.all(np.abs(np.abs(u[np.abs(dx) > 1e-12]) - lam) < 1e-9)
+    assert np.array_equal(P.tv_condat(np.array([1.0, 2.0, 0.5]), 0.0), np.array([1.0, 2.0, 0.5]))
+    assert rel(P.tv_condat(np.array([0.0, 10.0]), 100.0), np.array([5.0, 5.0])) < 1e-15
+
+
+def test_monotone_and_unimodal_bruteforce():
+    rng = np.random.RandomState(5)
+    grid = np.linspace(-1, 1, 5)
+    for _ in range(5):
+        v = rng.choice(grid, size=4)
+        iso = P._pava_nondecreasing(v)
+        assert np.all(np.diff(iso) >= -1e-14)
+        # PAVA optimum is at least as good as any non-decreasing grid vector
+        cands = [c for c in itertools.product(grid, repeat=4) if all(np.diff(c) >= 0)]
+        bf = _brute_force_projection(v, cands)
+        assert np.sum((iso - v) ** 2) <= np.sum((bf - v) ** 2) + 1e-12
+        uni = P.project_unimodal_vector(v, False)
+        k = int(np.argmax(uni))
+        assert np.all(np.diff(uni[:k + 1]) >= -1e-14) and np.all(np.diff(uni[k:]) <= 1e-14)
+        cands = [c for c in itertools.product(grid, repeat=4)
+                 if any(all(np.diff(c[:m + 1]) >= 0) and all(np.diff(c[m:]) <= 0) for m in range(4))]
+        bf = _brute_force_projection(v, cands)
+        assert np.sum((uni - v) ** 2) <= np.sum((bf - v) ** 2) + 1e-12
+    x = rng.randn(30)
+    u = P.project_unimodal_vector(x, True)
+    assert u.min() >= 0
+    assert rel(P.project_unimodal_vector(np.array([0., 1., 3., 2., 1.]), False), np.array([0., 1., 3., 2., 1.])) < 1e-15
+
+
+def test_elementwise_and_norm_prox_definitions():
+    rng = np.random.RandomState(7)
+    X = rng.randn(13, 5)
+    assert np.array_equal(P.project_box(X, 0, np.inf), np.maximum(X, 0))
+    assert np.array_equal(P.prox_abs(X, 0.3), np.sign(X) * np.maximum(np.abs(X) - 0.3, 0))
+    Y = P.project_L2(X, 1.0)
+    assert np.all(np.linalg.norm(Y, axis=0) <= 1 + 1e-14)
+    Y = P.prox_normalized_nonneg(X)
+    assert np.allclose(np.linalg.norm(Y, axis=0), 1) and Y.min() >= 0
+    neg = -np.abs(X)
+    Y = P.prox_normalized_nonneg(neg)
+    assert np.all(Y.sum(axis=0) == 1) and np.all(Y.argmax(axis=0) == neg.argmax(axis=0))
+    g = 0.8
+    Y = P.prox_L2(X, g)
+    for r in range(5):
+        n = np.linalg.norm(X[:, r])
+        assert rel(Y[:, r], X[:, r] * max(0, 1 - g / n)) < 1e-15
+    ops, regs = P.constraints_to_prox([1, 1, 1], [('GL smoothness', 0.5), ('TV regularization', 0.1), ('l1 regularization', 0.2)],
+                                      [13, 13, 13])
+    L = P.gl_laplacian(13)
+    assert rel((2 * 0.5 / 2.0 * L + np.eye(13)) @ ops[0](X, 2.0), X) < 1e-13
+    assert abs(regs[1](X) - 0.1 * np.sum(X[-1] - X[0])) < 1e-12         # telescoping, no abs (constraints_to_prox.m:81)
+    assert abs(regs[2](X) - 0.2 * np.abs(X).sum()) < 1e-12
+    with pytest.raises(ValueError):
+        P.constraints_to_prox([1], [None], [3])
+
+
+def test_stopping_conditions_and_exit_flag():
+    o = dict(AbsFuncTol=1e-4, OuterRelTol=1e-8, MaxOuterIters=10)
+    assert evaluate_stopping_conditions(1e-5, 0, 0, 0, 1.0, 0, 0, 0, o)          # abs tol; zeros: abs change 0 < tol
+    assert not evaluate_stopping_conditions(0.5, 0, 0, 0, 1.0, 0, 0, 0, o)
+    assert evaluate_stopping_conditions(1.0, 0, 0, 0, 1.0 + 1e-9, 0, 0, 0, o)    # relative change
+    assert not evaluate_stopping_conditions(1.0, 0.5, 0, 0, 1.0, 0.0, 0, 0, o)   # f_old<=0 -> absolute change
+    assert make_exit_flag(11, 1, 1, 1, 1, o, 0) == 'maxIterations'
+    fl = make_exit_flag(5, 1e-5, 1, 1e-9, 0, o, 0)
+    assert fl == {'f_tensors': 'AbsFuncTol', 'f_couplings': 'RelFuncTol', 'f_constraints': 'AbsFuncTol',
+                  'f_PAR2_couplings': 'AbsFuncTol'}
+
+
+def test_par2_oracle_converges_noise_free():
+    Z, G, _ = pg.config_cp_par2(I=10, J=9, K=8, Jk=12, Kp=6, R=2, seed=1)
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(
+        MaxOuterIters=400, AbsFuncTol=1e-9, innerRelPrTol_coupl=1e-5, innerRelPrTol_constr=1e-5,
+        innerRelDualTol_coupl=1e-5, innerRelDualTol_constr=1e-5))
+    assert out['func_val_conv'][-1] < 1e-3 * out['func_val_conv'][0]
+    for k, Pk in enumerate(Gout['P'][1]):
+        assert rel(Pk.T @ Pk, np.eye(2)) < 1e-10                                   # P_k'P_k = I (:532-534)
+
+
+@pytest.mark.parametrize('name', ['script6_small', 'cp_matrix_small', 'cp_tv_small'])
+def test_oracle_reproduces_golden(name):
+    Z, G, opts, gold = golden_case(name)
+    Gout, out = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=opts)
+    assert out['OuterIterations'] == int(gold['OuterIterations'])
+    assert np.max(np.abs(out['func_val_conv'] - gold['func_val_conv'])) < 1e-12
+    for i, F in enumerate(Gout['fac']):
+        assert rel(F, gold['out_fac_%d' % i]) < 1e-10
+    assert np.array_equal(out['innerIters'], gold['innerIters'])
