@@ -354,8 +354,8 @@ __device__ void unimodal_serial(const double* y, double* x, long long n, bool no
 
 // Thomas algorithm for (I + 2*g*Lgl) x = v, Lgl = graph Laplacian of constraints_to_prox.m:71-73
 __device__ void gl_solve_serial(const double* v, double* x, long long n, double g, double* cp) {
-  if (n == 1) {
-    x[0] = v[0];
+  if (n == 1) {  // L = [1] (constraints_to_prox.m:71-73 with szm = 1)
+    x[0] = v[0] / (1.0 + 2.0 * g);
     return;
   }
   const double offd = -2.0 * g;

@@ -504,7 +504,7 @@ __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __re
           break;
         case RED_GLQUAD: {
           // (L x)_i with L = tridiag(-1, 2, -1), corners 1
-          double lx = 0.0;
+          double lx = v;  // rows == 1: L = [1]
           if (jb.rows > 1) {
             if (i == 0) lx = v - a[1];
             else if (i == jb.rows - 1) lx = v - a[i - 1];
