@@ -1,0 +1,34 @@
+"""torchrun --nproc-per-node N tools/dist_check.py : multi-GPU parity of the sharded engine with the oracle."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'matlab-code_b200'))
+import torch, torch.distributed as dist
+import aoadmm_b200 as ab
+from oracle import problem_gen as pg
+from oracle.cmtf_fun_aoadmm import cmtf_fun_AOADMM as oracle_solve
+
+rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE']); lr = int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(lr)
+dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
+def uid():
+    t = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    if rank == 0: t.copy_(torch.tensor(list(ab.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0); return bytes(t.cpu().tolist())
+ok = True
+for dims in [(64, 48, 40, 80, 8), (130, 90, 37, 100, 32), (40, 36, 30, 64, 64)]:
+    Z, G, _ = pg.config_cp_matrix(*dims, seed=1)
+    opts = pg.default_options(MaxOuterIters=20)
+    zn = pg.znorm_const(Z)
+    Gd, od = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts, rank=rank, world_size=world, device=lr, unique_id=uid())
+    if rank == 0:
+        Go, oo = oracle_solve(Z, zn, G, options=opts)
+        errs = [np.linalg.norm(Gd['fac'][m] - Go['fac'][m]) / np.linalg.norm(Go['fac'][m]) for m in range(5)]
+        print(dims, 'world', world, 'max fac err %.2e' % max(errs), 'df %.2e' % abs(od['f_tensors'] - oo['f_tensors']), 'iters', od['OuterIterations'], oo['OuterIterations'])
+        ok &= max(errs) < 1e-8
+    # all ranks must hold identical state
+    t = torch.from_numpy(np.ascontiguousarray(Gd['fac'][2])).cuda(); t0 = t.clone(); dist.broadcast(t0, 0)
+    same = bool(torch.equal(t, t0))
+    if not same: print('rank', rank, 'state differs from rank 0'); ok = False
+if rank == 0: print('DIST OK' if ok else 'DIST FAILED')
+dist.destroy_process_group()
