@@ -35,9 +35,12 @@ WORKLOADS = {
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool: profiles/r01_fp64_probe.log (DMMA.8x8x4 issue-rate probe)
 
 
+DIMTREE = int(os.environ.get('BENCH_DIMTREE', '1'))
+
+
 def zero_tol_options(iters):
     return dict(MaxOuterIters=iters, MaxInnerIters=5, AbsFuncTol=0.0, OuterRelTol=0.0, innerRelPrTol_coupl=0.0,
-                innerRelPrTol_constr=0.0, innerRelDualTol_coupl=0.0, innerRelDualTol_constr=0.0, bsum=0)
+                innerRelPrTol_constr=0.0, innerRelDualTol_coupl=0.0, innerRelDualTol_constr=0.0, bsum=0, dimtree=DIMTREE)
 
 
 def make_problem(I, J, K, M, R, seed=0, with_tensor=False):
@@ -179,7 +182,11 @@ def main():
     config = {'workload': 'CP %dx%dx%d R=%d nonneg + coupled %dx%d matrix (SURVEY 8d C3 family, K=%d so the FP64 tensor '
                           'fits one GPU), MaxInnerIters=5, all tolerances 0' % (I, J, K, R, I, M, K),
               'name': args.workload, 'sharding': 'mode-3 slabs over %d rank(s)' % world,
-              'l2_policy': 'inputs (%.1f GB tensor) far larger than the 126 MB L2' % (8.0 * I * J * K / 1e9)}
+              'l2_policy': 'inputs (%.1f GB tensor) far larger than the 126 MB L2' % (8.0 * I * J * K / 1e9),
+              'tensor_passes_per_step': 2 if DIMTREE else 3,
+              'dimtree': ('on: the mode-2 MTTKRP also emits T = X x_1 A (J x K x R), mode 3 is a pass over T; 2 tensor passes '
+                          'and 2/3 of the reference flops per step, results equal to rounding' if DIMTREE else
+                          'off: three independent MTTKRP passes (the reference flop/byte count)')}
 
     if args.impl == 'reference':
         if rank != 0:

@@ -248,6 +248,9 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   if (device_ >= ndev) throw CudaError(1, "device ordinal out of range");
   AO_CUDA(cudaSetDevice(device_));
   AO_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+  AO_CUDA(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
+  AO_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  AO_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
 
   nb_modes_ = prob->nb_modes;
   n_objects_ = prob->n_objects;
@@ -360,6 +363,8 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     dev_alloc(m.C, m.R, m.R);
     dev_alloc(m.B, m.R, m.R);
     dev_alloc(m.L, m.R, m.R);
+    dev_alloc(m.Binv, m.R, m.R);
+    dev_alloc(m.Btmp, m.R, m.R);
     dev_alloc(m.GtG, m.R, m.R);
     AO_CUDA(cudaMalloc(&m.invdiag, sizeof(double) * m.R));
     AO_CUDA(cudaMalloc(&m.rho, sizeof(double)));
@@ -446,12 +451,13 @@ Engine::~Engine() {
   if (st_) cudaStreamSynchronize(st_);
   if (comm_ && nccl_) nccl_->CommDestroy(static_cast<ncclComm_t>(comm_));
   for (auto& m : modes_) {
-    for (DevMat* d : {&m.fac, &m.Z, &m.muZ, &m.muD, &m.A, &m.Alast, &m.C, &m.B, &m.L, &m.GtG, &m.Znew, &m.V}) dev_free(*d);
+    for (DevMat* d : {&m.fac, &m.Z, &m.muZ, &m.muD, &m.A, &m.Alast, &m.C, &m.B, &m.L, &m.Binv, &m.Btmp, &m.GtG, &m.Znew, &m.V}) dev_free(*d);
     if (m.invdiag) cudaFree(m.invdiag);
     if (m.rho) cudaFree(m.rho);
   }
   for (auto& o : objects_) {
     if (o.data) cudaFree(o.data);
+    if (o.Tbuf) cudaFree(o.Tbuf);
     for (auto& v : o.views) {
       if (v.f0_own) packed_factor_free(v.f0);
       if (v.f1_own) packed_factor_free(v.f1);
@@ -460,7 +466,7 @@ Engine::~Engine() {
   for (auto& d : delta_) dev_free(d);
   for (void* p : {(void*)mws_.ws, (void*)gram_ws_, (void*)admm_partials_, (void*)admm_sums_, (void*)admm_counter_,
                   prox_scratch_, (void*)krtmp_[0], (void*)krtmp_[1], (void*)ctl_dev_, (void*)jobs_dev_,
-                  (void*)red_dev_, (void*)cp0_tmp_})
+                  (void*)red_dev_, (void*)red_partials_, (void*)cp0_tmp_})
     if (p) cudaFree(p);
   if (ctl_host_) cudaFreeHost(ctl_host_);
   if (red_host_) cudaFreeHost(red_host_);
@@ -470,6 +476,9 @@ Engine::~Engine() {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
+  if (st2_) cudaStreamDestroy(st2_);
   if (st_) cudaStreamDestroy(st_);
 }
 
@@ -600,12 +609,31 @@ void Engine::allreduce(double* buf, size_t count) {
 void Engine::compute_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout) {
   View3& v = o.views[pos];
   const int R = mode(o.modes[0]).R;
+  const bool last_sharded = o.sharded && o.order >= 3 && pos == o.order - 1;
+  // dimension tree (3-way CP objects): the mode-2 pass also emits T = X x_1 F1; while F1 is unchanged the mode-3
+  // MTTKRP is a cheap pass over T instead of a third pass over the tensor.
+  const bool tree = opt_.dimtree != 0 && o.order == 3;
+  const uint64_t v1 = mode(o.modes[0]).version;
+  if (tree && pos == 2 && o.Tbuf != nullptr && o.T_version == v1) {
+    phase_begin(0);
+    if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
+    const ModeState& mj = mode(o.modes[1]);
+    launches_ += mttkrp3_from_T(v.t, o.Tbuf, R, mj.fac.p, mj.rows, scale, out + v.out_offset, ldout, st_, nullptr);
+    if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
+    phase_end();
+    return;
+  }
+  double* emit = nullptr;
+  if (tree && pos == 1) {
+    if (o.Tbuf == nullptr) AO_CUDA(cudaMalloc(&o.Tbuf, mttkrp_T_bytes(v.t, R)));
+    emit = o.Tbuf;
+    o.T_version = v1;
+  }
   pack_operand(v, 0);
   pack_operand(v, 1);
   phase_begin(o.order >= 3 ? 0 : 1);
-  const bool last_sharded = o.sharded && o.order >= 3 && pos == o.order - 1;
   if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
-  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr);
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit);
   if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
   phase_end();
 }
@@ -616,7 +644,6 @@ void Engine::refresh_gram(ModeState& m) {
 
 void Engine::precompute_mode(ModeState& m, int n_rho_terms, bool do_chol) {
   ObjectState& o = objects_[m.p];
-  compute_mttkrp(o, m.pos, o.weight, m.A.p, m.rows);  // A{m} = w * mttkrp (:97, :108, :111)
   PrepArgs a{};
   a.nhad = 0;
   for (int d = 0; d < o.order; ++d)
@@ -633,9 +660,18 @@ void Engine::precompute_mode(ModeState& m, int n_rho_terms, bool do_chol) {
   a.B = m.B.p;
   a.L = m.L.p;
   a.invdiag = m.invdiag;
+  a.Binv = m.Binv.p;
+  a.Btmp = m.Btmp.p;
   a.rho = m.rho;
   a.ctl = m.ctl;
-  launches_ += prep_system(a, st_, nullptr);
+  // the system preparation depends only on the Grams of the other modes: run it on the side stream while the
+  // MTTKRP of this mode streams the tensor on the main stream
+  AO_CUDA(cudaEventRecord(ev_fork_, st_));
+  AO_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+  launches_ += prep_system(a, st2_, nullptr);
+  AO_CUDA(cudaEventRecord(ev_join_, st2_));
+  compute_mttkrp(o, m.pos, o.weight, m.A.p, m.rows);  // A{m} = w * mttkrp (:97, :108, :111)
+  AO_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
   if (opt_.bsum) {  // :124-127 (last_mttkrp keeps the value before the BSUM term, :121)
     AO_CUDA(cudaMemcpyAsync(m.Alast.p, m.A.p, m.A.bytes(), cudaMemcpyDeviceToDevice, st_));
     const long long n = m.rows * m.R;
@@ -658,8 +694,7 @@ void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadm
     ModeState& m = *group[i];
     AdmmMode& am = g.m[i];
     am.A = m.A.p;
-    am.L = m.L.p;
-    am.invdiag = m.invdiag;
+    am.Binv = m.Binv.p;
     am.rho = m.rho;
     am.F = m.fac.p;
     am.Z = m.Z.p;
@@ -673,6 +708,7 @@ void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadm
     am.p1 = m.con.p1;
     if (m.constrained && !prox_is_elementwise(m.con.kind)) deferred.push_back(i);
   }
+  for (ModeState* mp : group) ++mp->version;
   InnerCtl* ctl = group[0]->ctl;
   InnerTol tol{opt.innerRelPrTol_coupl, opt.innerRelDualTol_coupl, opt.innerRelPrTol_constr, opt.innerRelDualTol_constr};
   for (int it = 0; it < opt.MaxInnerIters; ++it) {
@@ -737,6 +773,7 @@ void Engine::build_objective_jobs() {
   AO_CUDA(cudaMemcpy(jobs_dev_, jobs_host_.data(), sizeof(RedJob) * nj, cudaMemcpyHostToDevice));
   AO_CUDA(cudaMalloc(&red_dev_, sizeof(double) * (nj + 8)));
   AO_CUDA(cudaMallocHost(&red_host_, sizeof(double) * (nj + 8)));
+  AO_CUDA(cudaMalloc(&red_partials_, sizeof(double) * reduce_ws_doubles((int)nj + 8)));
 }
 
 void Engine::eval_objective(bool first, double f[4]) {
@@ -777,14 +814,14 @@ void Engine::eval_objective(bool first, double f[4]) {
       jb[1].a = scr;
       jb[1].b = nullptr;
       AO_CUDA(cudaMemcpyAsync(jobs_dev_ + nj, jb, sizeof(jb), cudaMemcpyHostToDevice, st_));
-      launches_ += reduce_jobs(jobs_dev_ + nj, 2, red_dev_ + nj, st_, nullptr);
+      launches_ += reduce_jobs(jobs_dev_ + nj, 2, red_dev_ + nj, red_partials_, admm_counter_, st_, nullptr);
       double r2[2];
       AO_CUDA(cudaMemcpyAsync(r2, red_dev_ + nj, sizeof(r2), cudaMemcpyDeviceToHost, st_));
       AO_CUDA(cudaStreamSynchronize(st_));
       f_obj[p] = o.weight * (o.znorm - 2.0 * r2[0] + r2[1]);
     }
   }
-  launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, st_, nullptr);
+  launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, red_partials_, admm_counter_, st_, nullptr);
   AO_CUDA(cudaMemcpyAsync(red_host_, red_dev_, sizeof(double) * nj, cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaMemcpyAsync(ctl_host_, ctl_dev_, sizeof(InnerCtl) * n_ctl_, cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
@@ -866,6 +903,7 @@ void Engine::set_state(int field, int index, int slice, const double* data, int6
                            std::to_string(d->cols));
   AO_CUDA(cudaMemcpyAsync(d->p, data, d->bytes(), cudaMemcpyHostToDevice, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
+  if (field == AOADMM_FIELD_FAC) ++modes_[index - 1].version;
 }
 
 void Engine::get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols) {
@@ -1000,6 +1038,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
               precompute_mode(m, 0, true);
               launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :134
               inner_fixed[m.id - 1] = 1;
+              ++m.version;
             } else {
               precompute_mode(m, 1, true);                           // :141-142
               std::vector<ModeState*> g1{&m};
@@ -1100,6 +1139,7 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   AO_CUDA(cudaStreamSynchronize(st_));
   launches_ += 3;
   o.znorm = 1.0;
+  o.T_version = 0;  // cached partial contractions refer to the old data
   for (auto p : tmp) cudaFree(p);
   cudaFree(sums);
 }

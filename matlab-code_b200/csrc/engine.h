@@ -31,12 +31,13 @@ struct ModeState {
   aoadmm_constraint con{};
   double ridge = 0.0;
   DevMat fac, Z, muZ, muD;    // G.fac, G.constraint_fac, G.constraint_dual_fac, G.coupling_dual_fac
-  DevMat A, Alast, C, B, L, GtG, Znew, V;
+  DevMat A, Alast, C, B, L, Binv, Btmp, GtG, Znew, V;
   double* invdiag = nullptr;
   double* rho = nullptr;      // device scalar
   PackedFactor packed;        // transposed copy used as DMMA B operand
   InnerCtl* ctl = nullptr;    // device; for coupled modes all modes of the group share the group's block
   int ctl_index = -1;
+  uint64_t version = 1;       // bumped whenever fac changes (validity stamp for cached partial contractions)
 };
 
 struct View3 {                // how mode position n of an object is computed
@@ -62,6 +63,8 @@ struct ObjectState {
   bool sharded = false;
   std::vector<View3> views;   // one per mode position
   int last_m = 0;             // global id of the mode updated last in a sweep (static)
+  double* Tbuf = nullptr;     // dimension tree: T(j,k,r) = sum_i X(i,j,k) F1(i,r), emitted by the mode-2 MTTKRP
+  uint64_t T_version = 0;     // version of the mode-1 factor T was computed from (0 = invalid)
 };
 
 class Engine {
@@ -109,6 +112,8 @@ class Engine {
 
   // scratch
   cudaStream_t st_ = nullptr;
+  cudaStream_t st2_ = nullptr;   // side stream: system preparation overlaps the MTTKRP of the same mode
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   MttkrpWorkspace mws_;
   double* gram_ws_ = nullptr;
   double* admm_partials_ = nullptr;
@@ -124,6 +129,7 @@ class Engine {
   std::vector<RedJob> jobs_host_;
   RedJob* jobs_dev_ = nullptr;
   double* red_dev_ = nullptr;
+  double* red_partials_ = nullptr;
   double* red_host_ = nullptr;  // pinned
   struct ObjTerms;
   std::unique_ptr<ObjTerms> terms_;

@@ -25,6 +25,8 @@
 
 namespace aoadmm {
 
+int64_t mttkrp_T_ld(const Tensor3& t);
+
 namespace {
 
 constexpr int kConsumerWarps = 8;
@@ -202,11 +204,14 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
 // EPI = 0: ws[(split*Rp + r)*ldo + j]   = sum_{k in range} Fe(k,r) * T(j,k,r)      (Fe = packed k factor)
 // EPI = 1: ws[(jt*Rp + r)*ldo + k]      = sum_{j in tile}  Fe(j,r) * T(j,k,r)      (Fe = packed j factor)
 // ---------------------------------------------------------------------------------------------
-template <int NT, int WARPS_N, int EPI>
+// EMIT (epilogue 0 only): additionally stores the un-scaled partial contraction T(j,k,r) = sum_i X(i,j,k) Fi(i,r)
+//          to Tbuf[(k*Rp + r)*ldt + j]; a later mode-3 MTTKRP is then a cheap pass over T (dimension tree).
+template <int NT, int WARPS_N, int EPI, bool EMIT>
 __global__ void __launch_bounds__(kThreads, 1)
 mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Ft_i,
                     const double* __restrict__ Ft_e, double* __restrict__ ws, int I, int J, int K, long long Ipad,
-                    long long Epad, int nit, int nsplit, long long ldo, int Rp_total, const int* __restrict__ skip) {
+                    long long Epad, int nit, int nsplit, long long ldo, int Rp_total, double* __restrict__ Tbuf,
+                    long long ldt, const int* __restrict__ skip) {
   using C = Cfg<NT, WARPS_N>;
   if (skip != nullptr && *skip != 0) return;
   extern __shared__ uint8_t smem_raw[];
@@ -313,6 +318,42 @@ mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __re
     }
     // ---- per-(j tile, k) epilogue
     if (EPI == 0) {
+      if (EMIT) {
+        double* sc = reinterpret_cast<double*>(smem_raw + (sS - smem_u32(smem_raw)));
+        const int slot = wm * 32 + lane;
+        if (C::KSPLIT == 2) {
+          if (hi == 1) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) {
+                sc[((mi * NT + nt) * 2 + 0) * 128 + slot] = T[mi][nt][0];
+                sc[((mi * NT + nt) * 2 + 1) * 128 + slot] = T[mi][nt][1];
+              }
+          }
+          named_bar_sync(1, kConsumerWarps * 32);
+        }
+        if (C::KSPLIT == 1 || hi == 0) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            const int j = jt * 128 + jrow[mi];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              double t0 = T[mi][nt][0], t1 = T[mi][nt][1];
+              if (C::KSPLIT == 2) {
+                t0 += sc[((mi * NT + nt) * 2 + 0) * 128 + slot];
+                t1 += sc[((mi * NT + nt) * 2 + 1) * 128 + slot];
+              }
+              if (j < J) {
+                const long long r = (long long)chunk * C::NC + ccol + 8 * nt;
+                Tbuf[((long long)k * Rp_total + r) * ldt + j] = t0;
+                Tbuf[((long long)k * Rp_total + r + 1) * ldt + j] = t1;
+              }
+            }
+          }
+        }
+        if (C::KSPLIT == 2) named_bar_sync(1, kConsumerWarps * 32);
+      }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const double2 c = *reinterpret_cast<const double2*>(Ft_e + ((long long)chunk * Epad + k) * C::LDC + ccol + 8 * nt);
@@ -407,6 +448,31 @@ __global__ void mttkrp_reduce_kernel(const double* __restrict__ ws, int nsplit, 
   double v = 0.0;
   for (int s = 0; s < nsplit; ++s) v += ws[((long long)s * Rp_total + r) * ldo + row];
   out[(long long)r * ldout + row] = scale * v;
+}
+
+// mode-3 MTTKRP from the cached partial contraction: out(k,r) = scale * sum_j T[(k*Rp + r)*ldt + j] * Fj(j,r)
+// one warp per (k, r); lanes stride over j (coalesced in T and in the column-major factor).
+__global__ void mttkrp_from_T_kernel(const double* __restrict__ Tbuf, long long ldt, int Rp_total, int J, int K, int R,
+                                     const double* __restrict__ Fj, long long ldf, double scale,
+                                     double* __restrict__ out, long long ldout, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x;
+  const int r = blockIdx.y * 8 + warp;
+  if (r >= R) return;
+  const double* trow = Tbuf + ((long long)k * Rp_total + r) * ldt;
+  const double* frow = Fj + (long long)r * ldf;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = lane;
+  for (; j + 96 < J; j += 128) {
+    a0 = fma(trow[j], frow[j], a0);
+    a1 = fma(trow[j + 32], frow[j + 32], a1);
+    a2 = fma(trow[j + 64], frow[j + 64], a2);
+    a3 = fma(trow[j + 96], frow[j + 96], a3);
+  }
+  for (; j < J; j += 32) a0 = fma(trow[j], frow[j], a0);
+  const double v = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) out[(long long)r * ldout + k] = scale * v;
 }
 
 __global__ void pack_factor_kernel(double* __restrict__ dst, long long rows_pad, int ldc, int NC, int nchunk,
@@ -532,9 +598,9 @@ int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk
   return 2;
 }
 
-template <int NT, int WARPS_N, int EPI>
+template <int NT, int WARPS_N, int EPI, bool EMIT>
 int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& fe, int R, double scale, double* out,
-                 int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip) {
+                 int64_t ldout, const MttkrpWorkspace& w, double* Tbuf, cudaStream_t st, const int* skip) {
   using C = Cfg<NT, WARPS_N>;
   const int jtiles = (int)ceil_div(t.J, 128), nit = (int)ceil_div(t.I, 32), nchunk = fi.nchunk;
   const int nsplit = choose_splits((long long)jtiles * nchunk, t.K);
@@ -543,7 +609,7 @@ int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& f
   const long long ldo = round_up(rows, 2);
   const int nparts = (EPI == 0) ? nsplit : jtiles;
   if ((size_t)nparts * Rp_total * ldo * 8 > w.ws_bytes) throw CudaError(1, "mttkrp workspace too small (inner)");
-  auto kern = mttkrp_inner_kernel<NT, WARPS_N, EPI>;
+  auto kern = mttkrp_inner_kernel<NT, WARPS_N, EPI, EMIT>;
   static bool attr_done = false;
   if (!attr_done) {
     AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -551,7 +617,8 @@ int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& f
   }
   dim3 grid(jtiles, nsplit, nchunk);
   kern<<<grid, kThreads, C::SMEM, st>>>(t.map_inner, fi.data, fe.data, w.ws, (int)t.I, (int)t.J, (int)t.K,
-                                        (long long)fi.rows_pad, (long long)fe.rows_pad, nit, nsplit, ldo, Rp_total, skip);
+                                        (long long)fi.rows_pad, (long long)fe.rows_pad, nit, nsplit, ldo, Rp_total, Tbuf,
+                                        (long long)mttkrp_T_ld(t), skip);
   AO_CHECK_LAUNCH();
   dim3 rgrid((unsigned)ceil_div(rows, 128), R);
   mttkrp_reduce_kernel<<<rgrid, 128, 0, st>>>(w.ws, nparts, Rp_total, ldo, rows, R, scale, out, ldout, skip);
@@ -616,15 +683,36 @@ size_t mttkrp_workspace_bytes(const Tensor3& t, int R) {
   return (size_t)parts * Rp * maxdim * 8;
 }
 
+int64_t mttkrp_T_ld(const Tensor3& t) { return round_up(t.J, 2); }
+
+size_t mttkrp_T_bytes(const Tensor3& t, int R) {
+  const int NC = mttkrp_chunk_cols(R);
+  const long long Rp = ceil_div(R, NC) * NC;
+  return (size_t)t.K * Rp * mttkrp_T_ld(t) * sizeof(double);
+}
+
+int mttkrp3_from_T(const Tensor3& t, const double* Tbuf, int R, const double* Fj, int64_t ldf, double scale,
+                   double* out, int64_t ldout, cudaStream_t st, const int* skip) {
+  const int NC = mttkrp_chunk_cols(R);
+  const int Rp = (int)(ceil_div(R, NC) * NC);
+  dim3 grid((unsigned)t.K, (unsigned)ceil_div(R, 8));
+  mttkrp_from_T_kernel<<<grid, 256, 0, st>>>(Tbuf, mttkrp_T_ld(t), Rp, (int)t.J, (int)t.K, R, Fj, ldf, scale, out, ldout,
+                                             skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
 int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFactor& f1, int R, double scale,
-            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip) {
+            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip, double* Tbuf) {
   const int NC = mttkrp_chunk_cols(R);
   if (f0.NC != NC || f1.NC != NC || f0.R != R || f1.R != R) throw CudaError(1, "packed factor / rank mismatch");
-#define AO_DISPATCH(NT, WNN)                                                                              \
-  do {                                                                                                    \
-    if (pos == 0) return launch_lead<NT, WNN>(t, f0, f1, R, scale, out, ldout, w, st, skip);              \
-    if (pos == 1) return launch_inner<NT, WNN, 0>(t, f0, f1, R, scale, out, ldout, w, st, skip);          \
-    return launch_inner<NT, WNN, 1>(t, f0, f1, R, scale, out, ldout, w, st, skip);                        \
+#define AO_DISPATCH(NT, WNN)                                                                                       \
+  do {                                                                                                             \
+    if (pos == 0) return launch_lead<NT, WNN>(t, f0, f1, R, scale, out, ldout, w, st, skip);                       \
+    if (pos == 1 && Tbuf != nullptr)                                                                               \
+      return launch_inner<NT, WNN, 0, true>(t, f0, f1, R, scale, out, ldout, w, Tbuf, st, skip);                   \
+    if (pos == 1) return launch_inner<NT, WNN, 0, false>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);   \
+    return launch_inner<NT, WNN, 1, false>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);                 \
   } while (0)
   switch (NC) {
     case 8: AO_DISPATCH(1, 1);

@@ -58,7 +58,14 @@ size_t mttkrp_workspace_bytes(const Tensor3& t, int R);
 // The two factors are passed in packed form in natural order (for pos=0: Fj,Fk; pos=1: Fi,Fk; pos=2: Fi,Fj).
 // `accumulate` adds into out instead of overwriting (used by nobody on the reference path).
 // Returns the number of kernel launches issued.
+// Tbuf != nullptr with pos == 1 additionally emits the partial contraction T(j,k,r) = sum_i X(i,j,k) F0(i,r)
+// (mttkrp_T_bytes bytes) for a later mttkrp3_from_T (dimension-tree reuse: one tensor pass serves modes 2 and 3).
 int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFactor& f1, int R, double scale,
-            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip);
+            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip,
+            double* Tbuf = nullptr);
+size_t mttkrp_T_bytes(const Tensor3& t, int R);
+// out(k,r) = scale * sum_j T(j,k,r) * Fj(j,r)   (Fj: J x R column-major, leading dimension ldf)
+int mttkrp3_from_T(const Tensor3& t, const double* Tbuf, int R, const double* Fj, int64_t ldf, double scale,
+                   double* out, int64_t ldout, cudaStream_t st, const int* skip);
 
 }  // namespace aoadmm

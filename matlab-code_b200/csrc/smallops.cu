@@ -19,7 +19,7 @@ namespace {
 // =====================================================================================================
 // Gram
 // =====================================================================================================
-constexpr int kGramChunk = 2048;
+constexpr int kGramChunk = 256;
 
 __global__ void gram_partial_kernel(const double* __restrict__ F, long long rows, long long ld, int R,
                                     double* __restrict__ ws, const int* __restrict__ skip) {
@@ -138,6 +138,43 @@ __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const i
       a.L[e] = v;
       if (ri == ci) a.invdiag[ri] = 1.0 / v;
     }
+    if (a.Binv != nullptr && s_err == 0) {
+      // inv(L): thread c owns column c (forward substitution of L x = e_c); V(i,c) kept in V[i + c*R]
+      double* V = use_smem ? (S + RR) : a.Binv;
+      __syncthreads();
+      // V(i,c) lives at V[i*R + c]: the loops are uniform across threads (rows above the diagonal come out as
+      // exact zeros), so L is read as a broadcast and V without bank conflicts.
+      for (int c = tid; c < R; c += nt) {
+        for (int i2 = 0; i2 < R; ++i2) {
+          double sacc = (i2 == c) ? 1.0 : 0.0;
+          for (int k = 0; k < i2; ++k) sacc = fma(-W[k * R + i2], V[k * R + c], sacc);
+          V[i2 * R + c] = sacc / W[i2 * R + i2];
+        }
+      }
+      __syncthreads();
+      // inv(B) = inv(L)' * inv(L)
+      if (use_smem) {
+        for (int e = tid; e < RR; e += nt) {
+          const int ca = e / R, cb = e % R;
+          const int lo = ca > cb ? ca : cb;
+          double acc = 0.0;
+          for (int i2 = lo; i2 < R; ++i2) acc = fma(V[i2 * R + ca], V[i2 * R + cb], acc);
+          a.Binv[e] = acc;
+        }
+      } else {
+        // large R: V aliases a.Binv, so form the product into the scratch matrix first
+        double* T = a.Btmp;
+        for (int e = tid; e < RR; e += nt) {
+          const int ca = e / R, cb = e % R;
+          const int lo = ca > cb ? ca : cb;
+          double acc = 0.0;
+          for (int i2 = lo; i2 < R; ++i2) acc = fma(V[i2 * R + ca], V[i2 * R + cb], acc);
+          T[e] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < RR; e += nt) a.Binv[e] = T[e];
+      }
+    }
   }
   if (tid == 0 && a.ctl != nullptr) {
     a.ctl->done = 0;
@@ -231,58 +268,93 @@ __device__ __forceinline__ void solve_row(double* row_s, int BT, int R, const do
   }
 }
 
-template <bool LSMEM>
-__global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl* ctl, double* sums, double* partials,
-                                unsigned* counter, int finalize) {
+// One inner ADMM iteration for a tile of 32 rows (lanes) x all R columns (warp w owns columns 8w..8w+7):
+//   per mode:  A_inner = A + rho/2 (Delta - muD) + rho/2 (Z - muZ)            (:608, :647-650)
+//              F = A_inner * inv(B)                                           (:609, :651  (A_inner/L')/L)
+//   Delta = sum_m rho_m (F_m + muD_m) / sum_m rho_m                            (:661-675)
+//   muD_m += F_m - Delta ; Z_m = prox(F_m + muZ_m) ; muZ_m += F_m - Z_m        (:679-682, :1420-1429)
+//   residual norms (:1079-1115) reduced deterministically; the last CTA evaluates the while-condition.
+// inv(B) is formed once per outer iteration by prep_system (B = w*C + n*rho/2*I has cond(B) <= 1 + 2wR/n, so the
+// explicit inverse is as accurate as the two triangular solves it replaces and turns the solve into a GEMM tile).
+template <bool BSMEM>
+__global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl* ctl, double* sums, double* partials,
+                                 unsigned* counter, int finalize) {
   if (ctl->done != 0) return;
   extern __shared__ double sm[];
   __shared__ double red[32];
   __shared__ bool s_last;
-  const int BT = blockDim.x, tid = threadIdx.x, R = g.R;
-  double* row_s = sm + tid;              // [R][BT]
-  double* dsum_s = sm + (size_t)R * BT + tid;  // [R][BT]
-  double* Ls = sm + (size_t)2 * R * BT;  // [R*R] (LSMEM)
-  double* invd_s = Ls + (LSMEM ? R * R : 0);
-  const long long i = (long long)blockIdx.x * BT + tid;
+  const int R = g.R, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthreads = blockDim.x;
+  double* a_s = sm;                      // [R][32]
+  double* Binv_s = sm + (size_t)R * 32;  // [R*R] when BSMEM
+  const long long i = (long long)blockIdx.x * 32 + lane;
   const bool active = i < g.rows;
+  const int e0 = w * 8;
   const int NS = 6 * g.nmodes + 1;
   double lsum[6 * kMaxGroup + 1];
   for (int s = 0; s < NS; ++s) lsum[s] = 0.0;
   const bool coupled = g.Delta != nullptr;
+  double dsum[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dsum[c] = 0.0;
   double sum_rho = 0.0;
-
-  if (coupled)
-    for (int e = 0; e < R; ++e) dsum_s[e * BT] = 0.0;
 
   for (int mi = 0; mi < g.nmodes; ++mi) {
     const AdmmMode& md = g.m[mi];
     const double rho = *md.rho;
     const double half = rho / 2.0;
     sum_rho += rho;
-    const double* L = md.L;
-    const double* invd = md.invdiag;
-    if (LSMEM) {
-      __syncthreads();
-      for (int e = tid; e < R * R; e += BT) Ls[e] = md.L[e];
-      for (int e = tid; e < R; e += BT) invd_s[e] = md.invdiag[e];
-      __syncthreads();
-      L = Ls;
-      invd = invd_s;
+    __syncthreads();  // previous mode's GEMM has finished reading a_s / Binv_s
+    if (BSMEM)
+      for (int e = tid; e < R * R; e += nthreads) Binv_s[e] = md.Binv[e];
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int e = e0 + c;
+        if (e < R) {
+          const long long idx = (long long)e * g.rows + i;
+          double a = md.A[(long long)e * md.ldA + i];
+          if (coupled) a += half * (g.Delta[idx] - md.muD[idx]);
+          if (md.constrained) a += half * (md.Z[idx] - md.muZ[idx]);
+          a_s[e * 32 + lane] = a;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (e0 + c < R) a_s[(e0 + c) * 32 + lane] = 0.0;
+    }
+    __syncthreads();
+    double x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = 0.0;
+    if (BSMEM && e0 + 8 <= R) {
+      const double* bp = Binv_s + e0;
+#pragma unroll 4
+      for (int j = 0; j < R; ++j) {
+        const double aj = a_s[j * 32 + lane];
+        const double* br = bp + (size_t)j * R;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = fma(aj, br[c], x[c]);
+      }
+    } else {
+      const double* B0 = BSMEM ? Binv_s : md.Binv;
+      for (int j = 0; j < R; ++j) {
+        const double aj = a_s[j * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (e0 + c < R) x[c] = fma(aj, B0[(size_t)j * R + e0 + c], x[c]);
+      }
     }
     if (active) {
-      for (int e = 0; e < R; ++e) {
-        double a = md.A[(long long)e * md.ldA + i];
-        if (coupled) a += half * (g.Delta[(long long)e * g.rows + i] - md.muD[(long long)e * g.rows + i]);
-        if (md.constrained) a += half * (md.Z[(long long)e * g.rows + i] - md.muZ[(long long)e * g.rows + i]);
-        row_s[e * BT] = a;
-      }
-      solve_row(row_s, BT, R, L, invd);
       double sF2 = 0.0;
-      for (int e = 0; e < R; ++e) {
-        const double x = row_s[e * BT];
-        md.F[(long long)e * md.ldF + i] = x;
-        sF2 = fma(x, x, sF2);
-        if (coupled) dsum_s[e * BT] += rho * (x + md.muD[(long long)e * g.rows + i]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int e = e0 + c;
+        if (e < R) {
+          md.F[(long long)e * md.ldF + i] = x[c];
+          sF2 = fma(x[c], x[c], sF2);
+          if (coupled) dsum[c] += rho * (x[c] + md.muD[(long long)e * g.rows + i]);
+        }
       }
       lsum[6 * mi + 0] = sF2;
     }
@@ -292,13 +364,17 @@ __global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl
     if (coupled) {
       const double inv = 1.0 / sum_rho;
       double sDD = 0.0;
-      for (int e = 0; e < R; ++e) {
-        const double dn = inv * dsum_s[e * BT];
-        const double dold = g.Delta[(long long)e * g.rows + i];
-        g.Delta[(long long)e * g.rows + i] = dn;
-        dsum_s[e * BT] = dn;
-        const double df = dn - dold;
-        sDD = fma(df, df, sDD);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int e = e0 + c;
+        if (e < R) {
+          const long long idx = (long long)e * g.rows + i;
+          const double dn = inv * dsum[c];
+          const double df = dn - g.Delta[idx];
+          g.Delta[idx] = dn;
+          dsum[c] = dn;
+          sDD = fma(df, df, sDD);
+        }
       }
       lsum[6 * g.nmodes] = sDD;
     }
@@ -307,18 +383,21 @@ __global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl
       const double rho = *md.rho;
       double sFD = 0.0, sMuD = 0.0, sFZ = 0.0, sZZ = 0.0, sMuZ = 0.0;
       const bool do_con = md.constrained && prox_is_elementwise(md.prox_kind);
-      for (int e = 0; e < R; ++e) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int e = e0 + c;
+        if (e >= R) continue;
+        const long long idx = (long long)e * g.rows + i;
         const double x = md.F[(long long)e * md.ldF + i];
         if (coupled) {
-          const double dn = dsum_s[e * BT];
-          const double mu = md.muD[(long long)e * g.rows + i] + x - dn;
-          md.muD[(long long)e * g.rows + i] = mu;
+          const double dn = dsum[c];
+          const double mu = md.muD[idx] + x - dn;
+          md.muD[idx] = mu;
           const double fd = x - dn;
           sFD = fma(fd, fd, sFD);
           sMuD = fma(mu, mu, sMuD);
         }
         if (do_con) {
-          const long long idx = (long long)e * g.rows + i;
           const double muz = md.muZ[idx];
           const double zold = md.Z[idx];
           const double z = prox_elem(md.prox_kind, x + muz, md.p0, md.p1, rho);
@@ -352,10 +431,10 @@ __global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int s = tid; s < NS; s += BT) {
-      const int mi = s / 6, w = s % 6;
+    for (int s = tid; s < NS; s += nthreads) {
+      const int mi = s / 6, ww = s % 6;
       // sums owned by a deferred (non element-wise) constraint update are left untouched
-      const bool deferred = (s < 6 * g.nmodes) && (w >= 3) && g.m[mi].constrained &&
+      const bool deferred = (s < 6 * g.nmodes) && (ww >= 3) && g.m[mi].constrained &&
                             !prox_is_elementwise(g.m[mi].prox_kind);
       if (deferred) continue;
       double v = 0.0;
@@ -369,7 +448,6 @@ __global__ void admm_row_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl
     }
   }
 }
-
 
 // deferred constraint update for a mode whose prox is not element-wise
 __global__ void admm_constraint_update_kernel(AdmmGroup g, int which, const double* __restrict__ Znew, FinInfo fin,
@@ -463,34 +541,28 @@ __global__ void ls_solve_kernel(const double* __restrict__ A, long long ldA, con
 // =====================================================================================================
 // reductions: one CTA per job
 // =====================================================================================================
+constexpr int kRedSplit = 8;
+
+// one job = sum over columns of a per-column quantity; CTA (job, y) handles columns y, y+kRedSplit, ...;
+// the last CTA adds the kRedSplit partials of every job in fixed order (deterministic).
 __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __restrict__ results,
-                                   const int* __restrict__ skip) {
+                                   double* __restrict__ partials, unsigned* counter, const int* __restrict__ skip) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ double red[32];
+  __shared__ bool s_last;
   const RedJob jb = jobs[blockIdx.x];
   const int tid = threadIdx.x, nt = blockDim.x;
-  double acc = 0.0;
-  if (jb.kind == RED_COLNORM) {
-    for (int c = 0; c < jb.cols; ++c) {
-      double s = 0.0;
-      for (long long i = tid; i < jb.rows; i += nt) {
-        const double v = jb.a[(long long)c * jb.lda + i];
-        s = fma(v, v, s);
-      }
-      s = block_sum(s, red);
-      if (tid == 0) acc += sqrt(s);
-    }
-    if (tid == 0) results[blockIdx.x] = acc;
-    return;
-  }
-  for (int c = 0; c < jb.cols; ++c) {
+  double total = 0.0;  // valid in thread 0
+  for (int c = blockIdx.y; c < jb.cols; c += kRedSplit) {
     const double* a = jb.a + (long long)c * jb.lda;
     const double* b = (jb.b != nullptr) ? jb.b + (long long)c * jb.ldb : nullptr;
+    double acc = 0.0;
     for (long long i = tid; i < jb.rows; i += nt) {
       const double v = a[i];
       switch (jb.kind) {
         case RED_DOT: acc = fma(v, b[i], acc); break;
-        case RED_NORM2: acc = fma(v, v, acc); break;
+        case RED_NORM2:
+        case RED_COLNORM: acc = fma(v, v, acc); break;
         case RED_DIFF2: {
           const double d = v - b[i];
           acc = fma(d, d, acc);
@@ -516,9 +588,25 @@ __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __re
         default: break;
       }
     }
+    acc = block_sum(acc, red);
+    if (tid == 0) total += (jb.kind == RED_COLNORM) ? sqrt(acc) : acc;
   }
-  acc = block_sum(acc, red);
-  if (tid == 0) results[blockIdx.x] = acc;
+  if (tid == 0) partials[blockIdx.x * kRedSplit + blockIdx.y] = total;
+  __threadfence();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = tid; j < (int)gridDim.x; j += nt) {
+      double v = 0.0;
+      for (int y = 0; y < kRedSplit; ++y) v += partials[j * kRedSplit + y];
+      results[j] = v;
+    }
+    if (tid == 0) *counter = 0u;
+  }
 }
 
 }  // namespace
@@ -540,7 +628,15 @@ int gram(const double* F, int64_t rows, int64_t ld, int R, double* G, double* ws
 }
 
 int prep_system(const PrepArgs& a, cudaStream_t st, const int* skip) {
-  const size_t smem = (a.R <= 64) ? (size_t)a.R * a.R * sizeof(double) : 0;
+  const size_t smem = (a.R <= 64) ? (size_t)2 * a.R * a.R * sizeof(double) : 0;
+  if (smem > 40 * 1024) {
+    static bool done = false;
+    if (!done) {
+      AO_CUDA(cudaFuncSetAttribute(prep_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
+      done = true;
+    }
+  }
+  if (a.Binv != nullptr && a.R > 64 && a.Btmp == nullptr) throw CudaError(1, "prep_system: Btmp scratch required for R > 64");
   prep_system_kernel<<<1, 256, smem, st>>>(a, skip);
   AO_CHECK_LAUNCH();
   return 1;
@@ -568,27 +664,29 @@ FinInfo make_fin(const AdmmGroup& g) {
 }
 template <typename K>
 void set_smem(K kern, size_t smem) {
-  if (smem > 48 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 }  // namespace
 
 size_t admm_ws_doubles(long long rows, int R, int nmodes) {
-  const RowLaunch c = row_launch_cfg(R, 2);
-  const size_t ctas_row = (size_t)ceil_div(std::max<long long>(rows, 1), c.BT);
+  (void)R;
+  const size_t ctas_row = (size_t)ceil_div(std::max<long long>(rows, 1), 32);
   return std::max<size_t>(ctas_row * (6 * nmodes + 1), (size_t)148 * 8 * 3) + 16;
 }
 
 int admm_iteration(const AdmmGroup& g, const InnerTol& tol, InnerCtl* ctl, double* sums, double* partials,
                    unsigned* counter, int finalize, cudaStream_t st) {
-  const RowLaunch c = row_launch_cfg(g.R, 2);
-  const unsigned ctas = (unsigned)ceil_div(std::max<long long>(g.rows, 1), c.BT);
+  const int nw = (int)ceil_div(g.R, 8);
+  const unsigned ctas = (unsigned)ceil_div(std::max<long long>(g.rows, 1), 32);
+  const bool bsmem = g.R <= 64;
+  const size_t smem = ((size_t)g.R * 32 + (bsmem ? (size_t)g.R * g.R : 0)) * sizeof(double);
   const FinInfo fin = make_fin(g);
-  if (c.lsmem) {
-    set_smem(admm_row_kernel<true>, c.smem);
-    admm_row_kernel<true><<<ctas, c.BT, c.smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
+  if (bsmem) {
+    set_smem(admm_tile_kernel<true>, smem);
+    admm_tile_kernel<true><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
   } else {
-    set_smem(admm_row_kernel<false>, c.smem);
-    admm_row_kernel<false><<<ctas, c.BT, c.smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
+    set_smem(admm_tile_kernel<false>, smem);
+    admm_tile_kernel<false><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
   }
   AO_CHECK_LAUNCH();
   return 1;
@@ -628,9 +726,13 @@ int ls_solve(const double* A, long long ldA, const double* L, const double* invd
   return 1;
 }
 
-int reduce_jobs(const RedJob* jobs_dev, int njobs, double* results_dev, cudaStream_t st, const int* skip) {
+size_t reduce_ws_doubles(int njobs) { return (size_t)njobs * kRedSplit; }
+
+int reduce_jobs(const RedJob* jobs_dev, int njobs, double* results_dev, double* partials, unsigned* counter,
+                cudaStream_t st, const int* skip) {
   if (njobs <= 0) return 0;
-  reduce_jobs_kernel<<<njobs, 512, 0, st>>>(jobs_dev, results_dev, skip);
+  dim3 grid(njobs, kRedSplit);
+  reduce_jobs_kernel<<<grid, 256, 0, st>>>(jobs_dev, results_dev, partials, counter, skip);
   AO_CHECK_LAUNCH();
   return 1;
 }

@@ -55,6 +55,8 @@ struct PrepArgs {
   double* B;              // out: system matrix
   double* L;              // out: lower Cholesky factor of B (col-major), strictly upper part zeroed
   double* invdiag;        // out: 1 / diag(L)
+  double* Binv;           // out (optional): inv(B) = inv(L)'*inv(L), used by the ADMM tile kernel
+  double* Btmp;           // scratch R x R, needed with Binv when R > 64
   double* rho;            // out: trace(C)/R * rho_scale
   InnerCtl* ctl;          // reset (done = 0, iters = 0); err set on failure
 };
@@ -67,8 +69,7 @@ constexpr int kMaxGroup = 8;
 
 struct AdmmMode {
   const double* A;        // right-hand side (weighted MTTKRP [+ bsum term]) rows x R
-  const double* L;        // Cholesky factor R x R
-  const double* invdiag;  // 1/diag(L)
+  const double* Binv;     // inv(B), R x R (symmetric)
   const double* rho;      // device scalar
   double* F;              // factor matrix
   double* Z;              // constraint_fac or nullptr
@@ -136,6 +137,9 @@ struct RedJob {
   const double* b;
 };
 // results[j] for each job; jobs resident in device memory (uploaded once)
-int reduce_jobs(const RedJob* jobs_dev, int njobs, double* results_dev, cudaStream_t st, const int* skip);
+// `partials` (>= reduce_ws_doubles(njobs)) and `counter` (one zeroed uint) are scratch.
+size_t reduce_ws_doubles(int njobs);
+int reduce_jobs(const RedJob* jobs_dev, int njobs, double* results_dev, double* partials, unsigned* counter,
+                cudaStream_t st, const int* skip);
 
 }  // namespace aoadmm

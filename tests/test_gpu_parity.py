@@ -213,6 +213,20 @@ def test_four_way_tensor(ab):
     assert_state_close(Gd, Go)
 
 
+@pytest.mark.parametrize('dims', [(120, 90, 70, 200, 8), (64, 48, 40, 80, 32), (40, 36, 30, 64, 64), (33, 21, 17, 50, 3)])
+def test_dimension_tree_matches_three_pass_and_oracle(ab, dims):
+    """engine knob options.dimtree=1: mode 3 is computed from the partial contraction emitted by the mode-2 pass."""
+    Z, G, _ = pg.config_cp_matrix(*dims, seed=2)
+    opts = pg.default_options(MaxOuterIters=25)
+    Go, oo, Gd, od = _both(ab, Z, G, dict(opts, dimtree=1))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+    Z, G, _ = pg.config_single_cp(sz=(50, 44, 38), R=5, seed=3, noise=0.1, constraints=[('non-negativity',)] * 3)
+    Go, oo, Gd, od = _both(ab, Z, G, dict(pg.default_options(MaxOuterIters=20), dimtree=1))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
