@@ -221,6 +221,19 @@ bool constraint_supported(int kind) {
 
 }  // namespace
 
+// reg_func of constraints_to_prox.m:49,:53,:57,:61,:77,:81 as a reduction kind (-1: the constraint has no regulariser value)
+static int reg_red_kind(int con_kind) {
+  switch (con_kind) {
+    case AOADMM_CON_L1_REG: return RED_L1;
+    case AOADMM_CON_L0_REG: return RED_NNZ;
+    case AOADMM_CON_L2_REG: return RED_COLNORM;
+    case AOADMM_CON_RIDGE: return RED_NORM2;
+    case AOADMM_CON_GL_SMOOTH: return RED_GLQUAD;
+    case AOADMM_CON_TV: return RED_TVSUM;
+    default: return -1;
+  }
+}
+
 struct Engine::ObjTerms {
   struct PerObject {
     int idx_dot = -1, idx_had = -1;
@@ -278,7 +291,6 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
       throw CudaError(2, "constraint kind " + std::to_string(m.con.kind) + " of mode " + std::to_string(m.id) +
                              " is not supported on device");
     if (m.R <= 0 || m.R > 256) throw CudaError(1, "rank must be in 1..256");
-    if (prob->n_slices != nullptr && prob->n_slices[i] > 0) throw CudaError(2, "PARAFAC2 objects are not supported by this build");
   }
 
   objects_.resize(n_objects_);
@@ -287,11 +299,15 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     ObjectState& o = objects_[p];
     o.model = src.model;
     o.order = src.order;
-    if (o.model != AOADMM_MODEL_CP) throw CudaError(2, "PARAFAC2 objects are not supported by this build");
+    if (o.model != AOADMM_MODEL_CP && o.model != AOADMM_MODEL_PAR2) throw CudaError(1, "unknown object model");
     if (o.order < 2 || o.order > 8) throw CudaError(1, "object order must be in 2..8");
     o.modes.assign(src.modes, src.modes + o.order);
     o.weight = src.weight;
     o.znorm = src.znorm_const;
+    if (o.model == AOADMM_MODEL_PAR2) {
+      setup_par2(prob, p);
+      continue;
+    }
     int R = 0;
     for (int d = 0; d < o.order; ++d) {
       const int mid = o.modes[d];
@@ -337,6 +353,7 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     for (auto& m : modes_)
       if (m.coupling == c) {
         if (first < 0) first = m.id;
+        if (m.par2_role == 2) throw CudaError(1, "the second PARAFAC2 mode cannot be coupled (cmtf_fun_AOADMM.m:191)");
         if (m.rows != mode(first).rows || m.R != mode(first).R)
           throw CudaError(1, "exactly coupled modes need identical factor shapes");
       }
@@ -401,7 +418,9 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   // views + workspaces
   size_t ws_bytes = 0, kr_doubles = 0;
   size_t cp0 = 0;
+  for (auto& s : par2_) ws_bytes = std::max(ws_bytes, mttkrp_workspace_bytes(s.view, s.R));
   for (auto& o : objects_) {
+    if (o.model == AOADMM_MODEL_PAR2) continue;
     build_views(o);
     for (auto& v : o.views) {
       ws_bytes = std::max(ws_bytes, mttkrp_workspace_bytes(v.t, mode(o.modes[0]).R));
@@ -464,6 +483,17 @@ Engine::~Engine() {
     }
   }
   for (auto& d : delta_) dev_free(d);
+  for (auto& s : par2_) {
+    for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
+    for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
+                    (void*)s.rho2, (void*)s.rho3, (void*)s.contrib, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
+                    (void*)s.res_partials})
+      if (q) cudaFree(q);
+    if (s.segn_host) cudaFreeHost(s.segn_host);
+    packed_factor_free(s.fW);
+    packed_factor_free(s.fA);
+    packed_factor_free(s.ones);
+  }
   for (void* p : {(void*)mws_.ws, (void*)gram_ws_, (void*)admm_partials_, (void*)admm_sums_, (void*)admm_counter_,
                   prox_scratch_, (void*)krtmp_[0], (void*)krtmp_[1], (void*)ctl_dev_, (void*)jobs_dev_,
                   (void*)red_dev_, (void*)red_partials_, (void*)cp0_tmp_})
@@ -648,6 +678,134 @@ void Engine::precompute_mode(ModeState& m, int n_rho_terms, bool do_chol) {
   a.nhad = 0;
   for (int d = 0; d < o.order; ++d)
     if (o.modes[d] != m.id) a.had[a.nhad++] = mode(o.modes[d]).GtG.p;  // :98-103, :109, :112
+  fill_prep(m, a, n_rho_terms, do_chol);
+  // the system preparation depends only on the Grams of the other modes: run it on the side stream while the
+  // MTTKRP of this mode streams the tensor on the main stream
+  AO_CUDA(cudaEventRecord(ev_fork_, st_));
+  AO_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+  launches_ += prep_system(a, st2_, nullptr);
+  AO_CUDA(cudaEventRecord(ev_join_, st2_));
+  compute_mttkrp(o, m.pos, o.weight, m.A.p, m.rows);  // A{m} = w * mttkrp (:97, :108, :111)
+  AO_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
+  apply_bsum(m);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PARAFAC2 block
+// ---------------------------------------------------------------------------------------------------
+void Engine::setup_par2(const aoadmm_problem* prob, int p) {
+  const aoadmm_object& src = prob->objects[p];
+  ObjectState& o = objects_[p];
+  if (o.order != 3) throw CudaError(1, "a PARAFAC2 object has exactly three modes (A, B_k, C)");
+  par2_.emplace_back();
+  Par2State& s = par2_.back();
+  const int idx = (int)par2_.size() - 1;
+  s.p = p;
+  s.m1 = o.modes[0];
+  s.m2 = o.modes[1];
+  s.m3 = o.modes[2];
+  for (int d = 0; d < 3; ++d) {
+    const int mid = o.modes[d];
+    if (mid < 1 || mid > nb_modes_) throw CudaError(1, "mode id out of range");
+    ModeState& m = mode(mid);
+    if (m.p != -1) throw CudaError(1, "mode " + std::to_string(mid) + " belongs to two objects");
+    m.p = p;
+    m.pos = d;
+    m.par2_role = d + 1;
+    m.par2 = idx;
+  }
+  ModeState &ma = mode(s.m1), &mb = mode(s.m2), &mc = mode(s.m3);
+  s.R = ma.R;
+  if (mb.R != s.R || mc.R != s.R) throw CudaError(1, "all modes of a PARAFAC2 object need the same rank");
+  if (s.R > 64) throw CudaError(2, "PARAFAC2 objects support at most 64 components on device");
+  s.K = (prob->n_slices != nullptr) ? prob->n_slices[s.m2 - 1] : 0;
+  const int64_t* jk = (prob->slice_rows != nullptr) ? prob->slice_rows[s.m2 - 1] : nullptr;
+  if (s.K <= 0 || jk == nullptr || src.n_slices != s.K || src.slices == nullptr)
+    throw CudaError(1, "PARAFAC2 object: slice sizes (Z.size of the second mode) and K data slices are required");
+  if (mc.rows != s.K) throw CudaError(1, "PARAFAC2 object: the third mode must have K rows");
+  s.I = ma.rows;
+  s.joff.assign(s.K + 1, 0);
+  for (int k = 0; k < s.K; ++k) {
+    if (jk[k] < s.R)  // cmtf_AOADMM.m:55-65
+      throw CudaError(1, "Number of components for PARAFAC2 is larger than size of slice " + std::to_string(k + 1));
+    s.joff[k + 1] = s.joff[k] + jk[k];
+    s.Jmax = std::max<int64_t>(s.Jmax, jk[k]);
+  }
+  s.Jtot = s.joff[s.K];
+  mb.rows = s.Jtot;
+  o.dims = {s.I, s.Jtot, (int64_t)s.K};
+  o.last_full = s.K;
+  o.shard_extent = s.K;
+  s.ldX = round_up(s.I, 2);
+  const size_t xbytes = std::max<size_t>((size_t)s.ldX * s.Jtot * sizeof(double), 256);
+  AO_CUDA(cudaMalloc(&s.X, xbytes));
+  if (s.ldX != s.I) AO_CUDA(cudaMemset(s.X, 0, xbytes));
+  std::vector<int> seg((size_t)s.Jtot);
+  for (int k = 0; k < s.K; ++k) {
+    if (src.slices[k] == nullptr) throw CudaError(1, "PARAFAC2 object: NULL slice");
+    AO_CUDA(cudaMemcpy2D(s.X + (size_t)s.joff[k] * s.ldX, (size_t)s.ldX * 8, src.slices[k], (size_t)s.I * 8,
+                         (size_t)s.I * 8, (size_t)jk[k], cudaMemcpyHostToDevice));
+    for (int64_t j = s.joff[k]; j < s.joff[k + 1]; ++j) seg[(size_t)j] = k;
+  }
+  AO_CUDA(cudaMalloc(&s.joff_dev, sizeof(long long) * (s.K + 1)));
+  {
+    std::vector<long long> tmp(s.joff.begin(), s.joff.end());
+    AO_CUDA(cudaMemcpy(s.joff_dev, tmp.data(), sizeof(long long) * (s.K + 1), cudaMemcpyHostToDevice));
+  }
+  AO_CUDA(cudaMalloc(&s.seg_dev, sizeof(int) * (size_t)s.Jtot));
+  AO_CUDA(cudaMemcpy(s.seg_dev, seg.data(), sizeof(int) * (size_t)s.Jtot, cudaMemcpyHostToDevice));
+  s.lay.K = s.K;
+  s.lay.R = s.R;
+  s.lay.Jtot = s.Jtot;
+  s.lay.Jmax = s.Jmax;
+  s.lay.joff = s.joff_dev;
+  s.lay.seg = s.seg_dev;
+  make_tensor3(s.view, s.X, s.I, s.Jtot, 1, s.ldX);
+  packed_factor_alloc(s.fW, s.Jtot, s.R);
+  packed_factor_alloc(s.fA, s.I, s.R);
+  packed_factor_alloc(s.ones, 1, s.R);
+  packed_factor_pack(s.ones, nullptr, 1, st_, nullptr);
+  ++launches_;
+  for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.PDold, &s.gM, &s.gS}) dev_alloc(*d, s.Jtot, s.R);
+  dev_alloc(s.DeltaB, s.R, s.R);
+  const size_t KRR = (size_t)s.K * s.R * s.R;
+  AO_CUDA(cudaMalloc(&s.G2, KRR * sizeof(double)));
+  AO_CUDA(cudaMalloc(&s.Binv2, KRR * sizeof(double)));
+  AO_CUDA(cudaMalloc(&s.Binv3, KRR * sizeof(double)));
+  AO_CUDA(cudaMalloc(&s.contrib, KRR * sizeof(double)));
+  AO_CUDA(cudaMalloc(&s.rho2, sizeof(double) * s.K));
+  AO_CUDA(cudaMalloc(&s.rho3, sizeof(double) * s.K));
+  AO_CUDA(cudaMalloc(&s.norms, sizeof(double) * s.K * 8));
+  AO_CUDA(cudaMemset(s.norms, 0, sizeof(double) * s.K * 8));
+  AO_CUDA(cudaMalloc(&s.Csum, sizeof(double) * s.R * s.R));
+  AO_CUDA(cudaMalloc(&s.segn, sizeof(double) * (s.K * 4 + 8)));
+  AO_CUDA(cudaMemset(s.segn, 0, sizeof(double) * (s.K * 4 + 8)));
+  AO_CUDA(cudaMalloc(&s.res_partials, sizeof(double) * 148 * 8));
+  AO_CUDA(cudaMallocHost(&s.segn_host, sizeof(double) * (s.K * 4 + 8)));
+  s.res = s.segn + (size_t)s.K * 4;
+  mc.rho_rows = s.rho3;
+  mc.Binv_rows = s.Binv3;
+  AO_CUDA(cudaDeviceSynchronize());
+}
+
+void Engine::par2_refresh_gram(Par2State& s) {  // :71-73, :216-218
+  launches_ += par2_batched_gram(s.lay, mode(s.m2).fac.p, s.G2, st_);
+}
+
+// T = Xall' * A (Jtot x R): shared by the mode-B right-hand sides (:193) and the mode-C ones (:221)
+void Engine::par2_update_T(Par2State& s) {
+  ModeState& a = mode(s.m1);
+  if (s.T_version == a.version) return;
+  phase_begin(1);
+  packed_factor_pack(s.fA, a.fac.p, a.rows, st_, nullptr);
+  ++launches_;
+  launches_ += mttkrp3(s.view, 1, s.fA, s.ones, s.R, 1.0, s.T.p, s.Jtot, mws_, st_, nullptr);
+  phase_end();
+  s.T_version = a.version;
+}
+
+void Engine::fill_prep(ModeState& m, PrepArgs& a, int n_rho_terms, bool do_chol) {
+  ObjectState& o = objects_[m.p];
   a.R = m.R;
   a.weight = o.weight;
   a.ridge = m.ridge;
@@ -664,22 +822,128 @@ void Engine::precompute_mode(ModeState& m, int n_rho_terms, bool do_chol) {
   a.Btmp = m.Btmp.p;
   a.rho = m.rho;
   a.ctl = m.ctl;
-  // the system preparation depends only on the Grams of the other modes: run it on the side stream while the
-  // MTTKRP of this mode streams the tensor on the main stream
-  AO_CUDA(cudaEventRecord(ev_fork_, st_));
-  AO_CUDA(cudaStreamWaitEvent(st2_, ev_fork_, 0));
-  launches_ += prep_system(a, st2_, nullptr);
-  AO_CUDA(cudaEventRecord(ev_join_, st2_));
-  compute_mttkrp(o, m.pos, o.weight, m.A.p, m.rows);  // A{m} = w * mttkrp (:97, :108, :111)
-  AO_CUDA(cudaStreamWaitEvent(st_, ev_join_, 0));
-  if (opt_.bsum) {  // :124-127 (last_mttkrp keeps the value before the BSUM term, :121)
-    AO_CUDA(cudaMemcpyAsync(m.Alast.p, m.A.p, m.A.bytes(), cudaMemcpyDeviceToDevice, st_));
-    const long long n = m.rows * m.R;
-    axpy_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), 148 * 8), 256, 0, st_>>>(m.A.p, m.fac.p,
-                                                                                           opt_.bsum_weight / 2.0, n);
-    AO_CHECK_LAUNCH();
-    ++launches_;
+}
+
+void Engine::apply_bsum(ModeState& m) {
+  if (!opt_.bsum) return;  // :124-127 (last_mttkrp keeps the value before the BSUM term, :121)
+  AO_CUDA(cudaMemcpyAsync(m.Alast.p, m.A.p, m.A.bytes(), cudaMemcpyDeviceToDevice, st_));
+  const long long n = m.rows * m.R;
+  axpy_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), 148 * 8), 256, 0, st_>>>(m.A.p, m.fac.p,
+                                                                                         opt_.bsum_weight / 2.0, n);
+  AO_CHECK_LAUNCH();
+  ++launches_;
+}
+
+// first PARAFAC2 mode (:159-178): A = w * sum_k X_k B_k diag(c_k),  C = sum_k diag(c_k) B_k'B_k diag(c_k)
+void Engine::par2_precompute_A(ModeState& m, int n_rho_terms) {
+  Par2State& s = par2_[m.par2];
+  ObjectState& o = objects_[m.p];
+  ModeState &mb = mode(s.m2), &mc = mode(s.m3);
+  phase_begin(1);
+  launches_ += par2_scale_rows(s.lay, s.W.p, mb.fac.p, mc.fac.p, mc.rows, 1.0, nullptr, 0.0, st_);
+  packed_factor_pack(s.fW, s.W.p, s.Jtot, st_, nullptr);
+  ++launches_;
+  launches_ += mttkrp3(s.view, 0, s.fW, s.ones, s.R, o.weight, m.A.p, m.rows, mws_, st_, nullptr);
+  phase_end();
+  launches_ += par2_modeA_had(s.lay, s.G2, mc.fac.p, mc.rows, s.Csum, st_);
+  PrepArgs a{};
+  a.nhad = 1;
+  a.had[0] = s.Csum;
+  fill_prep(m, a, n_rho_terms, true);
+  launches_ += prep_system(a, st_, nullptr);
+  apply_bsum(m);
+}
+
+// second PARAFAC2 mode: per-slice systems (:192-213) and ADMM_B_Parafac2 (:509-589)
+void Engine::par2_update_B(ModeState& m, int outer_iter) {
+  Par2State& s = par2_[m.par2];
+  ObjectState& o = objects_[m.p];
+  ModeState &ma = mode(s.m1), &mc = mode(s.m3);
+  par2_update_T(s);
+  const bool bs = opt_.bsum != 0;
+  launches_ += par2_scale_rows(s.lay, m.A.p, s.T.p, mc.fac.p, mc.rows, o.weight, bs ? m.fac.p : nullptr,
+                               bs ? opt_.bsum_weight / 2.0 : 0.0, st_);
+  const bool con_active = m.constrained && outer_iter >= opt_.iter_start_PAR2Bkconstraint;
+  Par2SysArgs sa{};
+  sa.mode = 2;
+  sa.G1 = ma.GtG.p;
+  sa.C = mc.fac.p;
+  sa.ldc = mc.rows;
+  sa.weight = o.weight;
+  sa.ridge = m.ridge;
+  sa.bsum_half = bs ? opt_.bsum_weight / 2.0 : 0.0;
+  sa.rho_scale = opt_.has_increase_factor_rhoBk ? opt_.increase_factor_rhoBk : 1.0;
+  sa.n_rho_terms = 1 + (con_active ? 1 : 0);
+  sa.rho_k = s.rho2;
+  sa.Binv = s.Binv2;
+  sa.ctl = m.ctl;
+  launches_ += par2_sys_prep(s.lay, sa, st_);
+  const bool deferred = con_active && !prox_is_elementwise(m.con.kind);
+  Par2BArgs b{};
+  b.A = m.A.p;
+  b.Binv = s.Binv2;
+  b.rho_k = s.rho2;
+  b.B = m.fac.p;
+  b.P = s.P.p;
+  b.mu = s.muDB.p;
+  b.DeltaB = s.DeltaB.p;
+  b.Z = m.Z.p;
+  b.muZ = m.muZ.p;
+  b.con_active = con_active ? 1 : 0;
+  b.prox_kind = m.con.kind;
+  b.p0 = m.con.p0;
+  b.p1 = m.con.p1;
+  b.PDold = s.PDold.p;
+  b.contrib = s.contrib;
+  b.gM = s.gM.p;
+  b.gS = s.gS.p;
+  b.norms = s.norms;
+  b.Znew = deferred ? m.Znew.p : nullptr;
+  InnerTol tol{opt_.innerRelPrTol_coupl, opt_.innerRelDualTol_coupl, opt_.innerRelPrTol_constr,
+               opt_.innerRelDualTol_constr};
+  for (int it = 0; it < opt_.MaxInnerIters; ++it) {
+    launches_ += par2_B_step1(s.lay, b, m.ctl, st_);
+    launches_ += par2_B_deltaB(s.lay, b, m.ctl, st_);
+    launches_ += par2_B_step2a(s.lay, b, m.ctl, st_);
+    if (deferred) {
+      launches_ += par2_B_form_prox_input(s.lay, b, m.V.p, m.ctl, st_);
+      for (int k = 0; k < s.K; ++k)  // :567-568: prox of every slice with its own rho_k
+        launches_ += prox_apply(m.con.kind, m.con.p0, m.con.p1, m.V.p + s.joff[k], s.Jtot, m.Znew.p + s.joff[k], s.Jtot,
+                                s.joff[k + 1] - s.joff[k], s.R, s.rho2 + k, 0.0, prox_scratch_, st_, &m.ctl->done);
+    }
+    launches_ += par2_B_step2b(s.lay, b, tol, m.ctl, admm_counter_, st_);
   }
+  par2_refresh_gram(s);
+  ++m.version;
+}
+
+// third PARAFAC2 mode (:220-243): per-row right-hand sides and systems
+void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct) {
+  Par2State& s = par2_[m.par2];
+  ObjectState& o = objects_[m.p];
+  ModeState &ma = mode(s.m1), &mb = mode(s.m2);
+  par2_update_T(s);
+  Par2SysArgs sa{};
+  sa.mode = 3;
+  sa.G1 = ma.GtG.p;
+  sa.G2 = s.G2;
+  sa.C = m.fac.p;
+  sa.ldc = m.rows;
+  sa.weight = o.weight;
+  sa.ridge = m.ridge;
+  sa.bsum_half = opt_.bsum ? opt_.bsum_weight / 2.0 : 0.0;
+  sa.rho_scale = 1.0;
+  sa.n_rho_terms = n_rho_terms;
+  sa.T = s.T.p;
+  sa.Bst = mb.fac.p;
+  sa.rhs = m.A.p;
+  sa.ls_direct = ls_direct ? 1 : 0;
+  sa.fac_out = m.fac.p;
+  sa.rho_k = s.rho3;
+  sa.Binv = s.Binv3;
+  sa.ctl = m.ctl;
+  launches_ += par2_sys_prep(s.lay, sa, st_);
+  launches_ += par2_rho_max(s.rho3, s.K, m.rho, st_);
 }
 
 void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt) {
@@ -696,6 +960,8 @@ void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadm
     am.A = m.A.p;
     am.Binv = m.Binv.p;
     am.rho = m.rho;
+    am.rho_rows = m.rho_rows;
+    am.Binv_rows = m.Binv_rows;
     am.F = m.fac.p;
     am.Z = m.Z.p;
     am.muZ = m.muZ.p;
@@ -746,6 +1012,11 @@ void Engine::build_objective_jobs() {
   };
   for (int p = 0; p < n_objects_; ++p) {
     ModeState& lm = mode(objects_[p].last_m);
+    if (objects_[p].model == AOADMM_MODEL_PAR2 && lm.par2_role != 1) {
+      // :1254 - the shortcut only exists when the first PARAFAC2 mode is the one updated last
+      par2_[lm.par2].explicit_residual = true;
+      continue;
+    }
     // Alast holds last_mttkrp when BSUM is on; decided at run time by swapping the pointer (see eval_objective)
     terms_->obj[p].idx_dot = add(RED_DOT, lm.A.p, lm.fac.p, lm.rows, lm.R);
     terms_->obj[p].idx_had = add(RED_DOT, lm.C.p, lm.GtG.p, lm.R, lm.R);
@@ -753,20 +1024,12 @@ void Engine::build_objective_jobs() {
   for (int i = 0; i < nb_modes_; ++i) {
     ModeState& m = modes_[i];
     auto& t = terms_->mode[i];
+    if (m.par2_role == 2) continue;  // per-slice terms come from par2_seg_norms
     t.idx_norm2 = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R);
     if (m.constrained) t.idx_diffZ = add(RED_DIFF2, m.fac.p, m.Z.p, m.rows, m.R);
     if (m.coupling != 0) t.idx_diffD = add(RED_DIFF2, m.fac.p, delta_[m.coupling - 1].p, m.rows, m.R);
-    if (m.constrained) {
-      switch (m.con.kind) {  // reg_func of constraints_to_prox.m:49,:53,:57,:61,:77,:81
-        case AOADMM_CON_L1_REG: t.idx_reg = add(RED_L1, m.fac.p, nullptr, m.rows, m.R); break;
-        case AOADMM_CON_L0_REG: t.idx_reg = add(RED_NNZ, m.fac.p, nullptr, m.rows, m.R); break;
-        case AOADMM_CON_L2_REG: t.idx_reg = add(RED_COLNORM, m.fac.p, nullptr, m.rows, m.R); break;
-        case AOADMM_CON_RIDGE: t.idx_reg = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R); break;
-        case AOADMM_CON_GL_SMOOTH: t.idx_reg = add(RED_GLQUAD, m.fac.p, nullptr, m.rows, m.R); break;
-        case AOADMM_CON_TV: t.idx_reg = add(RED_TVSUM, m.fac.p, nullptr, m.rows, m.R); break;
-        default: break;
-      }
-    }
+    if (m.constrained && reg_red_kind(m.con.kind) >= 0)
+      t.idx_reg = add(reg_red_kind(m.con.kind), m.fac.p, nullptr, m.rows, m.R);
   }
   const size_t nj = jobs_host_.size();
   AO_CUDA(cudaMalloc(&jobs_dev_, sizeof(RedJob) * (nj + 8)));
@@ -783,6 +1046,7 @@ void Engine::eval_objective(bool first, double f[4]) {
     // cp_func.m:47-56 / pca_func.m:29-40: f = w*(||X||^2 - 2*sum(A1 .* mttkrp(X,A,1)) + sum(prod of all Grams))
     for (int p = 0; p < n_objects_; ++p) {
       ObjectState& o = objects_[p];
+      if (o.model == AOADMM_MODEL_PAR2) continue;  // explicit residual below (:1262-1264)
       ModeState& m0 = mode(o.modes[0]);
       double* M = cp0_tmp_;
       double* scr = cp0_tmp_ + (size_t)m0.rows * m0.R;  // C | B | L | invdiag | rho
@@ -821,6 +1085,15 @@ void Engine::eval_objective(bool first, double f[4]) {
       f_obj[p] = o.weight * (o.znorm - 2.0 * r2[0] + r2[1]);
     }
   }
+  for (auto& s : par2_) {
+    ModeState& mb = mode(s.m2);
+    launches_ += par2_seg_norms(s.lay, mb.fac.p, mb.constrained ? mb.Z.p : nullptr, s.P.p, s.DeltaB.p,
+                                mb.constrained ? reg_red_kind(mb.con.kind) : -1, s.segn, st_);
+    if (first || s.explicit_residual)
+      launches_ += par2_residual(s.lay, s.X, s.ldX, s.I, mode(s.m1).fac.p, mode(s.m1).rows, mb.fac.p, mode(s.m3).fac.p,
+                                 mode(s.m3).rows, s.res_partials, admm_counter_, s.res, st_);
+    AO_CUDA(cudaMemcpyAsync(s.segn_host, s.segn, sizeof(double) * (s.K * 4 + 1), cudaMemcpyDeviceToHost, st_));
+  }
   launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, red_partials_, admm_counter_, st_, nullptr);
   AO_CUDA(cudaMemcpyAsync(red_host_, red_dev_, sizeof(double) * nj, cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaMemcpyAsync(ctl_host_, ctl_dev_, sizeof(InnerCtl) * n_ctl_, cudaMemcpyDeviceToHost, st_));
@@ -828,10 +1101,29 @@ void Engine::eval_objective(bool first, double f[4]) {
   phase_collect();
   const double* r = red_host_;
   double f_tensors = 0.0;
+  // per-slice terms of the PARAFAC2 second modes (host side: K ratios each)
+  struct SliceTerms {
+    double con = 0.0, par2 = 0.0, reg = 0.0, n2 = 0.0;
+  };
+  std::vector<SliceTerms> st2(par2_.size());
+  for (size_t q = 0; q < par2_.size(); ++q) {
+    const Par2State& s = par2_[q];
+    for (int k = 0; k < s.K; ++k) {
+      const double* h = s.segn_host + (size_t)k * 4;
+      const double nB = std::sqrt(h[0]);
+      st2[q].con += std::sqrt(h[1]) / nB;    // :1337
+      st2[q].par2 += std::sqrt(h[2]) / nB;   // :1355
+      st2[q].reg += h[3];                    // :1279-1281
+      st2[q].n2 += h[0];                     // :1293-1295
+    }
+  }
   for (int p = 0; p < n_objects_; ++p) {
-    if (!first) {
-      ObjectState& o = objects_[p];
-      // f_2 = sum(last_mttkrp .* fac) with last_mttkrp = A/w (:121, :1236-1237)
+    ObjectState& o = objects_[p];
+    if (o.model == AOADMM_MODEL_PAR2 && (first || terms_->obj[p].idx_dot < 0)) {
+      const Par2State& s = par2_[mode(o.modes[0]).par2];
+      f_obj[p] = o.weight * s.segn_host[(size_t)s.K * 4];   // :1262-1267
+    } else if (!first) {
+      // f_2 = sum(last_mttkrp .* fac) with last_mttkrp = A/w (:121, :1236-1237, :1256)
       const double f2 = r[terms_->obj[p].idx_dot] / o.weight;
       const double f3 = r[terms_->obj[p].idx_had];
       f_obj[p] = o.weight * (o.znorm - 2.0 * f2 + f3);
@@ -840,11 +1132,21 @@ void Engine::eval_objective(bool first, double f[4]) {
   }
   for (int i = 0; i < nb_modes_; ++i) {  // :1272-1288 regularisers
     const ModeState& m = modes_[i];
+    if (m.par2_role == 2) {
+      if (m.constrained && reg_red_kind(m.con.kind) >= 0) f_tensors += m.con.p0 * st2[m.par2].reg;
+      continue;
+    }
     const int ir = terms_->mode[i].idx_reg;
     if (ir >= 0) f_tensors += m.con.p0 * r[ir];
   }
-  if (has_ridge_)  // :1290-1300
-    for (int i = 0; i < nb_modes_; ++i) f_tensors += modes_[i].ridge * r[terms_->mode[i].idx_norm2];
+  if (has_ridge_)  // :1290-1300 (second PARAFAC2 mode: the loop runs over length(G.constraint_fac{n}), :1293)
+    for (int i = 0; i < nb_modes_; ++i) {
+      if (modes_[i].par2_role == 2) {
+        if (modes_[i].constrained) f_tensors += modes_[i].ridge * st2[modes_[i].par2].n2;
+      } else {
+        f_tensors += modes_[i].ridge * r[terms_->mode[i].idx_norm2];
+      }
+    }
   double f_coupl = 0.0;
   int nz = 0;
   for (int c = 1; c <= n_couplings_; ++c) {  // :1303-1329
@@ -860,66 +1162,106 @@ void Engine::eval_objective(bool first, double f[4]) {
   nz = 0;
   for (int i = 0; i < nb_modes_; ++i) {  // :1332-1348
     if (!modes_[i].constrained) continue;
-    const double v = std::sqrt(r[terms_->mode[i].idx_diffZ]) / std::sqrt(r[terms_->mode[i].idx_norm2]);
+    const double v = (modes_[i].par2_role == 2)
+                         ? st2[modes_[i].par2].con / (double)par2_[modes_[i].par2].K   // :1336-1339
+                         : std::sqrt(r[terms_->mode[i].idx_diffZ]) / std::sqrt(r[terms_->mode[i].idx_norm2]);
     f_con += v;
     if (v != 0.0) ++nz;
   }
   if (f_con > 0.0) f_con /= (double)nz;
+  double f_par2 = 0.0;                    // :1351-1362
+  for (size_t q = 0; q < par2_.size(); ++q) f_par2 += st2[q].par2;
+  if (f_par2 > 0.0) {
+    // the divisor is length(Z.size{Z.modes{pp}(2)}) with pp left at P by the loop (:1361)
+    const ObjectState& ol = objects_[n_objects_ - 1];
+    const double div = (ol.model == AOADMM_MODEL_PAR2) ? (double)par2_[mode(ol.modes[0]).par2].K : 1.0;
+    f_par2 /= div;
+  }
   f[0] = f_tensors;
   f[1] = f_coupl;
   f[2] = f_con;
-  f[3] = 0.0;
+  f[3] = f_par2;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // state exchange
 // ---------------------------------------------------------------------------------------------------
-static DevMat* field_ptr(std::vector<ModeState>& modes, std::vector<DevMat>& delta, int field, int index) {
+// Resolves a state field to its device matrix and, for the per-slice fields of a PARAFAC2 object, the row range of
+// slice `slice` inside the stacked Jtot x R storage.
+DevMat* Engine::par2_field(int field, int index, int slice, int64_t* row_off, int64_t* nrows) {
+  *row_off = 0;
+  *nrows = -1;
+  auto slice_range = [&](const Par2State& s) {
+    if (slice < 0 || slice >= s.K) throw CudaError(1, "state: slice index out of range");
+    *row_off = s.joff[slice];
+    *nrows = s.joff[slice + 1] - s.joff[slice];
+  };
   switch (field) {
-    case AOADMM_FIELD_FAC: return &modes.at(index - 1).fac;
-    case AOADMM_FIELD_CONSTRAINT_FAC: return &modes.at(index - 1).Z;
-    case AOADMM_FIELD_CONSTRAINT_DUAL: return &modes.at(index - 1).muZ;
-    case AOADMM_FIELD_COUPLING_DUAL: return &modes.at(index - 1).muD;
-    case AOADMM_FIELD_COUPLING_FAC: return &delta.at(index - 1);
+    case AOADMM_FIELD_FAC:
+    case AOADMM_FIELD_CONSTRAINT_FAC:
+    case AOADMM_FIELD_CONSTRAINT_DUAL:
+    case AOADMM_FIELD_COUPLING_DUAL: {
+      if (index < 1 || index > nb_modes_) throw CudaError(1, "state: mode index out of range");
+      ModeState& m = modes_[index - 1];
+      if (m.par2_role == 2) slice_range(par2_[m.par2]);
+      if (field == AOADMM_FIELD_FAC) return &m.fac;
+      if (field == AOADMM_FIELD_CONSTRAINT_FAC) return &m.Z;
+      if (field == AOADMM_FIELD_CONSTRAINT_DUAL) return &m.muZ;
+      return &m.muD;
+    }
+    case AOADMM_FIELD_COUPLING_FAC:
+      if (index < 1 || index > n_couplings_) throw CudaError(1, "state: coupling index out of range");
+      return &delta_[index - 1];
+    case AOADMM_FIELD_PAR2_P:
+    case AOADMM_FIELD_PAR2_DELTAB:
+    case AOADMM_FIELD_PAR2_MU_DELTAB: {
+      for (auto& s : par2_)
+        if (s.p == index - 1) {
+          if (field == AOADMM_FIELD_PAR2_DELTAB) return &s.DeltaB;
+          slice_range(s);
+          return field == AOADMM_FIELD_PAR2_P ? &s.P : &s.muDB;
+        }
+      throw CudaError(1, "state: object " + std::to_string(index) + " is not a PARAFAC2 object");
+    }
     default: return nullptr;
   }
 }
 
 void Engine::set_state(int field, int index, int slice, const double* data, int64_t rows, int64_t cols) {
-  (void)slice;
   AO_CUDA(cudaSetDevice(device_));
   if (data == nullptr) throw CudaError(1, "set_state: NULL data");
-  DevMat* d = nullptr;
-  try {
-    d = field_ptr(modes_, delta_, field, index);
-  } catch (const std::out_of_range&) {
-    throw CudaError(1, "set_state: index out of range");
-  }
+  int64_t off = 0, nr = -1;
+  DevMat* d = par2_field(field, index, slice, &off, &nr);
   if (d == nullptr) throw CudaError(2, "set_state: field not supported by this build");
   if (d->p == nullptr) throw CudaError(1, "set_state: field " + std::to_string(field) + " does not exist for index " + std::to_string(index));
-  if (d->rows != rows || d->cols != cols)
+  const int64_t want_rows = nr >= 0 ? nr : d->rows;
+  if (want_rows != rows || d->cols != cols)
     throw CudaError(1, "set_state: shape mismatch for field " + std::to_string(field) + " index " +
-                           std::to_string(index) + ": expected " + std::to_string(d->rows) + "x" +
+                           std::to_string(index) + ": expected " + std::to_string(want_rows) + "x" +
                            std::to_string(d->cols));
-  AO_CUDA(cudaMemcpyAsync(d->p, data, d->bytes(), cudaMemcpyHostToDevice, st_));
+  if (nr >= 0)
+    AO_CUDA(cudaMemcpy2DAsync(d->p + off, (size_t)d->rows * 8, data, (size_t)rows * 8, (size_t)rows * 8, (size_t)cols,
+                              cudaMemcpyHostToDevice, st_));
+  else
+    AO_CUDA(cudaMemcpyAsync(d->p, data, d->bytes(), cudaMemcpyHostToDevice, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
   if (field == AOADMM_FIELD_FAC) ++modes_[index - 1].version;
 }
 
 void Engine::get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols) {
-  (void)slice;
   AO_CUDA(cudaSetDevice(device_));
   if (data == nullptr) throw CudaError(1, "get_state: NULL data");
-  DevMat* d = nullptr;
-  try {
-    d = field_ptr(modes_, delta_, field, index);
-  } catch (const std::out_of_range&) {
-    throw CudaError(1, "get_state: index out of range");
-  }
+  int64_t off = 0, nr = -1;
+  DevMat* d = par2_field(field, index, slice, &off, &nr);
   if (d == nullptr) throw CudaError(2, "get_state: field not supported by this build");
   if (d->p == nullptr) throw CudaError(1, "get_state: field does not exist for this index");
-  if (d->rows != rows || d->cols != cols) throw CudaError(1, "get_state: shape mismatch");
-  AO_CUDA(cudaMemcpyAsync(data, d->p, d->bytes(), cudaMemcpyDeviceToHost, st_));
+  const int64_t want_rows = nr >= 0 ? nr : d->rows;
+  if (want_rows != rows || d->cols != cols) throw CudaError(1, "get_state: shape mismatch");
+  if (nr >= 0)
+    AO_CUDA(cudaMemcpy2DAsync(data, (size_t)rows * 8, d->p + off, (size_t)d->rows * 8, (size_t)rows * 8, (size_t)cols,
+                              cudaMemcpyDeviceToHost, st_));
+  else
+    AO_CUDA(cudaMemcpyAsync(data, d->p, d->bytes(), cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
 }
 
@@ -993,6 +1335,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
     bool changed = false;
     for (int p = 0; p < n_objects_; ++p) {
       ModeState& lm = mode(objects_[p].last_m);
+      if (terms_->obj[p].idx_dot < 0) continue;
       const double* want = opt_.bsum ? lm.Alast.p : lm.A.p;
       RedJob& j = jobs_host_[terms_->obj[p].idx_dot];
       if (j.a != want) {
@@ -1004,7 +1347,12 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
       AO_CUDA(cudaMemcpyAsync(jobs_dev_, jobs_host_.data(), sizeof(RedJob) * jobs_host_.size(), cudaMemcpyHostToDevice, st_));
   }
 
-  for (auto& m : modes_) refresh_gram(m);  // :62-81
+  for (auto& m : modes_)                    // :62-81
+    if (m.par2_role != 2) refresh_gram(m);
+  for (auto& s : par2_) {
+    par2_refresh_gram(s);
+    s.T_version = 0;
+  }
   double f[4];
   eval_objective(true, f);                  // :32
   if (out->func_val_conv) out->func_val_conv[0] = f[0];
@@ -1033,6 +1381,36 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
         for (ModeState* mp : cm) {                                   // :93
           ModeState& m = *mp;
           if (m.p != p) continue;
+          if (m.par2_role != 0) {                                    // :157-250
+            const int nterms = (coupl_id == 0) ? (m.constrained ? 1 : 0) : 1 + (m.constrained ? 1 : 0);
+            if (m.par2_role == 1) {
+              par2_precompute_A(m, nterms);
+              if (coupl_id == 0) {
+                if (!m.constrained) {
+                  launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :181
+                  inner_fixed[m.id - 1] = 1;
+                  ++m.version;
+                } else {
+                  std::vector<ModeState*> g1{&m};
+                  run_admm(g1, nullptr, opt_);                       // :186
+                }
+                refresh_gram(m);                                     // :190
+              }
+            } else if (m.par2_role == 2) {
+              par2_update_B(m, iter);                                // :192-218
+            } else {
+              const bool ls = (coupl_id == 0 && !m.constrained);
+              par2_precompute_C(m, nterms, ls);                      // :220-243
+              if (ls) {
+                inner_fixed[m.id - 1] = 1;
+                ++m.version;
+              } else if (coupl_id == 0) {
+                std::vector<ModeState*> g1{&m};
+                run_admm(g1, nullptr, opt_);                         // :245
+              }
+            }
+            continue;
+          }
           if (coupl_id == 0) {
             if (!m.constrained) {
               precompute_mode(m, 0, true);
@@ -1102,6 +1480,7 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   AO_CUDA(cudaSetDevice(device_));
   if (object < 1 || object > n_objects_) throw CudaError(1, "generate_cp_data: object out of range");
   ObjectState& o = objects_[object - 1];
+  if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "generate_cp_data: not a CP object");
   const int R = mode(o.modes[0]).R;
   GenArgs g{};
   g.order = o.order;
@@ -1148,6 +1527,7 @@ void Engine::mttkrp_to_host(int object, int pos, double* out) {
   AO_CUDA(cudaSetDevice(device_));
   if (object < 1 || object > n_objects_) throw CudaError(1, "mttkrp: object out of range");
   ObjectState& o = objects_[object - 1];
+  if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "mttkrp: not a CP object");
   if (pos < 1 || pos > o.order) throw CudaError(1, "mttkrp: position out of range");
   ModeState& m = mode(o.modes[pos - 1]);
   compute_mttkrp(o, pos - 1, 1.0, m.A.p, m.rows);
@@ -1160,6 +1540,7 @@ float Engine::time_mttkrp(int object, int pos, int reps) {
   AO_CUDA(cudaSetDevice(device_));
   if (object < 1 || object > n_objects_) throw CudaError(1, "time_mttkrp: object out of range");
   ObjectState& o = objects_[object - 1];
+  if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "time_mttkrp: not a CP object");
   if (pos < 1 || pos > o.order) throw CudaError(1, "time_mttkrp: position out of range");
   ModeState& m = mode(o.modes[pos - 1]);
   View3& v = o.views[pos - 1];

@@ -8,6 +8,7 @@
 
 #include "../../include/aoadmm.h"
 #include "mttkrp.cuh"
+#include "par2.cuh"
 #include "smallops.cuh"
 
 namespace aoadmm {
@@ -38,6 +39,31 @@ struct ModeState {
   InnerCtl* ctl = nullptr;    // device; for coupled modes all modes of the group share the group's block
   int ctl_index = -1;
   uint64_t version = 1;       // bumped whenever fac changes (validity stamp for cached partial contractions)
+  // PARAFAC2 objects: role 1 = A (first mode), 2 = stacked B_k, 3 = C; par2 = index into Engine::par2_
+  int par2_role = 0, par2 = -1;
+  const double* rho_rows = nullptr;   // role 3: per-row rho_k
+  const double* Binv_rows = nullptr;  // role 3: per-row inv(B_k)
+};
+
+// Device state of one PARAFAC2 object (layout in par2.cuh)
+struct Par2State {
+  int p = -1, K = 0, R = 0;
+  int64_t I = 0, Jtot = 0, Jmax = 0, ldX = 0;
+  int m1 = 0, m2 = 0, m3 = 0;            // global mode ids of A, B_k, C
+  std::vector<int64_t> joff;             // K+1 host copy of the slice offsets
+  Par2Layout lay;
+  long long* joff_dev = nullptr;
+  int* seg_dev = nullptr;
+  double* X = nullptr;                   // I x Jtot (leading dimension ldX)
+  Tensor3 view;                          // X as an I x Jtot x 1 tensor for the DMMA product kernels
+  PackedFactor fW, fA, ones;
+  DevMat W, T;                           // Jtot x R: scaled operand of the mode-A product; T = Xall' * A
+  uint64_t T_version = 0;                // version of A that T was computed from
+  DevMat P, muDB, DeltaB, PDold, gM, gS;
+  double *G2 = nullptr, *Binv2 = nullptr, *Binv3 = nullptr, *rho2 = nullptr, *rho3 = nullptr, *contrib = nullptr,
+         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr;
+  double* segn_host = nullptr;           // pinned: K x 4 per-slice objective terms + 1 residual
+  bool explicit_residual = false;        // objective needs ||X_k - A D_k B_k'||^2 (mode A is not updated last)
 };
 
 struct View3 {                // how mode position n of an object is computed
@@ -91,10 +117,20 @@ class Engine {
   void compute_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout);
   void pack_operand(View3& v, int which);
   void precompute_mode(ModeState& m, int n_rho_terms, bool do_chol);
+  void fill_prep(ModeState& m, PrepArgs& a, int n_rho_terms, bool do_chol);
+  void apply_bsum(ModeState& m);
   void run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt);
   void eval_objective(bool first, double f[4]);
   void check_errors(aoadmm_out* out);
   void allreduce(double* buf, size_t count);
+  // PARAFAC2 block (cmtf_fun_AOADMM.m:157-250, :509-589)
+  void setup_par2(const aoadmm_problem* prob, int p);
+  void par2_update_T(Par2State& s);
+  void par2_precompute_A(ModeState& m, int n_rho_terms);
+  void par2_update_B(ModeState& m, int outer_iter);
+  void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct);
+  void par2_refresh_gram(Par2State& s);
+  DevMat* par2_field(int field, int index, int slice, int64_t* row_off, int64_t* nrows);
 
   ModeState& mode(int id) { return modes_[id - 1]; }
 
@@ -103,6 +139,7 @@ class Engine {
   std::vector<ObjectState> objects_;
   std::vector<int> coupling_type_;
   std::vector<DevMat> delta_;  // coupling_fac per coupling id
+  std::vector<Par2State> par2_;
   bool has_ridge_ = false;
 
   // distributed

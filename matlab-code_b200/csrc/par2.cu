@@ -1,0 +1,691 @@
+// par2.cu - PARAFAC2 block kernels (see par2.cuh for the layout and the reference lines each entry point replaces).
+#include "par2.cuh"
+
+#include <algorithm>
+
+namespace aoadmm {
+
+namespace {
+
+constexpr int kP2Threads = 256;
+
+// ---------------------------------------------------------------------------------------------------------
+// small dense helpers on an R x R column-major matrix held in shared memory (whole CTA cooperates)
+// ---------------------------------------------------------------------------------------------------------
+// right-looking Cholesky of the lower triangle of W; returns false (uniformly) when a pivot is not positive
+__device__ bool cta_cholesky(double* W, int R) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = 0; j < R; ++j) {
+    const double d = W[j * R + j];
+    if (!(d > 0.0) || !isfinite(d)) return false;  // every thread reads the same value
+    const double s = sqrt(d);
+    __syncthreads();
+    for (int i = j + 1 + tid; i < R; i += nt) W[j * R + i] = W[j * R + i] / s;
+    if (tid == 0) W[j * R + j] = s;
+    __syncthreads();
+    const int n = R - j - 1;
+    for (int e = tid; e < n * n; e += nt) {
+      const int ci = e / n, ri = e % n;
+      if (ri >= ci) W[(j + 1 + ci) * R + (j + 1 + ri)] -= W[j * R + (j + 1 + ri)] * W[j * R + (j + 1 + ci)];
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// V (row i, column c at V[i*R + c]) = inv(L) for the lower factor held in W; then out = inv(L)' * inv(L)
+__device__ void cta_inverse_from_chol(const double* W, double* V, int R, double* out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int c = tid; c < R; c += nt) {
+    for (int i = 0; i < R; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s = fma(-W[k * R + i], V[k * R + c], s);
+      V[i * R + c] = s / W[i * R + i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < R * R; e += nt) {
+    const int ca = e / R, cb = e % R;
+    const int lo = ca > cb ? ca : cb;
+    double acc = 0.0;
+    for (int i = lo; i < R; ++i) acc = fma(V[i * R + ca], V[i * R + cb], acc);
+    out[e] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void par2_scale_rows_kernel(Par2Layout L, double* __restrict__ out, const double* __restrict__ in,
+                                       const double* __restrict__ C, long long ldc, double scale,
+                                       const double* __restrict__ addend, double add_scale) {
+  const long long n = L.Jtot * L.R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / L.Jtot, j = idx % L.Jtot;
+    double v = scale * in[idx] * C[L.seg[j] + r * ldc];
+    if (addend != nullptr) v += add_scale * addend[idx];
+    out[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kP2Threads) par2_batched_gram_kernel(Par2Layout L, const double* __restrict__ Bst,
+                                                                        double* __restrict__ G2) {
+  const int k = blockIdx.x, R = L.R;
+  const long long j0 = L.joff[k];
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  double* out = G2 + (size_t)k * R * R;
+  for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+    const int a = e % R, b = e / R;
+    if (a > b) continue;
+    const double* xa = Bst + j0 + (long long)a * L.Jtot;
+    const double* xb = Bst + j0 + (long long)b * L.Jtot;
+    double acc = 0.0;
+    for (int j = 0; j < Jk; ++j) acc = fma(xa[j], xb[j], acc);
+    out[a + b * R] = acc;
+    out[b + a * R] = acc;
+  }
+}
+
+__global__ void par2_modeA_had_kernel(Par2Layout L, const double* __restrict__ G2, const double* __restrict__ C,
+                                      long long ldc, double* __restrict__ Csum) {
+  const int R = L.R;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R * R) return;
+  const int a = e % R, b = e / R;
+  double acc = 0.0;
+  for (int k = 0; k < L.K; ++k) acc += (C[k + a * ldc] * G2[(size_t)k * R * R + e]) * C[k + b * ldc];
+  Csum[e] = acc;
+}
+
+__global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2SysArgs a) {
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  __shared__ double s_rho;
+  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  double* W = sm;            // system matrix / Cholesky factor
+  double* V = sm + RR;       // inverse of the factor
+  double* rhs_s = sm + 2 * RR;  // R
+  const long long j0 = L.joff[k];
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  if (k == 0 && tid == 0 && a.ctl != nullptr) {  // a new inner loop starts (err is sticky)
+    a.ctl->done = 0;
+    a.ctl->iters = 0;
+    a.ctl->res[0] = a.ctl->res[1] = a.ctl->res[2] = a.ctl->res[3] = 0.0;
+  }
+  double tr = 0.0;
+  for (int e = tid; e < RR; e += nt) {
+    const int r = e % R, c = e / R;
+    double v;
+    if (a.mode == 2)
+      v = (a.C[k + r * a.ldc] * a.G1[e]) * a.C[k + c * a.ldc];   // diag(c_k) A'A diag(c_k)   (:194)
+    else
+      v = a.G1[e] * a.G2[(size_t)k * RR + e];                    // A'A .* B_k'B_k            (:222)
+    V[e] = v;  // keep C_k for the system assembly
+    if (r == c) tr += v;
+  }
+  tr = block_sum(tr, red);
+  if (tid == 0) {
+    s_rho = tr / (double)R * a.rho_scale;                         // :195-198, :223
+    a.rho_k[k] = s_rho;
+  }
+  __syncthreads();
+  const double half = s_rho / 2.0;
+  for (int e = tid; e < RR; e += nt) {
+    double b = a.weight * V[e];
+    if (e % (R + 1) == 0) {
+      for (int q = 0; q < a.n_rho_terms; ++q) b += half;
+      if (a.ridge != 0.0) b += a.ridge;
+      if (a.bsum_half != 0.0) b += a.bsum_half;
+    }
+    W[e] = b;
+  }
+  if (a.mode == 3) {
+    // a_k(r) = w * sum_j T(j,r) B_k(j,r)   (= w * diag(A' X_k B_k), :221)  [+ bsum/2 * C(k,r), :231]
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int r = warp; r < R; r += nw) {
+      const double* t = a.T + j0 + (long long)r * L.Jtot;
+      const double* b = a.Bst + j0 + (long long)r * L.Jtot;
+      double acc = 0.0;
+      for (int j = lane; j < Jk; j += 32) acc = fma(t[j], b[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        double v = a.weight * acc;
+        if (a.bsum_half != 0.0) v += a.bsum_half * a.C[k + r * a.ldc];
+        rhs_s[r] = v;
+        a.rhs[k + (long long)r * L.K] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const bool ok = cta_cholesky(W, R);
+  if (!ok) {
+    if (tid == 0 && a.ctl != nullptr) a.ctl->err = 3;
+    return;
+  }
+  if (a.mode == 3 && a.ls_direct) {
+    // C(k,:) = (B_k \ a_k)'  (:236): forward / backward substitution with the Cholesky factor
+    if (tid == 0) {
+      for (int i = 0; i < R; ++i) {
+        double s = rhs_s[i];
+        for (int q = 0; q < i; ++q) s = fma(-W[q * R + i], rhs_s[q], s);
+        rhs_s[i] = s / W[i * R + i];
+      }
+      for (int i = R - 1; i >= 0; --i) {
+        double s = rhs_s[i];
+        for (int q = i + 1; q < R; ++q) s = fma(-W[i * R + q], rhs_s[q], s);
+        rhs_s[i] = s / W[i * R + i];
+      }
+      for (int r = 0; r < R; ++r) a.fac_out[k + (long long)r * L.K] = rhs_s[r];
+    }
+    return;
+  }
+  cta_inverse_from_chol(W, V, R, a.Binv + (size_t)k * RR);
+}
+
+__global__ void par2_rho_max_kernel(const double* __restrict__ rho_k, int K, double* __restrict__ out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmax(m, rho_k[k]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) r = fmax(r, red[w]);
+    *out = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ADMM_B_Parafac2, step 1 (:525-535): per slice  B_k = A_inner_k inv(Bsys_k);  P_k = polar((B_k+mu_k) DeltaB')
+// The polar factor U V' of the thin SVD is computed with a one-sided (Hestenes) Jacobi iteration on the J_k x R
+// matrix, round-robin pair ordering, one warp per column pair.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl,
+                                                                   int use_gmem) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  extern __shared__ double sm[];
+  __shared__ int s_rot;
+  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const long long j0 = L.joff[k], ld = L.Jtot;
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  double* dB = sm;
+  double* Bi = sm + RR;
+  double* V = sm + 2 * RR;
+  double* M = use_gmem ? a.gM + j0 * R : sm + 3 * RR;
+  double* S = use_gmem ? a.gS + j0 * R : sm + 3 * RR + (size_t)L.Jmax * R;
+  const double rho = a.rho_k[k], half = rho / 2.0;
+  for (int e = tid; e < RR; e += nt) {
+    dB[e] = a.DeltaB[e];
+    Bi[e] = a.Binv[(size_t)k * RR + e];
+    V[e] = (e % (R + 1) == 0) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int nitems = Jk * R;
+  // A_inner = A_k + rho_k/2 (P_k DeltaB - mu_k) [+ rho_k/2 (Z_k - muZ_k)]          (:526-529)
+  for (int it = tid; it < nitems; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    const long long g = j0 + j + (long long)c * ld;
+    double pd = 0.0;
+    for (int r = 0; r < R; ++r) pd = fma(a.P[j0 + j + (long long)r * ld], dB[r + c * R], pd);
+    a.PDold[g] = pd;
+    double v = a.A[g] + half * (pd - a.mu[g]);
+    if (a.con_active) v += half * (a.Z[g] - a.muZ[g]);
+    S[j + c * Jk] = v;
+  }
+  __syncthreads();
+  // B_k = A_inner inv(Bsys_k)   (:530) ;  M = B_k + mu_k
+  for (int it = tid; it < nitems; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    const long long g = j0 + j + (long long)c * ld;
+    double x = 0.0;
+    for (int r = 0; r < R; ++r) x = fma(S[j + r * Jk], Bi[r + c * R], x);
+    a.B[g] = x;
+    M[j + c * Jk] = x + a.mu[g];
+  }
+  __syncthreads();
+  // S = M DeltaB'   (:532)
+  for (int it = tid; it < nitems; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    double x = 0.0;
+    for (int r = 0; r < R; ++r) x = fma(M[j + r * Jk], dB[c + r * R], x);
+    S[j + c * Jk] = x;
+  }
+  __syncthreads();
+  // one-sided Jacobi: S <- S*V with orthogonal columns
+  const int Re = (R + 1) & ~1, npairs = Re / 2;
+  const double tol = 2.220446049250313e-16 * sqrt((double)Jk);
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int rd = 0; rd < Re - 1; ++rd) {
+      for (int q = warp; q < npairs; q += nw) {
+        int p1, p2;
+        if (q == 0) {
+          p1 = Re - 1;
+          p2 = rd;
+        } else {
+          p1 = (rd + q) % (Re - 1);
+          p2 = (rd - q + Re - 1) % (Re - 1);
+        }
+        if (p1 > p2) {
+          const int t = p1;
+          p1 = p2;
+          p2 = t;
+        }
+        if (p2 >= R) continue;  // bye (odd R)
+        double* x = S + (size_t)p1 * Jk;
+        double* y = S + (size_t)p2 * Jk;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int j = lane; j < Jk; j += 32) {
+          const double xv = x[j], yv = y[j];
+          al = fma(xv, xv, al);
+          be = fma(yv, yv, be);
+          ga = fma(xv, yv, ga);
+        }
+        al = warp_sum(al);
+        be = warp_sum(be);
+        ga = warp_sum(ga);
+        if (fabs(ga) > tol * sqrt(al * be)) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (int j = lane; j < Jk; j += 32) {
+            const double xv = x[j], yv = y[j];
+            x[j] = cs * xv - sn * yv;
+            y[j] = sn * xv + cs * yv;
+          }
+          for (int i = lane; i < R; i += 32) {
+            const double xv = V[i + p1 * R], yv = V[i + p2 * R];
+            V[i + p1 * R] = cs * xv - sn * yv;
+            V[i + p2 * R] = sn * xv + cs * yv;
+          }
+          if (lane == 0) s_rot = 1;
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (rot == 0) break;
+  }
+  // singular values -> 1/sigma (kept in the Bi area, no longer needed)
+  for (int r = warp; r < R; r += nw) {
+    const double* x = S + (size_t)r * Jk;
+    double al = 0.0;
+    for (int j = lane; j < Jk; j += 32) al = fma(x[j], x[j], al);
+    al = warp_sum(al);
+    if (lane == 0) Bi[r] = (al > 0.0) ? 1.0 / sqrt(al) : 0.0;
+  }
+  __syncthreads();
+  // P_k = U V'   (:534)
+  for (int it = tid; it < nitems; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    double x = 0.0;
+    for (int r = 0; r < R; ++r) x = fma(S[j + r * Jk] * Bi[r], V[c + r * R], x);
+    a.P[j0 + j + (long long)c * ld] = x;
+  }
+  __syncthreads();
+  // contribution to DeltaB: rho_k P_k' (B_k + mu_k)   (:541)
+  for (int e = tid; e < RR; e += nt) {
+    const int ra = e % R, cb = e / R;
+    const double* pc = a.P + j0 + (long long)ra * ld;
+    const double* mc = M + (size_t)cb * Jk;
+    double acc = 0.0;
+    for (int j = 0; j < Jk; ++j) acc = fma(pc[j], mc[j], acc);
+    a.contrib[(size_t)k * RR + e] = rho * acc;
+  }
+}
+
+__global__ void par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  __shared__ double s_sum;
+  const int R = L.R, RR = R * R;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < L.K; ++k) s += a.rho_k[k];   // :542
+    s_sum = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < RR; e += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < L.K; ++k) acc += a.contrib[(size_t)k * RR + e];
+    a.DeltaB[e] = acc / s_sum;                        // :544
+  }
+}
+
+__global__ void __launch_bounds__(kP2Threads) par2_B_step2a_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const long long j0 = L.joff[k], ld = L.Jtot;
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  double* dB = sm;
+  for (int e = tid; e < RR; e += nt) dB[e] = a.DeltaB[e];
+  __syncthreads();
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int it = tid; it < Jk * R; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    const long long g = j0 + j + (long long)c * ld;
+    double pd = 0.0;
+    for (int r = 0; r < R; ++r) pd = fma(a.P[j0 + j + (long long)r * ld], dB[r + c * R], pd);
+    const double b = a.B[g];
+    const double mun = a.mu[g] + b - pd;               // :546
+    a.mu[g] = mun;
+    const double d0 = b - pd, d2 = a.PDold[g] - pd;
+    s0 = fma(d0, d0, s0);
+    s1 = fma(b, b, s1);
+    s2 = fma(d2, d2, s2);
+    s3 = fma(mun, mun, s3);
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  s3 = block_sum(s3, red);
+  if (tid == 0) {
+    double* o = a.norms + (size_t)k * 8;
+    o[0] = s0;
+    o[1] = s1;
+    o[2] = s2;
+    o[3] = s3;
+  }
+}
+
+__global__ void par2_B_form_prox_input_kernel(Par2Layout L, Par2BArgs a, double* __restrict__ V, const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  const long long n = L.Jtot * L.R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x)
+    V[idx] = a.B[idx] + a.muZ[idx];
+}
+
+__global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L, Par2BArgs a, InnerTol tol,
+                                                                    InnerCtl* ctl, unsigned* counter) {
+  if (ctl->done != 0) return;
+  __shared__ double red[32];
+  __shared__ bool s_last;
+  const int k = blockIdx.x, R = L.R, tid = threadIdx.x, nt = blockDim.x;
+  const long long j0 = L.joff[k], ld = L.Jtot;
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  if (a.con_active) {
+    const double rho = a.rho_k[k];
+    double s4 = 0.0, s5 = 0.0, s6 = 0.0;
+    for (int it = tid; it < Jk * R; it += nt) {
+      const int c = it / Jk, j = it % Jk;
+      const long long g = j0 + j + (long long)c * ld;
+      const double b = a.B[g], muz = a.muZ[g], zold = a.Z[g];
+      const double z = (a.Znew != nullptr) ? a.Znew[g] : prox_elem(a.prox_kind, b + muz, a.p0, a.p1, rho);  // :568
+      const double mun = muz + b - z;                                                                       // :569
+      a.Z[g] = z;
+      a.muZ[g] = mun;
+      const double d4 = b - z, d5 = zold - z;
+      s4 = fma(d4, d4, s4);
+      s5 = fma(d5, d5, s5);
+      s6 = fma(mun, mun, s6);
+    }
+    s4 = block_sum(s4, red);
+    s5 = block_sum(s5, red);
+    s6 = block_sum(s6, red);
+    if (tid == 0) {
+      double* o = a.norms + (size_t)k * 8;
+      o[4] = s4;
+      o[5] = s5;
+      o[6] = s6;
+    }
+  }
+  __threadfence();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // residuals of :558-585, averaged over the slices in slice order (deterministic)
+  double rpk = 0.0, rdk = 0.0, rpc = 0.0, rdc = 0.0;
+  for (int kk = tid; kk < L.K; kk += nt) {
+    const double* o = a.norms + (size_t)kk * 8;
+    const double nB = sqrt(o[1]);
+    rpk += sqrt(o[0]) / nB;
+    rdk += sqrt(o[2]) / sqrt(o[3]);                   // not guarded in the reference (:584)
+    if (a.con_active) {
+      rpc += sqrt(o[4]) / nB;
+      const double sc = sqrt(o[6]);
+      rdc += (sc > 0.0) ? sqrt(o[5]) / sc : sqrt(o[5]);
+    }
+  }
+  rpk = block_sum(rpk, red);
+  rdk = block_sum(rdk, red);
+  rpc = block_sum(rpc, red);
+  rdc = block_sum(rdc, red);
+  if (tid == 0) {
+    const double invK = 1.0 / (double)L.K;
+    rpk *= invK;
+    rdk *= invK;
+    rpc *= invK;
+    rdc *= invK;
+    ctl->res[0] = rpk;
+    ctl->res[1] = rdk;
+    ctl->res[2] = rpc;
+    ctl->res[3] = rdc;
+    ctl->iters += 1;
+    const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
+    if (!cont) ctl->done = 1;
+    if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+    *counter = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kP2Threads) par2_seg_norms_kernel(Par2Layout L, const double* __restrict__ Bst,
+                                                                     const double* __restrict__ Z,
+                                                                     const double* __restrict__ P,
+                                                                     const double* __restrict__ DeltaB, int reg_kind,
+                                                                     double* __restrict__ out) {
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const long long j0 = L.joff[k], ld = L.Jtot;
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  double* dB = sm;
+  for (int e = tid; e < RR; e += nt) dB[e] = DeltaB[e];
+  __syncthreads();
+  double n2 = 0.0, dz = 0.0, dp = 0.0, rg = 0.0;
+  for (int it = tid; it < Jk * R; it += nt) {
+    const int c = it / Jk, j = it % Jk;
+    const long long g = j0 + j + (long long)c * ld;
+    const double b = Bst[g];
+    double pd = 0.0;
+    for (int r = 0; r < R; ++r) pd = fma(P[j0 + j + (long long)r * ld], dB[r + c * R], pd);
+    n2 = fma(b, b, n2);
+    dp = fma(b - pd, b - pd, dp);
+    if (Z != nullptr) {
+      const double d = b - Z[g];
+      dz = fma(d, d, dz);
+    }
+    switch (reg_kind) {
+      case RED_L1: rg += fabs(b); break;
+      case RED_NNZ: rg += (b != 0.0) ? 1.0 : 0.0; break;
+      case RED_NORM2: rg = fma(b, b, rg); break;
+      case RED_TVSUM:
+        if (j + 1 < Jk) rg += Bst[g + 1] - b;
+        break;
+      case RED_GLQUAD: {
+        double lx = b;
+        if (Jk > 1) {
+          if (j == 0) lx = b - Bst[g + 1];
+          else if (j == Jk - 1) lx = b - Bst[g - 1];
+          else lx = 2.0 * b - Bst[g - 1] - Bst[g + 1];
+        }
+        rg = fma(b, lx, rg);
+        break;
+      }
+      default: break;
+    }
+  }
+  n2 = block_sum(n2, red);
+  dz = block_sum(dz, red);
+  dp = block_sum(dp, red);
+  rg = block_sum(rg, red);
+  if (reg_kind == RED_COLNORM) {
+    double tot = 0.0;
+    for (int c = 0; c < R; ++c) {
+      double s = 0.0;
+      for (int j = tid; j < Jk; j += nt) {
+        const double b = Bst[j0 + j + (long long)c * ld];
+        s = fma(b, b, s);
+      }
+      s = block_sum(s, red);
+      if (tid == 0) tot += sqrt(s);
+    }
+    rg = tot;
+  }
+  if (tid == 0) {
+    out[(size_t)k * 4 + 0] = n2;
+    out[(size_t)k * 4 + 1] = dz;
+    out[(size_t)k * 4 + 2] = dp;
+    out[(size_t)k * 4 + 3] = rg;
+  }
+}
+
+__global__ void __launch_bounds__(256) par2_residual_kernel(Par2Layout L, const double* __restrict__ X, long long ldX,
+                                                             long long I, const double* __restrict__ A, long long ldA,
+                                                             const double* __restrict__ Bst,
+                                                             const double* __restrict__ C, long long ldc,
+                                                             double* __restrict__ partials, unsigned* counter,
+                                                             double* __restrict__ res) {
+  __shared__ double red[32];
+  __shared__ bool s_last;
+  const int R = L.R;
+  const long long n = I * L.Jtot;
+  double acc = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % I, j = idx / I;
+    const int k = L.seg[j];
+    double m = 0.0;
+    for (int r = 0; r < R; ++r) m = fma(A[i + r * ldA] * C[k + r * ldc], Bst[j + r * L.Jtot], m);
+    const double v = X[i + j * ldX] - m;
+    acc = fma(v, v, acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += partials[b];
+    *res = v;
+    *counter = 0u;
+  }
+}
+
+template <typename Kern>
+void opt_in_smem(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+unsigned flat_grid(long long n) { return (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8); }
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+}  // namespace
+
+size_t par2_step1_smem_bytes(long long Jmax, int R) {
+  const size_t small = (size_t)3 * R * R * sizeof(double);
+  const size_t big = small + (size_t)2 * Jmax * R * sizeof(double);
+  return big <= kSmemBudget ? big : small;
+}
+
+int par2_scale_rows(const Par2Layout& L, double* out, const double* in, const double* C, long long ldc, double scale,
+                    const double* addend, double add_scale, cudaStream_t st) {
+  par2_scale_rows_kernel<<<flat_grid(L.Jtot * L.R), 256, 0, st>>>(L, out, in, C, ldc, scale, addend, add_scale);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_batched_gram(const Par2Layout& L, const double* Bst, double* G2, cudaStream_t st) {
+  par2_batched_gram_kernel<<<L.K, kP2Threads, 0, st>>>(L, Bst, G2);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_modeA_had(const Par2Layout& L, const double* G2, const double* C, long long ldc, double* Csum, cudaStream_t st) {
+  par2_modeA_had_kernel<<<(unsigned)ceil_div(L.R * L.R, 128), 128, 0, st>>>(L, G2, C, ldc, Csum);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * L.R * L.R + L.R) * sizeof(double);
+  opt_in_smem(par2_sys_prep_kernel, smem);
+  par2_sys_prep_kernel<<<L.K, 128, smem, st>>>(L, a);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st) {
+  par2_rho_max_kernel<<<1, 256, 0, st>>>(rho_k, K, out);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
+  const size_t smem = par2_step1_smem_bytes(L.Jmax, L.R);
+  const int use_gmem = (smem == (size_t)3 * L.R * L.R * sizeof(double)) ? 1 : 0;
+  opt_in_smem(par2_B_step1_kernel, smem);
+  par2_B_step1_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl, use_gmem);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
+  par2_B_deltaB_kernel<<<1, 256, 0, st>>>(L, a, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_step2a(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
+  const size_t smem = (size_t)L.R * L.R * sizeof(double);
+  opt_in_smem(par2_B_step2a_kernel, smem);
+  par2_B_step2a_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_form_prox_input(const Par2Layout& L, const Par2BArgs& a, double* V, const InnerCtl* ctl, cudaStream_t st) {
+  par2_B_form_prox_input_kernel<<<flat_grid(L.Jtot * L.R), 256, 0, st>>>(L, a, V, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, InnerCtl* ctl, unsigned* counter,
+                  cudaStream_t st) {
+  par2_B_step2b_kernel<<<L.K, kP2Threads, 0, st>>>(L, a, tol, ctl, counter);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, const double* P, const double* DeltaB,
+                   int reg_kind, double* out, cudaStream_t st) {
+  const size_t smem = (size_t)L.R * L.R * sizeof(double);
+  opt_in_smem(par2_seg_norms_kernel, smem);
+  par2_seg_norms_kernel<<<L.K, kP2Threads, smem, st>>>(L, Bst, Z, P, DeltaB, reg_kind, out);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_residual(const Par2Layout& L, const double* X, long long ldX, long long I, const double* A, long long ldA,
+                  const double* Bst, const double* C, long long ldc, double* partials, unsigned* counter, double* res,
+                  cudaStream_t st) {
+  par2_residual_kernel<<<flat_grid(I * L.Jtot), 256, 0, st>>>(L, X, ldX, I, A, ldA, Bst, C, ldc, partials, counter, res);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+}  // namespace aoadmm

@@ -1,0 +1,104 @@
+// par2.cuh - device kernels of the PARAFAC2 block (functions/cmtf_fun_AOADMM.m:157-250 precompute,
+// :509-589 ADMM_B_Parafac2, :602-606 / :638-645 row-wise mode-C solves, :1254-1265 + :1351-1362 objective terms).
+//
+// Layout: the K slices X_k (I x J_k, column-major) of one PARAFAC2 object are stored side by side as one
+// I x Jtot column-major matrix (Jtot = sum_k J_k, slice k = columns joff[k] .. joff[k+1]-1), and every per-slice
+// J_k x R matrix (B_k, Z_Bk, mu_Z_Bk, P_k, mu_DeltaB_k) is stored stacked as one Jtot x R column-major matrix
+// (slice k = rows joff[k] .. joff[k+1]-1).  With this layout the two big products of the block are plain
+// matrix-block products served by the DMMA kernels of mttkrp.cu:
+//     mode A :  sum_k X_k B_k diag(c_k)   = Xall * W          W(j,:)  = B(j,:) .* C(seg(j),:)
+//     mode B :  X_k' A diag(c_k)  (all k) = (Xall' * A) .* C(seg(j),:)
+//     mode C :  diag(A' X_k B_k)          = segmented column dot of (Xall' * A) with B
+// and everything that is per-slice R x R work (Hadamard, rho_k, Cholesky, inverse, polar factor P_k) is one CTA
+// per slice.
+#pragma once
+#include "smallops.cuh"
+
+namespace aoadmm {
+
+struct Par2Layout {
+  int K = 0;
+  int R = 0;
+  long long Jtot = 0;
+  long long Jmax = 0;
+  const long long* joff = nullptr;  // device, K+1 entries
+  const int* seg = nullptr;         // device, Jtot entries: slice index of every stacked row
+};
+
+// out(j,r) = scale * in(j,r) * C(seg(j), r)  [+ add_scale * addend(j,r)]     (all stacked Jtot x R, ld = Jtot)
+int par2_scale_rows(const Par2Layout& L, double* out, const double* in, const double* C, long long ldc, double scale,
+                    const double* addend, double add_scale, cudaStream_t st);
+
+// G2[k] (R x R) = B_k' * B_k for every slice                                   (:72, :217)
+int par2_batched_gram(const Par2Layout& L, const double* Bst, double* G2, cudaStream_t st);
+
+// Csum (R x R) = sum_k diag(c_k) * G2[k] * diag(c_k)                           (:164)
+int par2_modeA_had(const Par2Layout& L, const double* G2, const double* C, long long ldc, double* Csum, cudaStream_t st);
+
+struct Par2SysArgs {
+  int mode;                // 2: B_k systems (:192-213), 3: C rows (:220-243)
+  const double* G1;        // A'A (R x R)
+  const double* G2;        // per-slice B_k'B_k (K x R x R)     (mode 3)
+  const double* C;         // C factor (K x R), ld = ldc
+  long long ldc;
+  double weight, ridge, bsum_half, rho_scale;
+  int n_rho_terms;         // number of rho_k/2*I terms
+  // mode 3 only: right-hand side a_k = w * diag(A' X_k B_k) (+ bsum/2 * C(k,:)) from T = Xall'*A and B
+  const double* T;         // Jtot x R
+  const double* Bst;       // Jtot x R
+  double* rhs;             // K x R (ld = K): row k = a_k
+  int ls_direct;           // mode 3, unconstrained + uncoupled: C(k,:) = B_k \ a_k written to fac_out (:236)
+  double* fac_out;         // K x R (ld = K)
+  // outputs
+  double* rho_k;           // K
+  double* Binv;            // K x R x R
+  InnerCtl* ctl;           // err = 3 when a system is not positive definite
+};
+int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st);
+
+// rho_max = max_k rho_k (update_constraint uses max(rho) when rho is a vector, :1423-1424)
+int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st);
+
+struct Par2BArgs {
+  const double* A;         // stacked right-hand sides A_k (Jtot x R)
+  const double* Binv;      // K x R x R
+  const double* rho_k;     // K
+  double* B;               // stacked B_k        (G.fac{m})
+  double* P;               // stacked P_k        (G.P{p})
+  double* mu;              // stacked mu_DeltaB  (G.mu_DeltaB{p})
+  double* DeltaB;          // R x R              (G.DeltaB{p})
+  double* Z;               // stacked constraint_fac or nullptr
+  double* muZ;             // stacked constraint_dual_fac or nullptr
+  int con_active;          // Z.constrained_modes(m) && iter >= iter_start_PAR2Bkconstraint
+  int prox_kind;
+  double p0, p1;
+  double* PDold;           // scratch Jtot x R: P_k*DeltaB before the update
+  double* contrib;         // scratch K x R x R: rho_k P_k'(B_k+mu_k)
+  double* gM;              // scratch Jtot x R (used when a slice does not fit shared memory)
+  double* gS;              // scratch Jtot x R
+  double* norms;           // scratch K x 8
+  double* Znew;            // deferred prox output (stacked) or nullptr
+};
+// one inner iteration of ADMM_B_Parafac2 is  step1 -> deltaB -> step2a -> [prox of every slice] -> step2b
+int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
+int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
+// coupling part: mu_k += B_k - P_k DeltaB ; per-slice norms 0..3
+int par2_B_step2a(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
+// V = B + muZ (input of a non element-wise prox)
+int par2_B_form_prox_input(const Par2Layout& L, const Par2BArgs& a, double* V, const InnerCtl* ctl, cudaStream_t st);
+// constraint part (element-wise prox inline, or Z taken from a.Znew) + residuals + exit test
+int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, InnerCtl* ctl, unsigned* counter,
+                  cudaStream_t st);
+
+// per-slice objective terms: out[k*4 + {0,1,2,3}] = ||B_k||^2, ||B_k - Z_k||^2, ||B_k - P_k DeltaB||^2, reg(B_k)
+int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, const double* P, const double* DeltaB,
+                   int reg_kind, double* out, cudaStream_t st);
+
+// res = sum_k || X_k - A diag(c_k) B_k' ||_F^2  (explicit residual of :1254-1265); partials >= 148*8 doubles
+int par2_residual(const Par2Layout& L, const double* X, long long ldX, long long I, const double* A, long long ldA,
+                  const double* Bst, const double* C, long long ldc, double* partials, unsigned* counter, double* res,
+                  cudaStream_t st);
+
+size_t par2_step1_smem_bytes(long long Jmax, int R);
+
+}  // namespace aoadmm

@@ -185,27 +185,6 @@ __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const i
 }
 
 // =====================================================================================================
-// element-wise prox (constraints_to_prox.m:13-18, :46-61)
-// =====================================================================================================
-__device__ __forceinline__ double prox_elem(int kind, double v, double p0, double p1, double rho) {
-  switch (kind) {
-    case PROX_NONNEG: return fmax(v, 0.0);
-    case PROX_BOX: return fmin(fmax(v, p0), p1);
-    case PROX_L1_REG: {
-      const double g = p0 / rho;
-      const double mag = fmax(fabs(v) - g, 0.0);
-      return (v > 0.0) ? mag : ((v < 0.0) ? -mag : 0.0);
-    }
-    case PROX_L0_REG: {
-      const double g = p0 / rho;
-      return (fabs(v) > sqrt(2.0 * g)) ? v : 0.0;
-    }
-    case PROX_RIDGE: return 1.0 / (2.0 * (p0 / rho) + 1.0) * v;
-    default: return v;
-  }
-}
-
-// =====================================================================================================
 // fused ADMM iteration (row-parallel)
 // =====================================================================================================
 struct FinInfo {
@@ -300,11 +279,13 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
 
   for (int mi = 0; mi < g.nmodes; ++mi) {
     const AdmmMode& md = g.m[mi];
-    const double rho = *md.rho;
+    // PARAFAC2 mode C: every row k has its own rho_k and its own R x R system (cmtf_fun_AOADMM.m:602-606, :638-645)
+    const bool rowsys = md.Binv_rows != nullptr;
+    const double rho = (md.rho_rows != nullptr) ? (active ? md.rho_rows[i] : 0.0) : *md.rho;
     const double half = rho / 2.0;
     sum_rho += rho;
     __syncthreads();  // previous mode's GEMM has finished reading a_s / Binv_s
-    if (BSMEM)
+    if (BSMEM && !rowsys)
       for (int e = tid; e < R * R; e += nthreads) Binv_s[e] = md.Binv[e];
     if (active) {
 #pragma unroll
@@ -327,7 +308,17 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     double x[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] = 0.0;
-    if (BSMEM && e0 + 8 <= R) {
+    if (rowsys) {
+      if (active) {
+        const double* Br = md.Binv_rows + (size_t)i * R * R;
+        for (int j = 0; j < R; ++j) {
+          const double aj = a_s[j * 32 + lane];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (e0 + c < R) x[c] = fma(aj, Br[(size_t)j * R + e0 + c], x[c]);
+        }
+      }
+    } else if (BSMEM && e0 + 8 <= R) {
       const double* bp = Binv_s + e0;
 #pragma unroll 4
       for (int j = 0; j < R; ++j) {
@@ -380,7 +371,7 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     }
     for (int mi = 0; mi < g.nmodes; ++mi) {
       const AdmmMode& md = g.m[mi];
-      const double rho = *md.rho;
+      const double rho = *md.rho;  // for a vector rho the prox uses max(rho) (update_constraint, :1423-1424)
       double sFD = 0.0, sMuD = 0.0, sFZ = 0.0, sZZ = 0.0, sMuZ = 0.0;
       const bool do_con = md.constrained && prox_is_elementwise(md.prox_kind);
 #pragma unroll

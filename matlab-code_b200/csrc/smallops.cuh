@@ -21,6 +21,27 @@ inline bool prox_is_elementwise(int k) {
   return k == PROX_NONNEG || k == PROX_BOX || k == PROX_L1_REG || k == PROX_L0_REG || k == PROX_RIDGE;
 }
 
+#ifdef __CUDACC__
+// element-wise prox operators (constraints_to_prox.m:13-18, :46-61)
+__device__ __forceinline__ double prox_elem(int kind, double v, double p0, double p1, double rho) {
+  switch (kind) {
+    case PROX_NONNEG: return fmax(v, 0.0);
+    case PROX_BOX: return fmin(fmax(v, p0), p1);
+    case PROX_L1_REG: {
+      const double g = p0 / rho;
+      const double mag = fmax(fabs(v) - g, 0.0);
+      return (v > 0.0) ? mag : ((v < 0.0) ? -mag : 0.0);
+    }
+    case PROX_L0_REG: {
+      const double g = p0 / rho;
+      return (fabs(v) > sqrt(2.0 * g)) ? v : 0.0;
+    }
+    case PROX_RIDGE: return 1.0 / (2.0 * (p0 / rho) + 1.0) * v;
+    default: return v;
+  }
+}
+#endif
+
 // ---- inner-loop control block (device resident) ---------------------------------------------------
 struct InnerCtl {
   int done;        // 1: the data-dependent exit test of the ADMM while-loop has fired
@@ -70,7 +91,9 @@ constexpr int kMaxGroup = 8;
 struct AdmmMode {
   const double* A;        // right-hand side (weighted MTTKRP [+ bsum term]) rows x R
   const double* Binv;     // inv(B), R x R (symmetric)
-  const double* rho;      // device scalar
+  const double* rho;      // device scalar (PARAFAC2 mode C: max_k rho_k, used by the prox)
+  const double* rho_rows; // optional: per-row rho (PARAFAC2 mode C), else nullptr
+  const double* Binv_rows;// optional: per-row inv(B_k), rows x R x R (PARAFAC2 mode C), else nullptr
   double* F;              // factor matrix
   double* Z;              // constraint_fac or nullptr
   double* muZ;            // constraint_dual_fac or nullptr

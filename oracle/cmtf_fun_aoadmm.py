@@ -498,7 +498,8 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
         if ridge is not None:                                                            # :1290-1300
             for n in range(nb_modes):
                 if isinstance(G['fac'][n], list):
-                    for kk in range(len(G['fac'][n])):
+                    cf = G['constraint_fac'][n]                      # :1293 loops over length(G.constraint_fac{n})
+                    for kk in range(len(cf) if isinstance(cf, list) else 0):
                         f_tensors += ridge[n] * _fro(G['fac'][n][kk]) ** 2
                 else:
                     f_tensors += ridge[n] * _fro(G['fac'][n]) ** 2

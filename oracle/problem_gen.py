@@ -338,3 +338,33 @@ def config_single_cp(sz=(12, 10, 8), R=3, seed=0, noise=0.1, constraints=None, c
     constrained = constrained if constrained is not None else [1 if c else 0 for c in constraints]
     return _finish(['CP'], sz, modes, [[1.0] * R], [noise], coupling, distr or [d_rand] * n, constrained,
                    constraints, [1.0], rng)
+
+
+def config_single_par2(I=18, Jk=(12, 9, 15, 11), R=3, seed=0, noise=0.05, constrained=(1, 0, 1), constraints=None,
+                       ridge=None):
+    """One uncoupled PARAFAC2 object with (possibly irregular, example_script4 style) slice heights J_k.
+    X_k = A diag(c_k) B_k' with B_k = Q_k H (Q_k orthonormal J_k x R) so that B_k'B_k is the same for every k."""
+    rng = np.random.RandomState(seed)
+    K = len(Jk)
+    sz = [I, [int(j) for j in Jk], K]
+    modes = [[1, 2, 3]]
+    A = rng.rand(I, R)
+    C = rng.rand(K, R) + 0.1
+    H = rng.rand(R, R) + np.eye(R)
+    X = []
+    for k in range(K):
+        Q, _ = np.linalg.qr(rng.randn(int(Jk[k]), R))
+        Xk = A @ np.diag(C[k, :]) @ (Q @ H).T
+        Nk = rng.randn(*Xk.shape)
+        X.append(Xk + noise * np.linalg.norm(Xk) / np.linalg.norm(Nk) * Nk)
+    obj, _ = normalize_objects([X], ['PAR2'])
+    nn = ('non-negativity',)
+    constraints = list(constraints) if constraints is not None else [nn if c else None for c in constrained]
+    coupling = {'lin_coupled_modes': [0, 0, 0], 'coupling_type': [], 'coupl_trafo_matrices': [None] * 3}
+    Z = {'loss_function': ['Frobenius'], 'model': ['PAR2'], 'modes': modes, 'size': sz, 'coupling': coupling,
+         'constrained_modes': list(constrained), 'constraints': constraints, 'weights': [1.0], 'object': obj}
+    if ridge is not None:
+        Z['ridge'] = list(ridge)
+    init_options = {'lambdas_init': [[1.0] * R], 'nvecs': 0, 'distr': [d_rand, d_rand, d_rand01], 'normalize': 1}
+    G = init_coupled_AOADMM_CMTF(Z, init_options, rng)
+    return Z, G, {'Atrue': [A, None, C]}

@@ -227,6 +227,86 @@ def test_dimension_tree_matches_three_pass_and_oracle(ab, dims):
     assert_state_close(Gd, Go)
 
 
+PAR2_KEYS = ('fac', 'constraint_fac', 'constraint_dual_fac', 'coupling_dual_fac', 'coupling_fac', 'P', 'DeltaB',
+             'mu_DeltaB')
+
+
+def _assert_par2_out_close(od, oo):
+    _assert_out_close(od, oo)
+    n = oo['OuterIterations'] + 1
+    assert np.max(np.abs(od['func_PAR2_coupl'][:n] - oo['func_PAR2_coupl'][:n])) < FIT_TOL
+    assert abs(od['f_PAR2_couplings'] - oo['f_PAR2_couplings']) < FIT_TOL
+
+
+@pytest.mark.parametrize('kw', [dict(I=20, J=30, K=40, Jk=30, Kp=20, R=3), dict(I=33, J=18, K=12, Jk=17, Kp=9, R=4),
+                                dict(I=64, J=40, K=24, Jk=64, Kp=32, R=16), dict(I=50, J=20, K=16, Jk=70, Kp=5, R=7)])
+def test_config4_family_cp_coupled_with_parafac2(ab, kw):
+    """C4 (example_script1 style): CP coupled in mode 1 with a regular PARAFAC2, nonneg on A, B_k, C."""
+    Z, G, _ = pg.config_cp_par2(seed=3, noise=0.1, **kw)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=20))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+def test_config4_zero_tolerances_and_noise_free(ab):
+    Z, G, _ = pg.config_cp_par2(seed=5, noise=0.0)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=30, **ZERO_TOL))
+    assert np.all(oo['innerIters'][[0, 3, 4, 5], :] == 5)
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+@pytest.mark.parametrize('case', [
+    dict(constrained=(1, 0, 1)),                                   # explicit residual objective (mode C updated last)
+    dict(constrained=(0, 0, 0)),                                   # ALS on A and row-wise ALS on C (:181, :236)
+    dict(constrained=(1, 1, 1)),                                   # nonneg B_k: element-wise prox inside the slice kernel
+    dict(constrained=(1, 1, 1), constraints=[('non-negativity',), ('l1 regularization', 1e-3), ('box', 0.0, 2.0)]),
+    dict(constrained=(0, 1, 1), constraints=[None, ('unimodality', True), ('non-negativity',)]),   # deferred per-slice prox
+    dict(constrained=(1, 1, 1), ridge=[1e-3, 2e-3, 1e-3]),
+    dict(constrained=(1, 0, 1), Jk=(7, 7, 7), R=7),               # J_k == R
+])
+def test_single_parafac2_object_irregular_slices(ab, case):
+    """example_script4 style irregular PARAFAC2 (varying J_k), every constraint placement.
+    The synthetic B_k = Q_k H have mixed signs, so a sign / sparsity constraint on B_k makes the iteration erratic
+    (objective not monotone) and rounding-level differences grow ~2x per outer iteration in BOTH implementations:
+    a 1-ulp perturbation of the ORACLE's own input moves its P_k by 4e-8 after 10 iterations (ridge case) and by O(1)
+    after 25.  Those ill-conditioned cases are compared over 6 outer iterations, the well-posed ones over 25."""
+    opts = pg.default_options(MaxOuterIters=6 if case['constrained'][1] else 25)
+    Z, G, _ = pg.config_single_par2(seed=8, **case)
+    Go, oo, Gd, od = _both(ab, Z, G, opts)
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+def test_parafac2_options_bsum_rho_factor_and_late_constraint(ab):
+    Z, G, _ = pg.config_single_par2(seed=9, constrained=(1, 1, 1))
+    opts = pg.default_options(MaxOuterIters=12, bsum=1, bsum_weight=1e-2, increase_factor_rhoBk=3.0,
+                              iter_start_PAR2Bkconstraint=5)
+    Go, oo, Gd, od = _both(ab, Z, G, opts)
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+def test_parafac2_mode_c_coupled_with_matrix(ab):
+    """third PARAFAC2 mode exactly coupled (row-wise rho_k in the Delta update, cmtf_fun_AOADMM.m:638-645, :666-669)."""
+    Z, G, _ = pg.config_single_par2(seed=10, Jk=(10, 12, 9, 11, 13, 10), constrained=(1, 0, 1))
+    rng = np.random.RandomState(3)
+    K, R, M = 6, 3, 14
+    Y = (rng.rand(K, R) + 0.1) @ rng.rand(M, R).T
+    Y = np.asfortranarray(Y / np.linalg.norm(Y))
+    nn = ('non-negativity',)
+    Z2 = dict(Z, object=Z['object'] + [Y], model=['PAR2', 'CP'], modes=[[1, 2, 3], [4, 5]], size=Z['size'] + [K, M],
+              loss_function=['Frobenius'] * 2, weights=[0.5, 0.5], constrained_modes=[1, 0, 1, 1, 1],
+              constraints=[nn, None, nn, nn, nn],
+              coupling={'lin_coupled_modes': [0, 0, 1, 1, 0], 'coupling_type': [0], 'coupl_trafo_matrices': [None] * 5})
+    init_options = {'lambdas_init': [[1.0] * R] * 2, 'nvecs': 0, 'distr': [pg.d_rand, pg.d_rand, pg.d_rand01, pg.d_rand, pg.d_rand],
+                    'normalize': 1}
+    G2 = pg.init_coupled_AOADMM_CMTF(Z2, init_options, rng)
+    Go, oo, Gd, od = _both(ab, Z2, G2, pg.default_options(MaxOuterIters=20))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
