@@ -119,3 +119,19 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp', '.m')):
                 txt = open(os.path.join(dp, f), errors='replace').read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt, os.path.join(dp, f)
+
+
+def test_mex_gateway_compiles_against_stub_mex_header():
+    """MATLAB is not available offline: the gateway source is at least compiled (syntax + C-ABI signatures) against a
+    declarations-only mex.h, and must bind only symbols that include/aoadmm.h declares."""
+    import re
+    import subprocess
+    src = os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'aoadmm_mex.cpp')
+    subprocess.check_call(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-I', os.path.join(ROOT, 'tests', 'stubs'),
+                           '-I', os.path.join(ROOT, 'include'), src])
+    header = open(os.path.join(ROOT, 'include', 'aoadmm.h')).read()
+    declared = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', header))
+    used = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', open(src).read())) - {'aoadmm_mex'}
+    assert used and used <= declared, used - declared
+    shim = open(os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'cmtf_fun_AOADMM.m')).read()
+    assert shim.startswith('function [G,out] = cmtf_fun_AOADMM(Z,Znorm_const,G,fh,gh,lscalar,uscalar,options)')
