@@ -180,21 +180,6 @@ double now_s() {
   return duration_cast<duration<double>>(steady_clock::now().time_since_epoch()).count();
 }
 
-void dev_alloc(DevMat& m, int64_t rows, int64_t cols) {
-  m.rows = rows;
-  m.cols = cols;
-  if (rows * cols > 0) {
-    AO_CUDA(cudaMalloc(&m.p, m.bytes()));
-    AO_CUDA(cudaMemset(m.p, 0, m.bytes()));
-    // the engine stream is non-blocking: legacy-stream memsets must have landed before it touches the buffer
-    AO_CUDA(cudaStreamSynchronize(0));
-  }
-}
-void dev_free(DevMat& m) {
-  if (m.p) cudaFree(m.p);
-  m.p = nullptr;
-}
-
 bool constraint_supported(int kind) {
   switch (kind) {
     case AOADMM_CON_NONE:
@@ -221,6 +206,21 @@ bool constraint_supported(int kind) {
 
 }  // namespace
 
+void dev_alloc(DevMat& m, int64_t rows, int64_t cols) {
+  m.rows = rows;
+  m.cols = cols;
+  if (rows * cols > 0) {
+    AO_CUDA(cudaMalloc(&m.p, m.bytes()));
+    AO_CUDA(cudaMemset(m.p, 0, m.bytes()));
+    // the engine stream is non-blocking: legacy-stream memsets must have landed before it touches the buffer
+    AO_CUDA(cudaStreamSynchronize(0));
+  }
+}
+void dev_free(DevMat& m) {
+  if (m.p) cudaFree(m.p);
+  m.p = nullptr;
+}
+
 // reg_func of constraints_to_prox.m:49,:53,:57,:61,:77,:81 as a reduction kind (-1: the constraint has no regulariser value)
 static int reg_red_kind(int con_kind) {
   switch (con_kind) {
@@ -239,7 +239,7 @@ struct Engine::ObjTerms {
     int idx_dot = -1, idx_had = -1;
   };
   struct PerMode {
-    int idx_norm2 = -1, idx_diffZ = -1, idx_diffD = -1, idx_reg = -1;
+    int idx_norm2 = -1, idx_diffZ = -1, idx_diffD = -1, idx_reg = -1, idx_normG = -1;
   };
   std::vector<PerObject> obj;
   std::vector<PerMode> mode;
@@ -271,9 +271,7 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   if (nb_modes_ <= 0 || n_objects_ <= 0) throw CudaError(1, "empty problem");
   has_ridge_ = prob->ridge != nullptr;
   coupling_type_.assign(prob->coupling_type, prob->coupling_type + n_couplings_);
-  for (int c = 0; c < n_couplings_; ++c)
-    if (coupling_type_[c] != 0)
-      throw CudaError(2, "coupling type " + std::to_string(coupling_type_[c]) + " is not supported by this build");
+  lin_groups_.resize(n_couplings_);
 
   modes_.resize(nb_modes_);
   for (int i = 0; i < nb_modes_; ++i) {
@@ -349,6 +347,10 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   // couplings: exact coupling needs identical shapes
   delta_.resize(n_couplings_);
   for (int c = 1; c <= n_couplings_; ++c) {
+    if (coupling_type_[c - 1] != 0) {
+      setup_linear_coupling(prob, c);
+      continue;
+    }
     int first = -1;
     for (auto& m : modes_)
       if (m.coupling == c) {
@@ -374,7 +376,7 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
         prox_bytes = std::max(prox_bytes, prox_scratch_bytes(m.con.kind, m.rows, m.R));
       }
     }
-    if (m.coupling != 0) dev_alloc(m.muD, m.rows, m.R);
+    if (m.coupling != 0 && m.lin < 0) dev_alloc(m.muD, m.rows, m.R);  // linear couplings: allocated with their own shape
     dev_alloc(m.A, m.rows, m.R);
     dev_alloc(m.Alast, m.rows, m.R);
     dev_alloc(m.C, m.R, m.R);
@@ -389,6 +391,8 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     gram_ws = std::max(gram_ws, gram_ws_doubles(m.rows, m.R));
     admm_ws = std::max(admm_ws, admm_ws_doubles(m.rows, m.R, kMaxGroup));
   }
+  for (int c = 1; c <= n_couplings_; ++c)
+    if (coupling_type_[c - 1] != 0) lin_build_jobs(c);
   AO_CUDA(cudaMalloc(&gram_ws_, gram_ws * sizeof(double)));
   AO_CUDA(cudaMalloc(&admm_partials_, admm_ws * sizeof(double)));
   AO_CUDA(cudaMalloc(&admm_sums_, (6 * kMaxGroup + 1) * sizeof(double)));
@@ -483,6 +487,7 @@ Engine::~Engine() {
     }
   }
   for (auto& d : delta_) dev_free(d);
+  free_linear_coupling();
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
     for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
@@ -812,7 +817,7 @@ void Engine::fill_prep(ModeState& m, PrepArgs& a, int n_rho_terms, bool do_chol)
   a.bsum_half = opt_.bsum ? opt_.bsum_weight / 2.0 : 0.0;
   a.n_rho_terms = n_rho_terms;
   a.rho_scale = 1.0;
-  a.HHt = nullptr;
+  a.HHt = (m.lin >= 0 && lin_modes_[m.lin].ctype == 2) ? lin_modes_[m.lin].HHt.p : nullptr;  // :314
   a.do_chol = do_chol ? 1 : 0;
   a.C = m.C.p;
   a.B = m.B.p;
@@ -1027,7 +1032,12 @@ void Engine::build_objective_jobs() {
     if (m.par2_role == 2) continue;  // per-slice terms come from par2_seg_norms
     t.idx_norm2 = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R);
     if (m.constrained) t.idx_diffZ = add(RED_DIFF2, m.fac.p, m.Z.p, m.rows, m.R);
-    if (m.coupling != 0) t.idx_diffD = add(RED_DIFF2, m.fac.p, delta_[m.coupling - 1].p, m.rows, m.R);
+    if (m.coupling != 0 && m.lin < 0) t.idx_diffD = add(RED_DIFF2, m.fac.p, delta_[m.coupling - 1].p, m.rows, m.R);
+    if (m.lin >= 0) {  // :1313-1321: ||G(F) - D(Delta)|| over ||G(F)|| (types 1,2,5) or ||F|| (types 3,4)
+      LinMode& lm = lin_modes_[m.lin];
+      t.idx_diffD = add(RED_DIFF2, lm.S1.p, lm.S2.p, lm.S1.rows, (int)lm.S1.cols);
+      if (lm.ctype == 1 || lm.ctype == 2 || lm.ctype == 5) t.idx_normG = add(RED_NORM2, lm.S1.p, nullptr, lm.S1.rows, (int)lm.S1.cols);
+    }
     if (m.constrained && reg_red_kind(m.con.kind) >= 0)
       t.idx_reg = add(reg_red_kind(m.con.kind), m.fac.p, nullptr, m.rows, m.R);
   }
@@ -1085,6 +1095,12 @@ void Engine::eval_objective(bool first, double f[4]) {
       f_obj[p] = o.weight * (o.znorm - 2.0 * r2[0] + r2[1]);
     }
   }
+  for (auto& m : modes_)
+    if (m.lin >= 0) {
+      LinMode& lm = lin_modes_[m.lin];
+      lin_G(lm, m, m.fac.p, lm.S1.p, nullptr);
+      lin_D(lm, m, delta_[m.coupling - 1].p, delta_[m.coupling - 1], lm.S2.p, nullptr);
+    }
   for (auto& s : par2_) {
     ModeState& mb = mode(s.m2);
     launches_ += par2_seg_norms(s.lay, mb.fac.p, mb.constrained ? mb.Z.p : nullptr, s.P.p, s.DeltaB.p,
@@ -1152,8 +1168,10 @@ void Engine::eval_objective(bool first, double f[4]) {
   for (int c = 1; c <= n_couplings_; ++c) {  // :1303-1329
     double cp = 0.0;
     for (int i = 0; i < nb_modes_; ++i)
-      if (modes_[i].coupling == c)
-        cp += std::sqrt(r[terms_->mode[i].idx_diffD]) / std::sqrt(r[terms_->mode[i].idx_norm2]);
+      if (modes_[i].coupling == c) {
+        const int iden = terms_->mode[i].idx_normG >= 0 ? terms_->mode[i].idx_normG : terms_->mode[i].idx_norm2;
+        cp += std::sqrt(r[terms_->mode[i].idx_diffD]) / std::sqrt(r[iden]);
+      }
     f_coupl += cp;
     if (cp != 0.0) ++nz;
   }
@@ -1424,12 +1442,21 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
             }
             refresh_gram(m);                                         // :148
           } else {
-            precompute_mode(m, 1 + (m.constrained ? 1 : 0), true);  // :269-273
+            const int ct = coupling_type_[coupl_id - 1];
+            const int con = m.constrained ? 1 : 0;
+            if (ct == 0 || ct == 3 || ct == 4) precompute_mode(m, 1 + con, true);   // :269-273, :336-340, :358-362
+            else if (ct == 2) precompute_mode(m, con, true);                         // :314-318 (rho/2*H*H' + constraint)
+            else precompute_mode(m, 0, false);                                       // :288-294, :377-383: B stays w*C
           }
         }
       }
       if (coupl_id != 0) {                                           // :253
-        run_admm(cm, delta_[coupl_id - 1].p, opt_);                  // :277
+        if (coupling_type_[coupl_id - 1] == 0) {
+          run_admm(cm, delta_[coupl_id - 1].p, opt_);                // :277
+        } else {
+          lin_prepare_group(coupl_id);
+          run_admm_linear(coupl_id, cm, opt_);                       // :300, :322, :344, :366, :389
+        }
         for (ModeState* mp : cm) refresh_gram(*mp);                  // :393-403
       }
     }

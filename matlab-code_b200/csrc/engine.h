@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/aoadmm.h"
+#include "linalg.cuh"
 #include "mttkrp.cuh"
 #include "par2.cuh"
 #include "smallops.cuh"
@@ -18,6 +19,9 @@ struct DevMat {
   int64_t rows = 0, cols = 0;
   size_t bytes() const { return (size_t)rows * cols * sizeof(double); }
 };
+
+void dev_alloc(DevMat& m, int64_t rows, int64_t cols);  // zero-initialised device matrix
+void dev_free(DevMat& m);
 
 struct NcclApi;  // dlopen'ed NCCL entry points (multi-GPU only)
 
@@ -39,10 +43,41 @@ struct ModeState {
   InnerCtl* ctl = nullptr;    // device; for coupled modes all modes of the group share the group's block
   int ctl_index = -1;
   uint64_t version = 1;       // bumped whenever fac changes (validity stamp for cached partial contractions)
+  int lin = -1;               // index into Engine::lin_modes_ when the mode is linearly coupled (type 1..5)
   // PARAFAC2 objects: role 1 = A (first mode), 2 = stacked B_k, 3 = C; par2 = index into Engine::par2_
   int par2_role = 0, par2 = -1;
   const double* rho_rows = nullptr;   // role 3: per-row rho_k
   const double* Binv_rows = nullptr;  // role 3: per-row inv(B_k)
+};
+
+// Linear coupling (coupling types 1..5, cmtf_fun_AOADMM.m:278-389, :698-1075): per-mode operands.
+// The coupling constraint of mode m is  G_m(F_m) = D_m(Delta)  in the "coupling space" S_m where mu_Delta_m lives:
+//   type 1: H F = Delta        type 2: F H = Delta       type 3: F = H Delta       type 4: F = Delta H
+//   type 5: H F = Delta H2
+struct LinMode {
+  int ctype = 0;
+  DevMat H, H2;                 // Z.coupling.coupl_trafo_matrices{m}, ...matrices2{m}
+  DevMat HHt;                   // type 2: H*H' (R x R), added to the system matrix as rho/2*HHt (:314)
+  DevMat tmpF, tmpF2;           // factor-shaped scratch
+  DevMat S1, S2, S3;            // coupling-space scratch: G_m(F), D_m(Delta), D_m(Delta - Delta_old)
+  DevMat Zold;                  // constrained modes: Z before the update
+  // types 1 and 5: sylvester(B2,B,A_inner) in the eigen-bases of H'H (computed once) and of B (per outer iteration)
+  DevMat U, VB, Bwork;
+  double* lam = nullptr;        // eigenvalues of H'H (rows of F)
+  double* muB = nullptr;        // eigenvalues of B (R)
+};
+
+struct LinGroup {
+  int ctype = 0;
+  std::vector<int> modes;       // global ids, ascending
+  DevMat Dold, Ddiff, AA, AAL, AAB, AAC, BB, Dt;
+  double* AAinvdiag = nullptr;
+  double* scal = nullptr;       // device scalars: [0] sum rho, [1] 1/sum rho, [2] scratch rho of prep_system
+  RedJob* jobs_dev = nullptr;
+  int njobs = 0;
+  double* red = nullptr;        // reduction results (njobs)
+  double* red_partials = nullptr;
+  LinFin fin{};                 // which reduction feeds which residual
 };
 
 // Device state of one PARAFAC2 object (layout in par2.cuh)
@@ -123,6 +158,15 @@ class Engine {
   void eval_objective(bool first, double f[4]);
   void check_errors(aoadmm_out* out);
   void allreduce(double* buf, size_t count);
+  // linear couplings (cmtf_fun_AOADMM.m:278-389, :698-1075)
+  void setup_linear_coupling(const aoadmm_problem* prob, int coupl_id);
+  void lin_G(const LinMode& lm, const ModeState& m, const double* F, double* out, const int* skip);
+  void lin_D(const LinMode& lm, const ModeState& m, const double* Delta, const DevMat& Dshape, double* out, const int* skip);
+  void lin_Gt(const LinMode& lm, const ModeState& m, const double* Y, double* out, const int* skip);
+  void lin_build_jobs(int coupl_id);
+  void free_linear_coupling();
+  void lin_prepare_group(int coupl_id);
+  void run_admm_linear(int coupl_id, std::vector<ModeState*>& group, const aoadmm_options& opt);
   // PARAFAC2 block (cmtf_fun_AOADMM.m:157-250, :509-589)
   void setup_par2(const aoadmm_problem* prob, int p);
   void par2_update_T(Par2State& s);
@@ -140,6 +184,8 @@ class Engine {
   std::vector<int> coupling_type_;
   std::vector<DevMat> delta_;  // coupling_fac per coupling id
   std::vector<Par2State> par2_;
+  std::vector<LinMode> lin_modes_;
+  std::vector<LinGroup> lin_groups_;   // indexed by coupling id - 1 (ctype 0 groups stay empty)
   bool has_ridge_ = false;
 
   // distributed

@@ -1,0 +1,299 @@
+// linalg.cu - see linalg.cuh
+#include "linalg.cuh"
+
+#include <algorithm>
+
+namespace aoadmm {
+
+namespace {
+
+constexpr int kTile = 32;
+constexpr int kKStep = 16;
+
+__global__ void __launch_bounds__(256) dgemm_small_kernel(int transA, int transB, long long M, long long N, long long K,
+                                                           double alpha, const double* __restrict__ alpha_dev,
+                                                           const double* __restrict__ A, long long lda,
+                                                           const double* __restrict__ B, long long ldb, double beta,
+                                                           double* __restrict__ C, long long ldc,
+                                                           const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  __shared__ double As[kKStep][kTile + 1];
+  __shared__ double Bs[kKStep][kTile + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * kTile, n0 = (long long)blockIdx.y * kTile;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (long long k0 = 0; k0 < K; k0 += kKStep) {
+    for (int e = tid; e < kKStep * kTile; e += 256) {
+      int kk, mm;
+      if (transA) {  // A stored K x M: consecutive threads walk k (contiguous)
+        kk = e % kKStep;
+        mm = e / kKStep;
+      } else {       // A stored M x K: consecutive threads walk m
+        mm = e % kTile;
+        kk = e / kTile;
+      }
+      const long long gm = m0 + mm, gk = k0 + kk;
+      double v = 0.0;
+      if (gm < M && gk < K) v = transA ? A[gk + gm * lda] : A[gm + gk * lda];
+      As[kk][mm] = v;
+    }
+    for (int e = tid; e < kKStep * kTile; e += 256) {
+      int kk, nn;
+      if (transB) {  // B stored N x K
+        nn = e % kTile;
+        kk = e / kTile;
+      } else {       // B stored K x N
+        kk = e % kKStep;
+        nn = e / kKStep;
+      }
+      const long long gn = n0 + nn, gk = k0 + kk;
+      double v = 0.0;
+      if (gn < N && gk < K) v = transB ? B[gn + gk * ldb] : B[gk + gn * ldb];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kKStep; ++kk) {
+      const double a0 = As[kk][tx], a1 = As[kk][tx + 16];
+      const double b0 = Bs[kk][ty], b1 = Bs[kk][ty + 16];
+      acc[0][0] = fma(a0, b0, acc[0][0]);
+      acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]);
+      acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  const double al = alpha * (alpha_dev != nullptr ? *alpha_dev : 1.0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const long long gm = m0 + tx + 16 * i, gn = n0 + ty + 16 * j;
+      if (gm < M && gn < N) {
+        double* c = C + gm + gn * ldc;
+        *c = (beta != 0.0) ? al * acc[i][j] + beta * (*c) : al * acc[i][j];
+      }
+    }
+}
+
+struct LinArgs {
+  const double* x[5];
+  double coef[5];
+  const double* coef_dev[5];
+  int n;
+};
+
+__global__ void lincomb_kernel(double* __restrict__ out, long long n, LinArgs a, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  double c[5];
+  for (int t = 0; t < a.n; ++t) c[t] = a.coef[t] * (a.coef_dev[t] != nullptr ? *a.coef_dev[t] : 1.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int t = 0; t < a.n; ++t) v += c[t] * a.x[t][i];
+    out[i] = v;
+  }
+}
+
+__global__ void transpose_kernel(const double* __restrict__ in, long long rows, long long cols, double* __restrict__ out,
+                                 const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long c = idx % cols, r = idx / cols;  // out index = c + r*cols
+    out[idx] = in[r + c * rows];
+  }
+}
+
+__global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* __restrict__ S, long long m, int n,
+                                                               double* __restrict__ V, double* __restrict__ sig) {
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (long long e = tid; e < (long long)n * n; e += nt) V[e] = (e % (n + 1) == 0) ? 1.0 : 0.0;
+  __syncthreads();
+  const int ne = (n + 1) & ~1, npairs = ne / 2;
+  const double tol = 2.220446049250313e-16 * sqrt((double)(m > 1 ? m : 1));
+  for (int sweep = 0; sweep < 60 && n > 1; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int rd = 0; rd < ne - 1; ++rd) {
+      for (int q = warp; q < npairs; q += nw) {
+        int p1, p2;
+        if (q == 0) {
+          p1 = ne - 1;
+          p2 = rd;
+        } else {
+          p1 = (rd + q) % (ne - 1);
+          p2 = (rd - q + ne - 1) % (ne - 1);
+        }
+        if (p1 > p2) {
+          const int t = p1;
+          p1 = p2;
+          p2 = t;
+        }
+        if (p2 >= n) continue;
+        double* x = S + (long long)p1 * m;
+        double* y = S + (long long)p2 * m;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (long long j = lane; j < m; j += 32) {
+          const double xv = x[j], yv = y[j];
+          al = fma(xv, xv, al);
+          be = fma(yv, yv, be);
+          ga = fma(xv, yv, ga);
+        }
+        al = warp_sum(al);
+        be = warp_sum(be);
+        ga = warp_sum(ga);
+        if (fabs(ga) > tol * sqrt(al * be)) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (long long j = lane; j < m; j += 32) {
+            const double xv = x[j], yv = y[j];
+            x[j] = cs * xv - sn * yv;
+            y[j] = sn * xv + cs * yv;
+          }
+          double* vx = V + (long long)p1 * n;
+          double* vy = V + (long long)p2 * n;
+          for (int i = lane; i < n; i += 32) {
+            const double xv = vx[i], yv = vy[i];
+            vx[i] = cs * xv - sn * yv;
+            vy[i] = sn * xv + cs * yv;
+          }
+          if (lane == 0) s_rot = 1;
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (rot == 0) break;
+  }
+  for (int c = warp; c < n; c += nw) {
+    const double* x = S + (long long)c * m;
+    double al = 0.0;
+    for (long long j = lane; j < m; j += 32) al = fma(x[j], x[j], al);
+    al = warp_sum(al);
+    if (lane == 0) sig[c] = sqrt(al);
+  }
+}
+
+__global__ void sylvester_scale_kernel(double* __restrict__ X, const double* __restrict__ At, long long rows, int cols,
+                                       const double* __restrict__ lam, double shift, const double* __restrict__ mu,
+                                       const double* __restrict__ rho_dev, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const double half = *rho_dev / 2.0;
+  const long long n = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx % rows, j = idx / rows;
+    X[idx] = At[idx] / (half * (lam[i] + shift) + mu[j]);
+  }
+}
+
+__global__ void sum_recip_kernel(double* __restrict__ out, LinArgs a) {
+  double s = 0.0;
+  for (int t = 0; t < a.n; ++t) s += a.coef[t] * (*a.coef_dev[t]);
+  out[0] = s;
+  out[1] = 1.0 / s;
+}
+
+__global__ void lin_finalize_kernel(LinFin fin, const double* __restrict__ red, InnerTol tol, InnerCtl* ctl) {
+  if (ctl->done != 0) return;
+  double rpk = 0.0, rdk = 0.0, rpc = 0.0, rdc = 0.0;
+  int nc = 0;
+  for (int i = 0; i < fin.nmodes; ++i) {
+    const LinFinMode& f = fin.m[i];
+    rpk += sqrt(red[f.i_pr_num]) / sqrt(red[f.i_pr_den]);
+    const double sc = sqrt(red[f.i_mu]), dn = sqrt(red[f.i_du_num]);
+    rdk += (sc > 0.0) ? dn / sc : dn;
+    if (f.constrained) {
+      ++nc;
+      rpc += sqrt(red[f.i_fz]) / sqrt(red[f.i_fn]);
+      const double sz = sqrt(red[f.i_muz]), zz = sqrt(red[f.i_zz]);
+      rdc += (sz > 0.0) ? zz / sz : zz;
+    }
+  }
+  rpk /= (double)fin.nmodes;
+  rdk /= (double)fin.nmodes;
+  if (nc > 0) {
+    rpc /= (double)nc;
+    rdc /= (double)nc;
+  }
+  ctl->res[0] = rpk;
+  ctl->res[1] = rdk;
+  ctl->res[2] = rpc;
+  ctl->res[3] = rdc;
+  ctl->iters += 1;
+  const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
+  if (!cont) ctl->done = 1;
+  if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+}
+
+unsigned flat_grid(long long n) { return (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8); }
+
+}  // namespace
+
+int dgemm_small(int transA, int transB, long long M, long long N, long long K, double alpha, const double* alpha_dev,
+                const double* A, long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
+                cudaStream_t st, const int* skip) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((unsigned)ceil_div(M, kTile), (unsigned)ceil_div(N, kTile));
+  dgemm_small_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, alpha_dev, A, lda, B, ldb, beta, C, ldc, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int lincomb(double* out, long long n, const LinTerm* terms, int nterms, cudaStream_t st, const int* skip) {
+  if (nterms < 1 || nterms > 5) throw CudaError(1, "lincomb: 1..5 terms");
+  LinArgs a{};
+  a.n = nterms;
+  for (int t = 0; t < nterms; ++t) {
+    a.x[t] = terms[t].x;
+    a.coef[t] = terms[t].coef;
+    a.coef_dev[t] = terms[t].coef_dev;
+  }
+  lincomb_kernel<<<flat_grid(n), 256, 0, st>>>(out, n, a, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int transpose_small(const double* in, long long rows, long long cols, double* out, cudaStream_t st, const int* skip) {
+  transpose_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(in, rows, cols, out, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st) {
+  jacobi_onesided_kernel<<<1, 512, 0, st>>>(S, m, n, V, sig);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int sylvester_scale(double* X, const double* At, long long rows, int cols, const double* lam, double shift,
+                    const double* mu, const double* rho_dev, cudaStream_t st, const int* skip) {
+  sylvester_scale_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(X, At, rows, cols, lam, shift, mu, rho_dev, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int sum_recip(double* out, const LinTerm* terms, int nterms, cudaStream_t st) {
+  if (nterms < 1 || nterms > 5) throw CudaError(2, "more than 5 modes in a linearly coupled group");
+  LinArgs a{};
+  a.n = nterms;
+  for (int t = 0; t < nterms; ++t) {
+    a.coef[t] = terms[t].coef;
+    a.coef_dev[t] = terms[t].coef_dev;
+  }
+  sum_recip_kernel<<<1, 1, 0, st>>>(out, a);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int lin_finalize(const LinFin& fin, const double* red, const InnerTol& tol, InnerCtl* ctl, cudaStream_t st) {
+  lin_finalize_kernel<<<1, 1, 0, st>>>(fin, red, tol, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+}  // namespace aoadmm

@@ -368,3 +368,86 @@ def config_single_par2(I=18, Jk=(12, 9, 15, 11), R=3, seed=0, noise=0.05, constr
     init_options = {'lambdas_init': [[1.0] * R], 'nvecs': 0, 'distr': [d_rand, d_rand, d_rand01], 'normalize': 1}
     G = init_coupled_AOADMM_CMTF(Z, init_options, rng)
     return Z, G, {'Atrue': [A, None, C]}
+
+
+def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='matrix'):
+    """A 3-way CP object linearly coupled (coupling types 1..5, cmtf_fun_AOADMM.m:278-389) with a matrix or a second
+    CP tensor, sizes in the style of example_script3 (type 4), example_script13 (type 5), example_script14 (type 1)."""
+    rng = np.random.RandomState(seed)
+    nn = ('non-negativity',)
+    sub = np.zeros((20, 40))
+    sub[np.arange(20), 2 * np.arange(20)] = 1.0                       # "take every second entry" (script 13/14)
+    part = np.vstack([np.eye(3), np.zeros((1, 3))])                   # partially shared components (script 3/13)
+    if ctype == 1:      # H F = Delta
+        I1, I4, R1, R2 = 20, 40, 3, 3
+        H = {1: np.eye(20), 4: sub}
+        H2 = {}
+    elif ctype == 2:    # F H = Delta
+        I1, I4, R1, R2 = 30, 30, 4, 3
+        H = {1: part.copy(), 4: np.eye(3)}
+        H2 = {}
+    elif ctype == 3:    # F = H Delta
+        I1, I4, R1, R2 = 30, 24, 3, 3
+        H = {1: rng.rand(30, 10), 4: rng.rand(24, 10)}
+        H2 = {}
+    elif ctype == 4:    # F = Delta H
+        I1, I4, R1, R2 = 30, 30, 4, 3
+        H = {1: np.eye(4), 4: part.copy()}
+        H2 = {}
+    elif ctype == 5:    # H F = Delta H2
+        I1, I4, R1, R2 = 20, 40, 4, 3
+        H = {1: np.eye(20), 4: sub}
+        H2 = {1: np.eye(4), 4: part.copy()}
+    else:
+        raise ValueError(ctype)
+    if second == 'matrix':
+        sz = [I1, 14, 12, I4, 18]
+        modes = [[1, 2, 3], [4, 5]]
+    else:
+        sz = [I1, 14, 12, I4, 11, 9]
+        modes = [[1, 2, 3], [4, 5, 6]]
+    nm = len(sz)
+    trafo = [None] * nm
+    trafo2 = [None] * nm
+    for m, h in H.items():
+        trafo[m - 1] = h
+    for m, h in H2.items():
+        trafo2[m - 1] = h
+    lin = [0] * nm
+    lin[0] = lin[3] = 1
+    coupling = {'lin_coupled_modes': lin, 'coupling_type': [ctype], 'coupl_trafo_matrices': trafo}
+    if ctype == 5:
+        coupling['coupl_trafo_matrices2'] = trafo2
+    lambdas = [[1.0] * R1, [1.0] * R2]
+    distr = [d_rand] * nm
+    model = ['CP', 'CP']
+    Delta_shapes = None
+    if ctype == 5:
+        # ground truth: Delta (q1 x q2); F1 = Delta H2_1 (H1_1 = I); rows of F4 picked by H1_4 equal Delta H2_4
+        Delta = rng.rand(20, 4)
+        A = [None] * nm
+        for p in range(2):
+            for n in modes[p]:
+                A[n - 1] = rng.rand(sz[n - 1], len(lambdas[p]))
+        A[0] = Delta @ H2[1]
+        A[3][::2, :] = Delta @ H2[4]
+        X = []
+        for p in range(2):
+            Xp = full_ktensor([A[m - 1] for m in modes[p]], lambdas[p])
+            N = rng.randn(*Xp.shape)
+            X.append(np.asfortranarray(Xp + noise * np.linalg.norm(Xp) / np.linalg.norm(N) * N))
+        Delta_shapes = [Delta]
+    else:
+        X, _, _ = create_coupled_data(model, sz, modes, lambdas, [noise] * 2, coupling, 0, distr, rng)
+    obj, _ = normalize_objects(X, model)
+    cm = [0] * nm
+    cons = [None] * nm
+    if constrained:
+        for m in (1, 4, 5):
+            cm[m - 1] = 1
+            cons[m - 1] = nn
+    Z = {'loss_function': ['Frobenius'] * 2, 'model': model, 'modes': modes, 'size': sz, 'coupling': coupling,
+         'constrained_modes': cm, 'constraints': cons, 'weights': [0.5, 0.5], 'object': obj}
+    init_options = {'lambdas_init': lambdas, 'nvecs': 0, 'distr': distr, 'normalize': 1}
+    G = init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=Delta_shapes)
+    return Z, G, {}

@@ -307,6 +307,25 @@ def test_parafac2_mode_c_coupled_with_matrix(ab):
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
+@pytest.mark.parametrize('ctype', [1, 2, 3, 4, 5])
+@pytest.mark.parametrize('constrained', [True, False])
+def test_linear_couplings_all_types(ab, ctype, constrained):
+    """coupling types 1..5 (HC=D, CH=D, C=HD, C=DH, H1C=DH2; cmtf_fun_AOADMM.m:278-389, :698-1075), CP + matrix."""
+    Z, G, _ = pg.config_linear_coupling(ctype, seed=ctype, constrained=constrained)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=30))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+@pytest.mark.parametrize('ctype', [1, 4, 5])
+def test_linear_couplings_two_tensors_zero_tolerances(ab, ctype):
+    Z, G, _ = pg.config_linear_coupling(ctype, seed=10 + ctype, second='tensor')
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=15, **ZERO_TOL))
+    assert np.all(oo['innerIters'][[0, 3], :] == 5)
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)

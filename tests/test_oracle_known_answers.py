@@ -187,3 +187,21 @@ def test_oracle_reproduces_golden(name):
     for i, F in enumerate(Gout['fac']):
         assert rel(F, gold['out_fac_%d' % i]) < 1e-10
     assert np.array_equal(out['innerIters'], gold['innerIters'])
+
+
+@pytest.mark.parametrize('ctype', [1, 2, 3, 4, 5])
+def test_linear_coupling_oracle_satisfies_the_coupling_constraint(ctype):
+    """Noise-free data generated WITH the coupling: the oracle's ADMM_coupled_case1..5 drive both the fit and the
+    coupling residual ||G(F) - D(Delta)|| / ||.|| to (near) zero - a known answer that needs no MATLAB."""
+    Z, G, _ = pg.config_linear_coupling(ctype, seed=3, noise=0.0, constrained=False)
+    Go, oo = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=400, AbsFuncTol=1e-9))
+    # type 5 with partially shared components stalls in a local minimum of the fit (f ~ 1.4e-3, coupling 3e-8)
+    assert oo['f_tensors'] < (5e-3 if ctype == 5 else 1e-5) and oo['f_couplings'] < 1e-3
+    H = Z['coupling']['coupl_trafo_matrices']
+    H2 = Z['coupling'].get('coupl_trafo_matrices2', [None] * 6)
+    D = Go['coupling_fac'][0]
+    for m in (1, 4):
+        F = Go['fac'][m - 1]
+        lhs = {1: lambda: H[m - 1] @ F, 2: lambda: F @ H[m - 1], 3: lambda: F, 4: lambda: F, 5: lambda: H[m - 1] @ F}[ctype]()
+        rhs = {1: lambda: D, 2: lambda: D, 3: lambda: H[m - 1] @ D, 4: lambda: D @ H[m - 1], 5: lambda: D @ H2[m - 1]}[ctype]()
+        assert np.linalg.norm(lhs - rhs) / np.linalg.norm(lhs) < 5e-3
