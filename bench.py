@@ -226,36 +226,44 @@ def main():
 
     Z, G, facs = make_problem(I, J, K, M, R, seed=0, with_tensor=False)
     lo, hi = ab.shard_range(K, rank, world)
-    solver = ab.Solver(Z, [1.0, float(np.sum(Z['object'][1] ** 2))], rank=rank, world_size=world, device=local_rank,
-                       unique_id=uid, shard=[(lo, hi), None])
+    Kloc = hi - lo
+    zn = [1.0, float(np.sum(Z['object'][1] ** 2))]
+    solver = ab.Solver(Z, zn, rank=rank, world_size=world, device=local_rank, unique_id=uid, shard=[(lo, hi), None])
     solver.generate_cp_data(1, facs, 0.2, 20261018)
     solver.set_state(G)
 
+    def timed_run(opts_fn, steps):
+        """W warm-up steps, then exactly `steps` outer iterations timed with CUDA events on the engine's stream."""
+        solver.set_state(G)
+        solver.run(opts_fn(max(args.warmup, 3)))
+        barrier()
+        l0 = solver.launch_count()
+        ph0 = solver.phase_ms().copy()
+        barrier()
+        t0 = time.perf_counter()
+        out = solver.run(opts_fn(steps))
+        ms = solver.last_run_ms()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        tmax = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        assert out['OuterIterations'] == steps
+        return float(tmax.item()), wall, solver.launch_count() - l0, solver.phase_ms() - ph0, out
+
     # ---- device-resident throughput (`value`) ----
-    solver.run(zero_tol_options(max(args.warmup, 3)))
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = solver.launch_count()
-    ph0 = solver.phase_ms().copy()
-    barrier()
-    t0 = time.perf_counter()
-    out = solver.run(zero_tol_options(args.steps))
-    dev_ms = solver.last_run_ms()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms, wall_ms, launches, ph, out = timed_run(zero_tol_options, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = solver.launch_count() - l0
-    ph = solver.phase_ms() - ph0
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms = float(tmax.item())
-    assert out['OuterIterations'] == args.steps
+    # the same step with three independent tensor passes (the reference's own flop/byte count), for transparency
+    three_ms = None
+    if DIMTREE:
+        n3 = max(3, args.steps // 2)
+        three_ms = timed_run(lambda it: dict(zero_tol_options(it), dimtree=0), n3)[0] / n3
 
     # ---- per-mode MTTKRP kernel times (CUDA events on the engine's stream) for the roofline ----
-    Kloc = hi - lo
     flops_mode = 2.0 * I * J * Kloc * R
     bytes_mode = 8.0 * I * J * Kloc
     mode_ms = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
@@ -267,8 +275,14 @@ def main():
             hbm_peak = float(json.load(f)['hbm_gbs'])
     except Exception:
         pass
+    # dram bytes per launch from the ncu --set full captures of profiles/r01_ncu_mttkrp_summary.md: 1.004x (R=32, the
+    # C2 launch itself) / 1.005x (R=64, captured on a K=64 slab of the same 4096x4096 tile shape) the algorithmic bytes
+    traffic_ratio = {'c2': 1.004, 'c3k1024': 1.005}.get(args.workload)
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s',
-                'frac': achieved / FP64_DMMA_PEAK_TFLOPS, 'traffic': None,
+                'frac': achieved / FP64_DMMA_PEAK_TFLOPS,
+                'traffic': bytes_mode * traffic_ratio if traffic_ratio else None,
+                'traffic_note': 'dram__bytes_read+write per launch = %.3f x algorithmic bytes (ncu --set full, '
+                                'profiles/r01_mttkrp_*_full_raw.csv)' % traffic_ratio if traffic_ratio else None,
                 'kernel': 'mttkrp_lead_kernel / mttkrp_inner_kernel (FP64 DMMA.8x8x4 + TMA), 3 modes',
                 'per_mode_ms': mode_ms, 'per_mode_tflops': [flops_mode / (m * 1e-3) / 1e12 for m in mode_ms],
                 'per_mode_hbm_gbs': [bytes_mode / (m * 1e-3) / 1e9 for m in mode_ms], 'hbm_peak_gbs_measured': hbm_peak,
@@ -279,36 +293,58 @@ def main():
                 'algorithmic_flops_per_launch': flops_mode, 'algorithmic_bytes_per_launch': bytes_mode,
                 'mttkrp_share_of_step': float(ph[0] / dev_ms) if dev_ms > 0 else None}
 
-    solver.close()   # the resident tensor must go before the end-to-end leg allocates its own
-
-    # ---- end-to-end through the C ABI with host buffers ----
+    # ---- end-to-end through the C ABI with HOST buffers ----
     e2e = None
     if not args.no_e2e:
-        # The coupled matrix, the full state (5 factors, 5 Z, 5 mu_Z, Delta, 2 mu_Delta) go host->device, the state comes
-        # back device->host, inside the timed region.  The tensor is device-generated at this size (137 GB cannot exist
-        # on the host), so it is re-created on device inside the timed region instead of copied.
+        # The tensor slab of this rank is brought to the host once (outside the timed region) so that the timed call
+        # starts, like the reference's cmtf_fun_AOADMM call, from data in host memory: aoadmm_create copies the tensor
+        # and the coupled matrix host->device, set_state the 16 state matrices, run does `steps` outer iterations,
+        # get_state brings the state back.
+        n_loc = I * J * Kloc
+        host, how = None, None
+        if _host_memory_ok(8.0 * I * J * K):
+            try:
+                tpin = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+                host, how = tpin.numpy().reshape((I, J, Kloc), order='F'), 'pinned'
+            except Exception:
+                try:
+                    host, how = np.empty((I, J, Kloc), order='F'), 'pageable'
+                except MemoryError:
+                    host = None
+        if host is not None:
+            solver.get_object_data(1, host)
+        solver.close()   # the resident tensor must go before the end-to-end leg allocates its own
+        Zh = dict(Z, object=[host, Z['object'][1]])
+        uid2 = None if world == 1 else _fresh_uid(ab, dist, torch, rank)
         barrier()
         t0 = time.perf_counter()
-        s2 = ab.Solver(Z, [1.0, float(np.sum(Z['object'][1] ** 2))], rank=rank, world_size=world, device=local_rank,
-                       unique_id=None if world == 1 else _fresh_uid(ab, dist, torch, rank), shard=[(lo, hi), None])
-        s2.generate_cp_data(1, facs, 0.2, 20261018)
+        s2 = ab.Solver(Zh, zn, rank=rank, world_size=world, device=local_rank, unique_id=uid2, shard=[(lo, hi), None])
+        if host is None:
+            s2.generate_cp_data(1, facs, 0.2, 20261018)
         s2.set_state(G)
         o2 = s2.run(zero_tol_options(args.steps))
         G2 = s2.get_state()
         barrier()
         e2e_s = time.perf_counter() - t0
         s2.close()
+        assert o2['OuterIterations'] == args.steps and np.isfinite(o2['f_tensors'])
         tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
         state_bytes = sum(a.nbytes for k in ('fac', 'constraint_fac', 'constraint_dual_fac', 'coupling_dual_fac', 'coupling_fac')
                           for a in G[k] if a is not None)
-        h2d = state_bytes + Z['object'][1].nbytes + sum(f.nbytes for f in facs)
+        h2d = state_bytes + Z['object'][1].nbytes + (8.0 * n_loc if host is not None else sum(f.nbytes for f in facs))
         e2e = {'value': args.steps / e2e_s, 'unit': 'outer_iters/s', 'h2d_bytes_per_step': h2d / args.steps,
-               'd2h_bytes_per_step': state_bytes / args.steps,
-               'note': 'one cmtf_fun_AOADMM call of %d outer iterations through the C ABI (create + generate tensor on '
-                       'device + set_state + run + get_state + destroy), host wall clock, max over ranks' % args.steps}
+               'd2h_bytes_per_step': state_bytes / args.steps, 'seconds': e2e_s, 'host_tensor': how or 'none',
+               'note': ('one cmtf_fun_AOADMM call of %d outer iterations through the C ABI, host wall clock, max over ranks: '
+                        'create (tensor slab %.1f GB + matrix host->device from %s host memory) + set_state + run + get_state '
+                        '+ destroy; the solver is iterative, so the data cross PCIe once per call, not once per step'
+                        % (args.steps, 8.0 * n_loc / 1e9, how)) if host is not None else
+                       ('host memory cannot hold the %.1f GB slab on this box: the tensor is re-generated on device inside '
+                        'the timed region instead of copied' % (8.0 * n_loc / 1e9))}
+    else:
+        solver.close()
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -320,6 +356,9 @@ def main():
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
                 'cpu_baseline': cb, 'wall_ms_per_step': wall_ms / args.steps,
+                'three_pass': ({'value': 1e3 / three_ms, 'ms_per_step': three_ms,
+                                'note': 'same step with options.dimtree=0: three independent tensor passes, the '
+                                        "reference's flop and byte count"} if three_ms else None),
                 'final_f_tensors': out['f_tensors'],
                 'timing': 'CUDA events on the engine stream around the whole run (includes the one-off iteration-0 '
                           'objective of cmtf_fun_AOADMM.m:32), max over ranks'}
@@ -327,6 +366,27 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _host_memory_ok(need_bytes):
+    """True when the box (and the cgroup, if limited) can hold `need_bytes` more host memory with 15 % headroom."""
+    try:
+        avail = None
+        for line in open('/proc/meminfo'):
+            if line.startswith('MemAvailable:'):
+                avail = int(line.split()[1]) * 1024
+        for path in ('/sys/fs/cgroup/memory.max', '/sys/fs/cgroup/memory/memory.limit_in_bytes'):
+            if os.path.exists(path):
+                txt = open(path).read().strip()
+                if txt.isdigit():
+                    used = 0
+                    for up in ('/sys/fs/cgroup/memory.current', '/sys/fs/cgroup/memory/memory.usage_in_bytes'):
+                        if os.path.exists(up):
+                            used = int(open(up).read().strip())
+                    avail = min(avail, int(txt) - used) if avail is not None else int(txt) - used
+        return avail is not None and need_bytes * 1.15 < avail
+    except Exception:
+        return False
 
 
 def _fresh_uid(ab, dist, torch, rank):

@@ -211,6 +211,10 @@ int aoadmm_gram(const double *F, int64_t rows, int32_t R, double *G, int32_t dev
  * (SURVEY.md 8d C3).  Writes the new Znorm_const (=1) into the handle. */
 int aoadmm_generate_cp_data(aoadmm_handle *h, int32_t object, const double *const *factors,
                             double noise, uint64_t seed);
+/* Copy this rank's slab of CP object `object` (1-based) back to a caller buffer with the layout aoadmm_create
+ * takes (dims of the leading modes x shard_extent, column-major, no padding).  bench.py uses it to obtain the
+ * device-generated tensor as a HOST buffer for the end-to-end leg. */
+int aoadmm_get_object_data(aoadmm_handle *h, int32_t object, double *out, int64_t n_elements);
 /* one timed MTTKRP of object `object` in mode position `pos` (1-based position inside the object)
  * using the factors currently resident in the handle; returns device milliseconds (CUDA events). */
 int aoadmm_time_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t reps, float *ms_out);

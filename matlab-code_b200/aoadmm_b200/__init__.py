@@ -394,6 +394,12 @@ class Solver:
         arr = (_capi.c_double_p * len(fs))(*[_dp(f) for f in fs])
         _capi.check(lib.aoadmm_generate_cp_data(self._h, obj, arr, float(noise), int(seed)), self._h)
 
+    def get_object_data(self, obj, out):
+        """This rank's slab of CP object `obj` (1-based) into the F-contiguous float64 array `out`."""
+        assert out.dtype == np.float64 and out.flags['F_CONTIGUOUS']
+        _capi.check(lib.aoadmm_get_object_data(self._h, obj, _dp(out), out.size), self._h)
+        return out
+
     def time_mttkrp(self, obj, pos, reps=3):
         ms = C.c_float(0)
         _capi.check(lib.aoadmm_time_mttkrp(self._h, obj, pos, reps, C.byref(ms)), self._h)

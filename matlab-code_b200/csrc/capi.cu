@@ -129,6 +129,11 @@ int aoadmm_generate_cp_data(aoadmm_handle* h, int32_t object, const double* cons
   return guard(h, [&] { h->eng->generate_cp_data(object, factors, noise, seed); });
 }
 
+int aoadmm_get_object_data(aoadmm_handle* h, int32_t object, double* out, int64_t n_elements) {
+  if (!h || !out) return AOADMM_ERR_INVALID_ARG;
+  return guard(h, [&] { h->eng->object_to_host(object, out, n_elements); });
+}
+
 int aoadmm_time_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t reps, float* ms_out) {
   if (!h || !ms_out) return AOADMM_ERR_INVALID_ARG;
   return guard(h, [&] { *ms_out = h->eng->time_mttkrp(object, pos, reps); });
@@ -203,6 +208,18 @@ int aoadmm_prox(const aoadmm_constraint* spec, const double* X, int64_t rows, in
     const size_t sb = aoadmm::prox_scratch_bytes(spec->kind, rows, (int)cols);
     DevBuf scratch(sb / sizeof(double) + 1);
     AO_CUDA(cudaMemcpy(dx.p, X, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (spec->kind == AOADMM_CON_QUADRATIC) {
+      if (spec->matrix_n != rows) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "quadratic regularization: L must be rows x rows");
+      aoadmm::QuadProx q;
+      aoadmm::quad_prox_setup(q, spec->matrix, rows, spec->p0, (int)cols, 0);
+      aoadmm::quad_prox_apply(q, dx.p, rows, dout.p, rows, (int)cols, nullptr, rho, 0, nullptr);
+      AO_CUDA(cudaDeviceSynchronize());
+      aoadmm::quad_prox_free(q);
+      AO_CUDA(cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+      return;
+    }
+    if (spec->kind == AOADMM_CON_TPARAFAC2)
+      throw aoadmm::CudaError(AOADMM_ERR_UNSUPPORTED, "tPARAFAC2 acts on all PARAFAC2 slices at once: use the solver");
     aoadmm::prox_apply(spec->kind, spec->p0, spec->p1, dx.p, rows, dout.p, rows, rows, (int)cols, nullptr, rho,
                        sb ? scratch.p : nullptr, 0, nullptr);
     AO_CUDA(cudaDeviceSynchronize());

@@ -199,7 +199,10 @@ bool constraint_supported(int kind) {
     case AOADMM_CON_L2_REG:
     case AOADMM_CON_RIDGE:
     case AOADMM_CON_GL_SMOOTH:
-    case AOADMM_CON_TV: return true;
+    case AOADMM_CON_TV:
+    case AOADMM_CON_ORTHONORMAL:
+    case AOADMM_CON_QUADRATIC:
+    case AOADMM_CON_TPARAFAC2: return true;
     default: return false;
   }
 }
@@ -230,6 +233,7 @@ static int reg_red_kind(int con_kind) {
     case AOADMM_CON_RIDGE: return RED_NORM2;
     case AOADMM_CON_GL_SMOOTH: return RED_GLQUAD;
     case AOADMM_CON_TV: return RED_TVSUM;
+    case AOADMM_CON_TPARAFAC2: return RED_TSMOOTH;   // t_smoothness_penalty.m:5-9 (only through par2_seg_norms)
     default: return -1;
   }
 }
@@ -341,8 +345,23 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
                            cudaMemcpyHostToDevice));
     AO_CUDA(cudaDeviceSynchronize());  // pageable H2D copies return before the DMA has finished
   }
-  for (auto& m : modes_)
+  for (auto& m : modes_) {
     if (m.p < 0) throw CudaError(1, "mode " + std::to_string(m.id) + " belongs to no object");
+    if (!m.constrained) continue;
+    if (m.con.kind == AOADMM_CON_TPARAFAC2) {  // cmtf_AOADMM.m:33-41
+      if (m.par2_role != 2)
+        throw CudaError(1, "The tPARAFAC2 constraint can only be imposed on the second mode of a PARAFAC2 model");
+      const Par2State& s = par2_[m.par2];
+      for (int k = 0; k < s.K; ++k)
+        if (s.joff[k + 1] - s.joff[k] != s.Jmax) throw CudaError(1, "tPARAFAC2 needs slices of equal size");
+    }
+    if (m.con.kind == AOADMM_CON_QUADRATIC) {
+      if (m.par2_role == 2) throw CudaError(2, "quadratic regularization on the second PARAFAC2 mode is not supported on device");
+      if (m.con.matrix_n != m.rows) throw CudaError(1, "quadratic regularization: L must be rows x rows");
+      quad_prox_setup(m.quad, m.con.matrix, m.rows, m.con.p0, m.R, st_);
+      m.con.matrix = nullptr;  // the host buffer belongs to the caller
+    }
+  }
 
   // couplings: exact coupling needs identical shapes
   delta_.resize(n_couplings_);
@@ -477,6 +496,7 @@ Engine::~Engine() {
     for (DevMat* d : {&m.fac, &m.Z, &m.muZ, &m.muD, &m.A, &m.Alast, &m.C, &m.B, &m.L, &m.Binv, &m.Btmp, &m.GtG, &m.Znew, &m.V}) dev_free(*d);
     if (m.invdiag) cudaFree(m.invdiag);
     if (m.rho) cudaFree(m.rho);
+    quad_prox_free(m.quad);
   }
   for (auto& o : objects_) {
     if (o.data) cudaFree(o.data);
@@ -491,7 +511,7 @@ Engine::~Engine() {
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
     for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
-                    (void*)s.rho2, (void*)s.rho3, (void*)s.contrib, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
+                    (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
                     (void*)s.res_partials})
       if (q) cudaFree(q);
     if (s.segn_host) cudaFreeHost(s.segn_host);
@@ -780,6 +800,7 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   AO_CUDA(cudaMalloc(&s.contrib, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.rho2, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.rho3, sizeof(double) * s.K));
+  AO_CUDA(cudaMalloc(&s.tdiag, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.norms, sizeof(double) * s.K * 8));
   AO_CUDA(cudaMemset(s.norms, 0, sizeof(double) * s.K * 8));
   AO_CUDA(cudaMalloc(&s.Csum, sizeof(double) * s.R * s.R));
@@ -912,9 +933,13 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
     launches_ += par2_B_step2a(s.lay, b, m.ctl, st_);
     if (deferred) {
       launches_ += par2_B_form_prox_input(s.lay, b, m.V.p, m.ctl, st_);
-      for (int k = 0; k < s.K; ++k)  // :567-568: prox of every slice with its own rho_k
-        launches_ += prox_apply(m.con.kind, m.con.p0, m.con.p1, m.V.p + s.joff[k], s.Jtot, m.Znew.p + s.joff[k], s.Jtot,
-                                s.joff[k + 1] - s.joff[k], s.R, s.rho2 + k, 0.0, prox_scratch_, st_, &m.ctl->done);
+      if (m.con.kind == AOADMM_CON_TPARAFAC2) {  // :553-554: all slices at once with the vector rho
+        launches_ += par2_tsmooth_prox(s.lay, m.V.p, s.rho2, m.con.p0, s.tdiag, m.Znew.p, m.ctl, st_);
+      } else {
+        for (int k = 0; k < s.K; ++k)  // :567-568: prox of every slice with its own rho_k
+          launches_ += apply_prox(m, m.V.p + s.joff[k], s.Jtot, m.Znew.p + s.joff[k], s.Jtot, s.joff[k + 1] - s.joff[k], s.R,
+                                  s.rho2 + k, &m.ctl->done);
+      }
     }
     launches_ += par2_B_step2b(s.lay, b, tol, m.ctl, admm_counter_, st_);
   }
@@ -949,6 +974,12 @@ void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct) {
   sa.ctl = m.ctl;
   launches_ += par2_sys_prep(s.lay, sa, st_);
   launches_ += par2_rho_max(s.rho3, s.K, m.rho, st_);
+}
+
+int Engine::apply_prox(ModeState& m, const double* X, long long ldx, double* out, long long ldo, long long rows, int cols,
+                       const double* rho_dev, const int* skip) {
+  if (m.con.kind == AOADMM_CON_QUADRATIC) return quad_prox_apply(m.quad, X, ldx, out, ldo, cols, rho_dev, 0.0, st_, skip);
+  return prox_apply(m.con.kind, m.con.p0, m.con.p1, X, ldx, out, ldo, rows, cols, rho_dev, 0.0, prox_scratch_, st_, skip);
 }
 
 void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt) {
@@ -987,8 +1018,7 @@ void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadm
     for (size_t d = 0; d < deferred.size(); ++d) {
       ModeState& m = *group[deferred[d]];
       launches_ += admm_form_prox_input(g, deferred[d], m.V.p, ctl, st_);
-      launches_ += prox_apply(m.con.kind, m.con.p0, m.con.p1, m.V.p, m.rows, m.Znew.p, m.rows, m.rows, m.R, m.rho, 0.0,
-                              prox_scratch_, st_, &ctl->done);
+      launches_ += apply_prox(m, m.V.p, m.rows, m.Znew.p, m.rows, m.rows, m.R, m.rho, &ctl->done);
       launches_ += admm_constraint_update(g, deferred[d], m.Znew.p, tol, ctl, admm_sums_, admm_partials_, admm_counter_,
                                           (d + 1 == deferred.size()) ? 1 : 0, st_);
     }
@@ -1040,6 +1070,8 @@ void Engine::build_objective_jobs() {
     }
     if (m.constrained && reg_red_kind(m.con.kind) >= 0)
       t.idx_reg = add(reg_red_kind(m.con.kind), m.fac.p, nullptr, m.rows, m.R);
+    if (m.constrained && m.con.kind == AOADMM_CON_QUADRATIC)   // constraints_to_prox.m:67: eta*trace(x'*L*x), L*x in m.V
+      t.idx_reg = add(RED_DOT, m.fac.p, m.V.p, m.rows, m.R);
   }
   const size_t nj = jobs_host_.size();
   AO_CUDA(cudaMalloc(&jobs_dev_, sizeof(RedJob) * (nj + 8)));
@@ -1095,6 +1127,9 @@ void Engine::eval_objective(bool first, double f[4]) {
       f_obj[p] = o.weight * (o.znorm - 2.0 * r2[0] + r2[1]);
     }
   }
+  for (auto& m : modes_)
+    if (m.constrained && m.con.kind == AOADMM_CON_QUADRATIC)
+      launches_ += dgemm_small(0, 0, m.rows, m.R, m.rows, 1.0, nullptr, m.quad.L, m.rows, m.fac.p, m.rows, 0.0, m.V.p, m.rows, st_, nullptr);
   for (auto& m : modes_)
     if (m.lin >= 0) {
       LinMode& lm = lin_modes_[m.lin];
@@ -1548,6 +1583,19 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   o.T_version = 0;  // cached partial contractions refer to the old data
   for (auto p : tmp) cudaFree(p);
   cudaFree(sums);
+}
+
+void Engine::object_to_host(int object, double* out, int64_t n_elements) {
+  AO_CUDA(cudaSetDevice(device_));
+  if (object < 1 || object > n_objects_) throw CudaError(1, "get_object_data: object out of range");
+  ObjectState& o = objects_[object - 1];
+  if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "get_object_data: not a CP object");
+  size_t slab = 1;
+  for (int d = 1; d < o.order; ++d) slab *= (size_t)o.dims[d];
+  if ((int64_t)((size_t)o.dims[0] * slab) != n_elements) throw CudaError(1, "get_object_data: size mismatch");
+  AO_CUDA(cudaStreamSynchronize(st_));
+  AO_CUDA(cudaMemcpy2D(out, (size_t)o.dims[0] * 8, o.data, (size_t)o.ld0 * 8, (size_t)o.dims[0] * 8, slab,
+                       cudaMemcpyDeviceToHost));
 }
 
 void Engine::mttkrp_to_host(int object, int pos, double* out) {

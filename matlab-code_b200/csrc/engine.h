@@ -43,6 +43,7 @@ struct ModeState {
   InnerCtl* ctl = nullptr;    // device; for coupled modes all modes of the group share the group's block
   int ctl_index = -1;
   uint64_t version = 1;       // bumped whenever fac changes (validity stamp for cached partial contractions)
+  QuadProx quad;              // 'quadratic regularization': eigen-basis of L
   int lin = -1;               // index into Engine::lin_modes_ when the mode is linearly coupled (type 1..5)
   // PARAFAC2 objects: role 1 = A (first mode), 2 = stacked B_k, 3 = C; par2 = index into Engine::par2_
   int par2_role = 0, par2 = -1;
@@ -96,7 +97,7 @@ struct Par2State {
   uint64_t T_version = 0;                // version of A that T was computed from
   DevMat P, muDB, DeltaB, PDold, gM, gS;
   double *G2 = nullptr, *Binv2 = nullptr, *Binv3 = nullptr, *rho2 = nullptr, *rho3 = nullptr, *contrib = nullptr,
-         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr;
+         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr, *tdiag = nullptr;
   double* segn_host = nullptr;           // pinned: K x 4 per-slice objective terms + 1 residual
   bool explicit_residual = false;        // objective needs ||X_k - A D_k B_k'||^2 (mode A is not updated last)
 };
@@ -137,6 +138,7 @@ class Engine {
   void run(const aoadmm_options* opt, aoadmm_out* out);
   void generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed);
   float time_mttkrp(int object, int pos, int reps);
+  void object_to_host(int object, double* out, int64_t n_elements);
   void mttkrp_to_host(int object, int pos, double* out);  // unweighted MTTKRP of the resident factors
   int64_t launches() const { return launches_; }
   void phase_ms(double ms[3]);
@@ -153,6 +155,9 @@ class Engine {
   void pack_operand(View3& v, int which);
   void precompute_mode(ModeState& m, int n_rho_terms, bool do_chol);
   void fill_prep(ModeState& m, PrepArgs& a, int n_rho_terms, bool do_chol);
+  // Z.prox_operators{m}(X, rho) for the constraint of mode m on a rows x cols block (cmtf_fun_AOADMM.m:1424-1426)
+  int apply_prox(ModeState& m, const double* X, long long ldx, double* out, long long ldo, long long rows, int cols,
+                 const double* rho_dev, const int* skip);
   void apply_bsum(ModeState& m);
   void run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt);
   void eval_objective(bool first, double f[4]);

@@ -378,8 +378,7 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
         AO_CUDA(cudaMemcpyAsync(lm.Zold.p, m.Z.p, m.Z.bytes(), cudaMemcpyDeviceToDevice, st_));
         LinTerm t[2] = {{m.fac.p, 1.0, nullptr}, {m.muZ.p, 1.0, nullptr}};
         launches_ += lincomb(lm.tmpF.p, nF, t, 2, st_, skip);
-        launches_ += prox_apply(m.con.kind, m.con.p0, m.con.p1, lm.tmpF.p, m.rows, m.Z.p, m.rows, m.rows, m.R, m.rho, 0.0,
-                                prox_scratch_, st_, skip);
+        launches_ += apply_prox(m, lm.tmpF.p, m.rows, m.Z.p, m.rows, m.rows, m.R, m.rho, skip);
         LinTerm u[3] = {{m.muZ.p, 1.0, nullptr}, {m.fac.p, 1.0, nullptr}, {m.Z.p, -1.0, nullptr}};
         launches_ += lincomb(m.muZ.p, nF, u, 3, st_, skip);
       }

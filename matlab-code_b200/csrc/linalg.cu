@@ -2,6 +2,8 @@
 #include "linalg.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <vector>
 
 namespace aoadmm {
 
@@ -106,7 +108,9 @@ __global__ void transpose_kernel(const double* __restrict__ in, long long rows, 
 }
 
 __global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* __restrict__ S, long long m, int n,
-                                                               double* __restrict__ V, double* __restrict__ sig) {
+                                                               double* __restrict__ V, double* __restrict__ sig,
+                                                               const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
   __shared__ int s_rot;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   for (long long e = tid; e < (long long)n * n; e += nt) V[e] = (e % (n + 1) == 0) ? 1.0 : 0.0;
@@ -191,6 +195,29 @@ __global__ void sylvester_scale_kernel(double* __restrict__ X, const double* __r
   }
 }
 
+__global__ void scale_cols_inv_kernel(double* __restrict__ S, long long rows, int cols, const double* __restrict__ sig,
+                                      const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const double s = sig[idx / rows];
+    S[idx] = (s > 0.0) ? S[idx] / s : 0.0;
+  }
+}
+
+__global__ void quad_scale_rows_kernel(double* __restrict__ Y, long long rows, int cols, const double* __restrict__ lam,
+                                       double eta, const double* __restrict__ rho_dev, double rho_host,
+                                       const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const double rho = (rho_dev != nullptr) ? *rho_dev : rho_host;
+  const double g = 2.0 * eta / rho;
+  const long long n = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x)
+    Y[idx] = Y[idx] / (g * lam[idx % rows] + 1.0);
+}
+
 __global__ void sum_recip_kernel(double* __restrict__ out, LinArgs a) {
   double s = 0.0;
   for (int t = 0; t < a.n; ++t) s += a.coef[t] * (*a.coef_dev[t]);
@@ -264,8 +291,21 @@ int transpose_small(const double* in, long long rows, long long cols, double* ou
   return 1;
 }
 
-int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st) {
-  jacobi_onesided_kernel<<<1, 512, 0, st>>>(S, m, n, V, sig);
+int scale_cols_inv(double* S, long long rows, int cols, const double* sig, cudaStream_t st, const int* skip) {
+  scale_cols_inv_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(S, rows, cols, sig, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int quad_scale_rows(double* Y, long long rows, int cols, const double* lam, double eta, const double* rho_dev,
+                    double rho_host, cudaStream_t st, const int* skip) {
+  quad_scale_rows_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(Y, rows, cols, lam, eta, rho_dev, rho_host, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st, const int* skip) {
+  jacobi_onesided_kernel<<<1, 512, 0, st>>>(S, m, n, V, sig, skip);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -275,6 +315,57 @@ int sylvester_scale(double* X, const double* At, long long rows, int cols, const
   sylvester_scale_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(X, At, rows, cols, lam, shift, mu, rho_dev, skip);
   AO_CHECK_LAUNCH();
   return 1;
+}
+
+void quad_prox_setup(QuadProx& q, const double* L_host, long long n, double eta, int maxcols, cudaStream_t st) {
+  if (L_host == nullptr || n <= 0) throw CudaError(1, "quadratic regularization: matrix L is required");
+  if (n > 4096) throw CudaError(2, "quadratic regularization: at most 4096 rows on device");
+  double amax = 0.0, asym = 0.0;
+  for (long long j = 0; j < n; ++j)
+    for (long long i = 0; i < n; ++i) {
+      amax = std::max(amax, std::fabs(L_host[i + j * n]));
+      asym = std::max(asym, std::fabs(L_host[i + j * n] - L_host[j + i * n]));
+    }
+  if (asym > 1e-12 * std::max(amax, 1e-300)) throw CudaError(2, "quadratic regularization: L must be symmetric on device");
+  q.n = n;
+  q.eta = eta;
+  q.maxcols = maxcols;
+  const size_t nn = (size_t)n * n;
+  AO_CUDA(cudaMalloc(&q.L, nn * sizeof(double)));
+  AO_CUDA(cudaMalloc(&q.Q, nn * sizeof(double)));
+  AO_CUDA(cudaMalloc(&q.lam, (size_t)n * sizeof(double)));
+  AO_CUDA(cudaMalloc(&q.tmp, std::max(nn, (size_t)n * maxcols) * sizeof(double)));
+  AO_CUDA(cudaMemcpy(q.L, L_host, nn * sizeof(double), cudaMemcpyHostToDevice));
+  // eigenvectors: one-sided Jacobi on (a copy of) the symmetric L orthogonalises the columns of L*Q
+  AO_CUDA(cudaMemcpy(q.tmp, L_host, nn * sizeof(double), cudaMemcpyHostToDevice));
+  jacobi_onesided(q.tmp, n, (int)n, q.Q, q.lam, st, nullptr);
+  // eigenvalues with their sign: Rayleigh quotients q_i' L q_i  (q.tmp now holds L*Q)
+  std::vector<double> Qh(nn), Th(nn), lam((size_t)n);
+  AO_CUDA(cudaMemcpyAsync(Qh.data(), q.Q, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+  AO_CUDA(cudaMemcpyAsync(Th.data(), q.tmp, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+  AO_CUDA(cudaStreamSynchronize(st));
+  for (long long i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (long long j = 0; j < n; ++j) s += Qh[(size_t)(j + i * n)] * Th[(size_t)(j + i * n)];
+    lam[(size_t)i] = s;
+  }
+  AO_CUDA(cudaMemcpy(q.lam, lam.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void quad_prox_free(QuadProx& q) {
+  for (double** p : {&q.L, &q.Q, &q.lam, &q.tmp}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
+int quad_prox_apply(const QuadProx& q, const double* X, long long ldx, double* out, long long ldo, int cols,
+                    const double* rho_dev, double rho_host, cudaStream_t st, const int* skip) {
+  if (cols > q.maxcols) throw CudaError(1, "quadratic regularization: too many columns");
+  int n = dgemm_small(1, 0, q.n, cols, q.n, 1.0, nullptr, q.Q, q.n, X, ldx, 0.0, q.tmp, q.n, st, skip);
+  n += quad_scale_rows(q.tmp, q.n, cols, q.lam, q.eta, rho_dev, rho_host, st, skip);
+  n += dgemm_small(0, 0, q.n, cols, q.n, 1.0, nullptr, q.Q, q.n, q.tmp, q.n, 0.0, out, ldo, st, skip);
+  return n;
 }
 
 int sum_recip(double* out, const LinTerm* terms, int nterms, cudaStream_t st) {

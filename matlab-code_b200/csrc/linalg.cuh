@@ -30,7 +30,15 @@ int transpose_small(const double* in, long long rows, long long cols, double* ou
 //   sig[j] = ||S(:,j)||_2 afterwards.
 // For S = H (q x n) this yields the eigen-decomposition H'H = V diag(sig^2) V'; for a symmetric positive definite S
 // it yields S = V diag(sig) V'.
-int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st);
+int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st, const int* skip = nullptr);
+
+// S(:,j) *= 1/sig[j]  (0 when sig[j] == 0)
+int scale_cols_inv(double* S, long long rows, int cols, const double* sig, cudaStream_t st, const int* skip);
+
+// Y(i,:) /= (2*eta/rho * lam[i] + 1)   (prox of the quadratic regulariser in the eigen-basis of L,
+// constraints_to_prox.m:62-66: (2*eta/rho*L + I) \ x)
+int quad_scale_rows(double* Y, long long rows, int cols, const double* lam, double eta, const double* rho_dev,
+                    double rho_host, cudaStream_t st, const int* skip);
 
 // X(i,j) = At(i,j) / (half_rho * (lam[i] + shift) + mu[j])   with half_rho = *rho_dev / 2   (Sylvester in eigen-bases)
 int sylvester_scale(double* X, const double* At, long long rows, int cols, const double* lam, double shift,

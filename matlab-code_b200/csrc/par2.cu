@@ -477,6 +477,53 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L,
   }
 }
 
+__global__ void par2_tsmooth_diag_kernel(Par2Layout L, const double* __restrict__ rho_k, double eta,
+                                         double* __restrict__ dp, const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int K = L.K;
+  const double c = -2.0 * eta;
+  for (int k = 0; k < K; ++k) {  // t_smoothness_prox.m:23-37
+    double a = 4.0 * eta + rho_k[k];
+    if (k == 0) a -= 2.0 * eta;
+    if (k == K - 1) a -= 2.0 * eta;
+    if (k > 0) {
+      const double m = c / dp[k - 1];  // :41-45
+      a -= m * c;
+    }
+    dp[k] = a;
+  }
+}
+
+__global__ void par2_tsmooth_solve_kernel(Par2Layout L, const double* __restrict__ V, const double* __restrict__ rho_k,
+                                          double eta, const double* __restrict__ dp, double* __restrict__ out,
+                                          const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  const int K = L.K;
+  const long long J = L.joff[1] - L.joff[0];
+  const long long n = J * L.R;
+  const double c = -2.0 * eta;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long j = e % J, r = e / J;
+    const long long base = j + r * L.Jtot;
+    double prev = rho_k[0] * V[base];
+    out[base] = prev;
+    for (int k = 1; k < K; ++k) {  // forward elimination of the right-hand sides (:41-45)
+      const long long g = base + (long long)k * J;
+      const double m = c / dp[k - 1];
+      prev = rho_k[k] * V[g] - m * prev;
+      out[g] = prev;
+    }
+    double q = out[base + (long long)(K - 1) * J] / dp[K - 1];  // back substitution (:48-54)
+    out[base + (long long)(K - 1) * J] = q;
+    for (int k = K - 2; k >= 0; --k) {
+      const long long g = base + (long long)k * J;
+      q = (out[g] - c * q) / dp[k];
+      out[g] = q;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kP2Threads) par2_seg_norms_kernel(Par2Layout L, const double* __restrict__ Bst,
                                                                      const double* __restrict__ Z,
                                                                      const double* __restrict__ P,
@@ -509,6 +556,12 @@ __global__ void __launch_bounds__(kP2Threads) par2_seg_norms_kernel(Par2Layout L
       case RED_NORM2: rg = fma(b, b, rg); break;
       case RED_TVSUM:
         if (j + 1 < Jk) rg += Bst[g + 1] - b;
+        break;
+      case RED_TSMOOTH:
+        if (k > 0) {
+          const double d = b - Bst[g - Jk];  // same element of the previous slice (equal J_k)
+          rg = fma(d, d, rg);
+        }
         break;
       case RED_GLQUAD: {
         double lx = b;
@@ -669,6 +722,15 @@ int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, 
   par2_B_step2b_kernel<<<L.K, kP2Threads, 0, st>>>(L, a, tol, ctl, counter);
   AO_CHECK_LAUNCH();
   return 1;
+}
+
+int par2_tsmooth_prox(const Par2Layout& L, const double* V, const double* rho_k, double eta, double* dp, double* out,
+                      const InnerCtl* ctl, cudaStream_t st) {
+  par2_tsmooth_diag_kernel<<<1, 32, 0, st>>>(L, rho_k, eta, dp, ctl);
+  AO_CHECK_LAUNCH();
+  par2_tsmooth_solve_kernel<<<flat_grid((L.Jtot / L.K) * L.R), 256, 0, st>>>(L, V, rho_k, eta, dp, out, ctl);
+  AO_CHECK_LAUNCH();
+  return 2;
 }
 
 int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, const double* P, const double* DeltaB,

@@ -90,6 +90,13 @@ int par2_B_form_prox_input(const Par2Layout& L, const Par2BArgs& a, double* V, c
 int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, InnerCtl* ctl, unsigned* counter,
                   cudaStream_t st);
 
+// tPARAFAC2 prox over all slices at once (t_smoothness_prox.m:23-56): for every element (j,r) the K values solve the
+// tridiagonal system  diag(4l+rho_k; ends 2l+rho_k), off-diagonals -2l, right-hand side rho_k*V_k(j,r)  by the Thomas
+// algorithm.  Needs equal J_k.  dp (K doubles) is scratch for the eliminated diagonal.
+int par2_tsmooth_prox(const Par2Layout& L, const double* V, const double* rho_k, double eta, double* dp, double* out,
+                      const InnerCtl* ctl, cudaStream_t st);
+constexpr int RED_TSMOOTH = 100;  // reg kind for par2_seg_norms: ||B_k - B_{k-1}||^2 (t_smoothness_penalty.m:5-9)
+
 // per-slice objective terms: out[k*4 + {0,1,2,3}] = ||B_k||^2, ||B_k - Z_k||^2, ||B_k - P_k DeltaB||^2, reg(B_k)
 int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, const double* P, const double* DeltaB,
                    int reg_kind, double* out, cudaStream_t st);

@@ -8,6 +8,7 @@
 // Repository functions project_box / project_simplex / project_L1 / project_L2 / project_monotone /
 // prox_abs / prox_zero / prox_L2 (un-vendored; implemented from their mathematical definitions).
 #include "smallops.cuh"
+#include "linalg.cuh"
 
 #include <algorithm>
 
@@ -436,6 +437,8 @@ constexpr size_t kSerialSmemLimit = 200 * 1024;
 }  // namespace
 
 size_t prox_scratch_bytes(int kind, long long rows, int cols) {
+  if (kind == PROX_ORTHONORMAL)  // copy of X, rotations V, singular values
+    return ((size_t)rows * cols + (size_t)cols * cols + (size_t)cols) * sizeof(double);
   if (!is_serial_kind(kind)) return 0;
   const size_t per = (size_t)serial_doubles_per_col(kind, rows) * sizeof(double);
   return (per > kSerialSmemLimit) ? per * (size_t)cols : 0;
@@ -470,6 +473,20 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
       AO_CHECK_LAUNCH();
       return 1;
     default: break;
+  }
+  if (kind == PROX_ORTHONORMAL) {
+    // project_ortho.m:3-4: Z = U*V' of the thin SVD = polar factor, by one-sided Jacobi: X*W = U*diag(sig)
+    if (rows < cols) throw CudaError(2, "'orthonormal' needs at least as many rows as columns on device");
+    if (scratch == nullptr) throw CudaError(1, "prox_apply: scratch buffer required for 'orthonormal'");
+    double* S = static_cast<double*>(scratch);
+    double* W = S + (size_t)rows * cols;
+    double* sig = W + (size_t)cols * cols;
+    AO_CUDA(cudaMemcpy2DAsync(S, (size_t)rows * 8, X, (size_t)ldx * 8, (size_t)rows * 8, (size_t)cols,
+                              cudaMemcpyDeviceToDevice, st));
+    int n = jacobi_onesided(S, rows, cols, W, sig, st, skip);
+    n += scale_cols_inv(S, rows, cols, sig, st, skip);
+    n += dgemm_small(0, 1, rows, cols, cols, 1.0, nullptr, S, rows, W, cols, 0.0, out, ldo, st, skip);
+    return n;
   }
   if (is_serial_kind(kind)) {
     const long long per = serial_doubles_per_col(kind, rows);

@@ -140,6 +140,22 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
                long long rows, int cols, const double* rho_dev, double rho_host, void* scratch, cudaStream_t st,
                const int* skip);
 
+// 'quadratic regularization' (constraints_to_prox.m:62-67): prox(x,rho) = (2*eta/rho*L + I) \ x for a SYMMETRIC L,
+// applied in the eigen-basis L = Q diag(lam) Q' (computed once): out = Q * ((Q'x) ./ (2*eta/rho*lam + 1)).
+struct QuadProx {
+  double* L = nullptr;    // n x n (kept for the regulariser value eta*trace(x'Lx))
+  double* Q = nullptr;    // n x n eigenvectors
+  double* lam = nullptr;  // n eigenvalues
+  double* tmp = nullptr;  // n x maxcols scratch
+  long long n = 0;
+  int maxcols = 0;
+  double eta = 0.0;
+};
+void quad_prox_setup(QuadProx& q, const double* L_host, long long n, double eta, int maxcols, cudaStream_t st);
+void quad_prox_free(QuadProx& q);
+int quad_prox_apply(const QuadProx& q, const double* X, long long ldx, double* out, long long ldo, int cols,
+                    const double* rho_dev, double rho_host, cudaStream_t st, const int* skip);
+
 // ---- reductions ---------------------------------------------------------------------------------------
 enum RedKind : int {
   RED_DOT = 0,         // sum a.*b

@@ -451,3 +451,27 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
     init_options = {'lambdas_init': lambdas, 'nvecs': 0, 'distr': distr, 'normalize': 1}
     G = init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=Delta_shapes)
     return Z, G, {}
+
+
+def config_tparafac2(I=16, J=14, K=9, R=3, seed=0, noise=0.05, eta=0.05, drift=0.05):
+    """example_script11 style: PARAFAC2 whose B_k evolve smoothly over k (B_k = B_0 + k*drift*D), nonneg A and C and the
+    temporal-smoothness ('tPARAFAC2') regulariser on the B_k mode."""
+    rng = np.random.RandomState(seed)
+    A = rng.rand(I, R)
+    C = rng.rand(K, R) + 0.5
+    B0 = rng.rand(J, R)
+    D = rng.randn(J, R)
+    X = []
+    for k in range(K):
+        Xk = A @ np.diag(C[k, :]) @ (B0 + k * drift * D).T
+        Nk = rng.randn(*Xk.shape)
+        X.append(Xk + noise * np.linalg.norm(Xk) / np.linalg.norm(Nk) * Nk)
+    obj, _ = normalize_objects([X], ['PAR2'])
+    nn = ('non-negativity',)
+    coupling = {'lin_coupled_modes': [0, 0, 0], 'coupling_type': [], 'coupl_trafo_matrices': [None] * 3}
+    Z = {'loss_function': ['Frobenius'], 'model': ['PAR2'], 'modes': [[1, 2, 3]], 'size': [I, [J] * K, K],
+         'coupling': coupling, 'constrained_modes': [1, 1, 1], 'constraints': [nn, ('tPARAFAC2', eta), nn],
+         'weights': [1.0], 'object': obj}
+    init_options = {'lambdas_init': [[1.0] * R], 'nvecs': 0, 'distr': [d_rand, d_rand, d_rand01], 'normalize': 1}
+    G = init_coupled_AOADMM_CMTF(Z, init_options, rng)
+    return Z, G, {}

@@ -125,6 +125,60 @@ def test_prox_idempotent_projections(ab):
         assert rel(ab.prox(con, once), once) < 1e-12, con
 
 
+@pytest.mark.parametrize('rows,cols', [(5, 5), (40, 3), (300, 16), (2049, 64), (500, 200)])
+def test_prox_orthonormal_polar_factor(ab, rows, cols):
+    """'orthonormal' (project_ortho.m:3-4: U*V' of the thin SVD) by one-sided Jacobi."""
+    V = np.random.RandomState(rows + cols).randn(rows, cols)
+    Y = ab.prox(('orthonormal',), V)
+    assert rel(Y, P.project_ortho(V)) < 1e-11
+    assert np.linalg.norm(Y.T @ Y - np.eye(cols)) < 1e-12 * cols
+
+
+@pytest.mark.parametrize('rows,cols', [(1, 1), (7, 2), (120, 6), (700, 16)])
+def test_prox_quadratic_regularization(ab, rows, cols):
+    """'quadratic regularization' (constraints_to_prox.m:62-66) with a symmetric L: graph Laplacian and an indefinite one."""
+    rng = np.random.RandomState(rows)
+    V = rng.randn(rows, cols)
+    S = rng.randn(rows, rows)
+    for L, eta in ((P.gl_laplacian(rows), 0.5), (0.05 * (S + S.T) / max(rows, 1) ** 0.5, 0.3)):
+        con = ('quadratic regularization', eta, L)
+        ops, _ = P.constraints_to_prox([1], [con], [rows])
+        for rho in (1.0, 0.37):
+            assert rel(ab.prox(con, V, rho=rho), ops[0](V, rho)) < 1e-10, (rows, cols, rho)
+    with pytest.raises(ab.AoadmmError) as e:
+        ab.prox(('quadratic regularization', 0.1, np.triu(np.ones((rows, rows))) if rows > 1 else np.ones((2, 2))), V)
+    assert e.value.status_name in ('UNSUPPORTED', 'INVALID_ARG')
+
+
+def test_orthonormal_and_quadratic_in_the_loop(ab):
+    I, J, K, R = 30, 26, 22, 3
+    L = P.gl_laplacian(I)
+    for cons in ([('quadratic regularization', 1e-2, L), ('orthonormal',), ('non-negativity',)],
+                 [('orthonormal',), ('l2-ball', 1.0), ('quadratic regularization', 1e-3, P.gl_laplacian(K))]):
+        Z, G, _ = pg.config_single_cp(sz=(I, J, K), R=R, seed=12, noise=0.1, constraints=cons, distr=[pg.d_randn] * 3)
+        Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=20))
+        _assert_out_close(od, oo)
+        assert_state_close(Gd, Go)
+
+
+def test_tparafac2_constraint(ab):
+    """example_script11 style: temporal smoothness across the B_k of a regular PARAFAC2 (t_smoothness_prox.m)."""
+    Z, G, _ = pg.config_tparafac2(seed=2, eta=0.05)   # B_k drifting smoothly over k, K=9 slices of 16 x 14
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=25))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+    Zbad = dict(Z, size=[Z['size'][0], [14] * 8 + [13], 9])   # unequal slices: the penalty is undefined
+    Zbad['object'] = [Z['object'][0][:8] + [Z['object'][0][8][:, :13]]]
+    Gbad = dict(G)
+    for key in ('fac', 'constraint_fac', 'constraint_dual_fac'):
+        Gbad[key] = list(G[key])
+        Gbad[key][1] = G[key][1][:8] + [G[key][1][8][:13]]
+    Gbad['P'] = [G['P'][0][:8] + [G['P'][0][8][:13]]]
+    Gbad['mu_DeltaB'] = [G['mu_DeltaB'][0][:8] + [G['mu_DeltaB'][0][8][:13]]]
+    with pytest.raises(ab.AoadmmError):
+        ab.cmtf_fun_AOADMM(Zbad, pg.znorm_const(Zbad), Gbad, None, None, None, None, pg.default_options(MaxOuterIters=2))
+
+
 def test_custom_constraint_is_unsupported(ab):
     with pytest.raises(ab.AoadmmError) as e:
         ab.prox(('custom', None), np.zeros((3, 2)))
