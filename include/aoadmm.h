@@ -225,6 +225,9 @@ int aoadmm_launch_count(const aoadmm_handle *h, int64_t *count);
 int aoadmm_phase_ms(const aoadmm_handle *h, double ms[3]);
 /* device time (CUDA events on the engine's stream, first to last kernel) of the last aoadmm_run, ms */
 int aoadmm_last_run_ms(const aoadmm_handle *h, double *ms);
+/* same, but only the outer iterations (cmtf_fun_AOADMM.m:87-476), i.e. without the one-off iteration-0 objective
+ * of cmtf_fun_AOADMM.m:32 (one extra MTTKRP per tensor) */
+int aoadmm_last_loop_ms(const aoadmm_handle *h, double *ms);
 
 #ifdef __cplusplus
 }

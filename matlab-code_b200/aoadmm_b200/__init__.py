@@ -415,6 +415,11 @@ class Solver:
         _capi.check(lib.aoadmm_last_run_ms(self._h, C.byref(v)), self._h)
         return v.value
 
+    def last_loop_ms(self):
+        v = C.c_double(0)
+        _capi.check(lib.aoadmm_last_loop_ms(self._h, C.byref(v)), self._h)
+        return v.value
+
     def phase_ms(self):
         a = np.zeros(3)
         _capi.check(lib.aoadmm_phase_ms(self._h, _dp(a)), self._h)

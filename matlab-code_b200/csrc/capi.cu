@@ -157,6 +157,12 @@ int aoadmm_last_run_ms(const aoadmm_handle* h, double* ms) {
   return AOADMM_OK;
 }
 
+int aoadmm_last_loop_ms(const aoadmm_handle* h, double* ms) {
+  if (!h || !ms) return AOADMM_ERR_INVALID_ARG;
+  *ms = h->eng->last_loop_ms();
+  return AOADMM_OK;
+}
+
 // ---- operator-level entry points ---------------------------------------------------------------
 int aoadmm_mttkrp(const double* X, int32_t order, const int64_t* dims, const double* const* factors, int32_t R,
                   int32_t n, double* out, int32_t device) {

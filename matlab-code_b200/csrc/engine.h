@@ -143,6 +143,7 @@ class Engine {
   int64_t launches() const { return launches_; }
   void phase_ms(double ms[3]);
   double last_run_ms() const { return last_run_ms_; }
+  double last_loop_ms() const { return last_loop_ms_; }
   std::string last_error;
 
  private:
@@ -232,8 +233,8 @@ class Engine {
   void phase_end();
   void phase_collect();
   aoadmm_options opt_{};
-  cudaEvent_t run_ev_[2] = {nullptr, nullptr};
-  double last_run_ms_ = 0.0;
+  cudaEvent_t run_ev_[3] = {nullptr, nullptr, nullptr};
+  double last_run_ms_ = 0.0, last_loop_ms_ = 0.0;
 };
 
 }  // namespace aoadmm

@@ -190,7 +190,8 @@ __global__ void prox_simplex_row_kernel(double eta, const double* __restrict__ X
 
 // ---- serial per-column algorithms ------------------------------------------------------------------
 // Condat 2013 direct 1-D TV: x = argmin 0.5||x-y||^2 + lam * sum |x[i+1]-x[i]|
-__device__ void tv_condat_serial(const double* y, double* x, long long n, double lam) {
+// rc[c] = 1/c (correctly rounded) replaces the two divisions per step by multiplications (<= 1 ulp from x/c).
+__device__ __forceinline__ void tv_condat_serial(const double* y, double* x, long long n, double lam, const double* rc) {
   if (n <= 0) return;
   if (!(lam > 0.0)) {
     for (long long i = 0; i < n; ++i) x[i] = y[i];
@@ -215,7 +216,7 @@ __device__ void tv_condat_serial(const double* y, double* x, long long n, double
         umax = minlam;
         umin = vmax + umax - vmin;
       } else {
-        vmin += umin / (double)(k - k0 + 1);
+        vmin += umin * rc[k - k0 + 1];
         do x[k0++] = vmin; while (k0 <= k);
         return;
       }
@@ -241,12 +242,12 @@ __device__ void tv_condat_serial(const double* y, double* x, long long n, double
         k++;
         if (umin >= lam) {
           kminus = k;
-          vmin += (umin - lam) / (double)(kminus - k0 + 1);
+          vmin += (umin - lam) * rc[kminus - k0 + 1];
           umin = lam;
         }
         if (umax <= minlam) {
           kplus = k;
-          vmax += (umax + lam) / (double)(kplus - k0 + 1);
+          vmax += (umax + lam) * rc[kplus - k0 + 1];
           umax = minlam;
         }
       }
@@ -372,15 +373,17 @@ __device__ void gl_solve_serial(const double* v, double* x, long long n, double 
   for (long long i = n - 2; i >= 0; --i) x[i] = x[i] - cp[i] * x[i + 1];
 }
 
-// one CTA (32 threads) per column; column staged in shared memory when it fits, else in global scratch
+// one CTA (32 threads) per column; column staged in shared memory when it fits (SMEM: the compiler then emits
+// LDS/STS instead of generic loads), else in global scratch
+template <bool SMEM>
 __global__ void prox_serial_col_kernel(int kind, double p0, const double* __restrict__ X, long long ldx,
                                        double* __restrict__ out, long long ldo, long long rows,
                                        const double* rho_dev, double rho_host, double* gscratch,
-                                       long long scratch_per_col, int use_smem, const int* __restrict__ skip) {
+                                       long long scratch_per_col, const int* __restrict__ skip) {
   if (skip != nullptr && *skip != 0) return;
   extern __shared__ double sm[];
   const double rho = load_rho(rho_dev, rho_host);
-  double* base = use_smem ? sm : (gscratch + (long long)blockIdx.x * scratch_per_col);
+  double* base = SMEM ? sm : (gscratch + (long long)blockIdx.x * scratch_per_col);
   const double* x = X + (long long)blockIdx.x * ldx;
   double* o = out + (long long)blockIdx.x * ldo;
   const long long n = rows;
@@ -388,10 +391,12 @@ __global__ void prox_serial_col_kernel(int kind, double p0, const double* __rest
   double* res = base + n;    // n
   double* work = base + 2 * n;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
+  if (kind == PROX_TV)
+    for (long long i = threadIdx.x; i <= n; i += blockDim.x) work[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   if (threadIdx.x == 0) {
     if (kind == PROX_TV) {
-      tv_condat_serial(y, res, n, p0 / rho);
+      tv_condat_serial(y, res, n, p0 / rho, work);
     } else if (kind == PROX_NONDECREASING || kind == PROX_NONINCREASING) {
       double* level = work;
       double* weight = work + n;
@@ -418,7 +423,7 @@ __global__ void prox_serial_col_kernel(int kind, double p0, const double* __rest
 long long serial_doubles_per_col(int kind, long long rows) {
   const long long n = rows, n1 = rows + 1;
   switch (kind) {
-    case PROX_TV: return 2 * n;
+    case PROX_TV: return 3 * n + 1;
     case PROX_NONDECREASING:
     case PROX_NONINCREASING: return 2 * n + 2 * n + (n + 1) / 2 + 2;
     case PROX_UNIMODAL: return 2 * n + 5 * n1 + n1 + 4;
@@ -496,13 +501,17 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     if (use_smem && bytes > 48 * 1024) {
       static size_t configured = 0;
       if (bytes > configured) {
-        AO_CUDA(cudaFuncSetAttribute(prox_serial_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        AO_CUDA(cudaFuncSetAttribute(prox_serial_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSerialSmemLimit));
         configured = kSerialSmemLimit;
       }
     }
-    prox_serial_col_kernel<<<cols, 32, use_smem ? bytes : 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
-                                                                    static_cast<double*>(scratch), per, use_smem, skip);
+    if (use_smem)
+      prox_serial_col_kernel<true><<<cols, 32, bytes, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
+                                                            static_cast<double*>(scratch), per, skip);
+    else
+      prox_serial_col_kernel<false><<<cols, 32, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
+                                                         static_cast<double*>(scratch), per, skip);
     AO_CHECK_LAUNCH();
     return 1;
   }
