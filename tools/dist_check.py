@@ -30,5 +30,22 @@ for dims in [(64, 48, 40, 80, 8), (130, 90, 37, 100, 32), (40, 36, 30, 64, 64)]:
     t = torch.from_numpy(np.ascontiguousarray(Gd['fac'][2])).cuda(); t0 = t.clone(); dist.broadcast(t0, 0)
     same = bool(torch.equal(t, t0))
     if not same: print('rank', rank, 'state differs from rank 0'); ok = False
+# PARAFAC2 objects (replicated) next to a sharded CP tensor, and a linear coupling (type 4, type 1)
+extra = [('cp+par2', pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=3, noise=0.1)[:2]),
+         ('lin4', pg.config_linear_coupling(4, seed=4)[:2]), ('lin1', pg.config_linear_coupling(1, seed=1, second='tensor')[:2])]
+for name, (Z, G) in extra:
+    opts = pg.default_options(MaxOuterIters=15)
+    zn = pg.znorm_const(Z)
+    Gd, od = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts, rank=rank, world_size=world, device=lr, unique_id=uid())
+    if rank == 0:
+        Go, oo = oracle_solve(Z, zn, G, options=opts)
+        errs = []
+        for a, b in zip(Gd['fac'], Go['fac']):
+            if isinstance(b, list):
+                errs += [np.linalg.norm(x - y) / np.linalg.norm(y) for x, y in zip(a, b)]
+            else:
+                errs.append(np.linalg.norm(a - b) / np.linalg.norm(b))
+        print(name, 'world', world, 'max fac err %.2e' % max(errs), 'df %.2e' % abs(od['f_tensors'] - oo['f_tensors']))
+        ok &= max(errs) < 1e-8
 if rank == 0: print('DIST OK' if ok else 'DIST FAILED')
 dist.destroy_process_group()
