@@ -511,7 +511,7 @@ Engine::~Engine() {
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
     for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
-                    (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
+                    (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.Vprev, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
                     (void*)s.res_partials})
       if (q) cudaFree(q);
     if (s.segn_host) cudaFreeHost(s.segn_host);
@@ -799,6 +799,7 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   AO_CUDA(cudaMalloc(&s.Binv2, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.Binv3, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.contrib, KRR * sizeof(double)));
+  AO_CUDA(cudaMalloc(&s.Vprev, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.rho2, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.rho3, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.tdiag, sizeof(double) * s.K));
@@ -926,10 +927,11 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
   b.gS = s.gS.p;
   b.norms = s.norms;
   b.Znew = deferred ? m.Znew.p : nullptr;
+  b.Vprev = s.Vprev;
   InnerTol tol{opt_.innerRelPrTol_coupl, opt_.innerRelDualTol_coupl, opt_.innerRelPrTol_constr,
                opt_.innerRelDualTol_constr};
   for (int it = 0; it < opt_.MaxInnerIters; ++it) {
-    launches_ += par2_B_step1(s.lay, b, m.ctl, st_);
+    launches_ += par2_B_step1(s.lay, b, m.ctl, it > 0 ? 1 : 0, st_);  // cold start once per outer iteration
     launches_ += par2_B_deltaB(s.lay, b, m.ctl, st_);
     launches_ += par2_B_step2a(s.lay, b, m.ctl, st_);
     if (deferred) {

@@ -97,7 +97,7 @@ struct Par2State {
   uint64_t T_version = 0;                // version of A that T was computed from
   DevMat P, muDB, DeltaB, PDold, gM, gS;
   double *G2 = nullptr, *Binv2 = nullptr, *Binv3 = nullptr, *rho2 = nullptr, *rho3 = nullptr, *contrib = nullptr,
-         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr, *tdiag = nullptr;
+         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr, *tdiag = nullptr, *Vprev = nullptr;
   double* segn_host = nullptr;           // pinned: K x 4 per-slice objective terms + 1 residual
   bool explicit_residual = false;        // objective needs ||X_k - A D_k B_k'||^2 (mode A is not updated last)
 };

@@ -91,9 +91,20 @@ __global__ void par2_modeA_had_kernel(Par2Layout L, const double* __restrict__ G
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= R * R) return;
   const int a = e % R, b = e / R;
-  double acc = 0.0;
-  for (int k = 0; k < L.K; ++k) acc += (C[k + a * ldc] * G2[(size_t)k * R * R + e]) * C[k + b * ldc];
-  Csum[e] = acc;
+  const double* ca = C + a * ldc;
+  const double* cb = C + b * ldc;
+  const double* g = G2 + e;
+  const size_t RR = (size_t)R * R;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = 0;
+  for (; k + 3 < L.K; k += 4) {
+    a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
+    a1 += (ca[k + 1] * g[(size_t)(k + 1) * RR]) * cb[k + 1];
+    a2 += (ca[k + 2] * g[(size_t)(k + 2) * RR]) * cb[k + 2];
+    a3 += (ca[k + 3] * g[(size_t)(k + 3) * RR]) * cb[k + 3];
+  }
+  for (; k < L.K; ++k) a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
+  Csum[e] = (a0 + a1) + (a2 + a3);
 }
 
 __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2SysArgs a) {
@@ -201,7 +212,7 @@ __global__ void par2_rho_max_kernel(const double* __restrict__ rho_k, int K, dou
 // matrix, round-robin pair ordering, one warp per column pair.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl,
-                                                                   int use_gmem) {
+                                                                   int use_gmem, int warm) {
   if (ctl != nullptr && ctl->done != 0) return;
   extern __shared__ double sm[];
   __shared__ int s_rot;
@@ -244,17 +255,33 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
     M[j + c * Jk] = x + a.mu[g];
   }
   __syncthreads();
-  // S = M DeltaB'   (:532)
+  // S = M DeltaB' W  (:532) with W = I on a cold start, else the rotations found for this slice in the previous inner
+  // iteration (the matrix changes little between inner iterations, so the Jacobi iteration below then needs 1-2 sweeps
+  // instead of 6-8; the polar factor it converges to is the same).  Wm = DeltaB' W is formed in the Binv area.
+  double* Wm = Bi;
+  if (warm) {
+    for (int e = tid; e < RR; e += nt) V[e] = a.Vprev[(size_t)k * RR + e];
+    __syncthreads();
+    for (int e = tid; e < RR; e += nt) {
+      const int r = e % R, c = e / R;
+      double x = 0.0;
+      for (int q = 0; q < R; ++q) x = fma(dB[q + r * R], V[q + c * R], x);
+      Wm[e] = x;
+    }
+  } else {
+    for (int e = tid; e < RR; e += nt) Wm[e] = dB[(e / R) + (e % R) * R];  // DeltaB'
+  }
+  __syncthreads();
   for (int it = tid; it < nitems; it += nt) {
     const int c = it / Jk, j = it % Jk;
     double x = 0.0;
-    for (int r = 0; r < R; ++r) x = fma(M[j + r * Jk], dB[c + r * R], x);
+    for (int r = 0; r < R; ++r) x = fma(M[j + r * Jk], Wm[r + c * R], x);
     S[j + c * Jk] = x;
   }
   __syncthreads();
   // one-sided Jacobi: S <- S*V with orthogonal columns
   const int Re = (R + 1) & ~1, npairs = Re / 2;
-  const double tol = 2.220446049250313e-16 * sqrt((double)Jk);
+  const double tol2 = 2.220446049250313e-16 * 2.220446049250313e-16 * (double)Jk;
   for (int sweep = 0; sweep < 60; ++sweep) {
     if (tid == 0) s_rot = 0;
     __syncthreads();
@@ -286,10 +313,10 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
         al = warp_sum(al);
         be = warp_sum(be);
         ga = warp_sum(ga);
-        if (fabs(ga) > tol * sqrt(al * be)) {
+        if (ga * ga > tol2 * (al * be)) {
           const double zeta = (be - al) / (2.0 * ga);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
           for (int j = lane; j < Jk; j += 32) {
             const double xv = x[j], yv = y[j];
             x[j] = cs * xv - sn * yv;
@@ -309,6 +336,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
     __syncthreads();
     if (rot == 0) break;
   }
+  for (int e = tid; e < RR; e += nt) a.Vprev[(size_t)k * RR + e] = V[e];
   // singular values -> 1/sigma (kept in the Bi area, no longer needed)
   for (int r = warp; r < R; r += nw) {
     const double* x = S + (size_t)r * Jk;
@@ -337,20 +365,30 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   }
 }
 
-__global__ void par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl) {
+__global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl) {
   if (ctl != nullptr && ctl->done != 0) return;
+  __shared__ double red[32];
   __shared__ double s_sum;
-  const int R = L.R, RR = R * R;
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int k = 0; k < L.K; ++k) s += a.rho_k[k];   // :542
-    s_sum = s;
-  }
+  const int R = L.R, RR = R * R, K = L.K;
+  // sum_k rho_k (:542) in a fixed (strided + tree) order: deterministic, independent of the launch
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s += a.rho_k[k];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) s_sum = s;
   __syncthreads();
-  for (int e = threadIdx.x; e < RR; e += blockDim.x) {
-    double acc = 0.0;
-    for (int k = 0; k < L.K; ++k) acc += a.contrib[(size_t)k * RR + e];
-    a.DeltaB[e] = acc / s_sum;                        // :544
+  const double tot = s_sum;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RR; e += gridDim.x * blockDim.x) {
+    const double* c = a.contrib + e;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {   // four independent load streams; fixed association => deterministic
+      a0 += c[(size_t)k * RR];
+      a1 += c[(size_t)(k + 1) * RR];
+      a2 += c[(size_t)(k + 2) * RR];
+      a3 += c[(size_t)(k + 3) * RR];
+    }
+    for (; k < K; ++k) a0 += c[(size_t)k * RR];
+    a.DeltaB[e] = ((a0 + a1) + (a2 + a3)) / tot;      // :541-544
   }
 }
 
@@ -688,17 +726,17 @@ int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st) {
   return 1;
 }
 
-int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
+int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, int warm, cudaStream_t st) {
   const size_t smem = par2_step1_smem_bytes(L.Jmax, L.R);
   const int use_gmem = (smem == (size_t)3 * L.R * L.R * sizeof(double)) ? 1 : 0;
   opt_in_smem(par2_B_step1_kernel, smem);
-  par2_B_step1_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl, use_gmem);
+  par2_B_step1_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl, use_gmem, warm);
   AO_CHECK_LAUNCH();
   return 1;
 }
 
 int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
-  par2_B_deltaB_kernel<<<1, 256, 0, st>>>(L, a, ctl);
+  par2_B_deltaB_kernel<<<(unsigned)ceil_div(L.R * L.R, 64), 256, 0, st>>>(L, a, ctl);
   AO_CHECK_LAUNCH();
   return 1;
 }

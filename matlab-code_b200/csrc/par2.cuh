@@ -78,9 +78,11 @@ struct Par2BArgs {
   double* gS;              // scratch Jtot x R
   double* norms;           // scratch K x 8
   double* Znew;            // deferred prox output (stacked) or nullptr
+  double* Vprev;           // K x R x R: Jacobi rotations of the previous inner iteration (warm start)
 };
 // one inner iteration of ADMM_B_Parafac2 is  step1 -> deltaB -> step2a -> [prox of every slice] -> step2b
-int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
+// warm != 0: start the Jacobi iteration from the rotations of the previous call (a.Vprev)
+int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, int warm, cudaStream_t st);
 int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
 // coupling part: mu_k += B_k - P_k DeltaB ; per-slice norms 0..3
 int par2_B_step2a(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);

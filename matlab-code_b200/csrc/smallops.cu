@@ -548,7 +548,33 @@ __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __re
     const double* a = jb.a + (long long)c * jb.lda;
     const double* b = (jb.b != nullptr) ? jb.b + (long long)c * jb.ldb : nullptr;
     double acc = 0.0;
-    for (long long i = tid; i < jb.rows; i += nt) {
+    long long i = tid;
+    if (jb.kind == RED_DOT || jb.kind == RED_NORM2 || jb.kind == RED_COLNORM || jb.kind == RED_DIFF2) {
+      // the three hot kinds: four independent load streams per thread (latency hiding at one CTA per SM)
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+      for (; i + 3LL * nt < jb.rows; i += 4LL * nt) {
+        const double v0 = a[i], v1 = a[i + nt], v2 = a[i + 2LL * nt], v3 = a[i + 3LL * nt];
+        if (jb.kind == RED_DOT) {
+          c0 = fma(v0, b[i], c0);
+          c1 = fma(v1, b[i + nt], c1);
+          c2 = fma(v2, b[i + 2LL * nt], c2);
+          c3 = fma(v3, b[i + 3LL * nt], c3);
+        } else if (jb.kind == RED_DIFF2) {
+          const double d0 = v0 - b[i], d1 = v1 - b[i + nt], d2 = v2 - b[i + 2LL * nt], d3 = v3 - b[i + 3LL * nt];
+          c0 = fma(d0, d0, c0);
+          c1 = fma(d1, d1, c1);
+          c2 = fma(d2, d2, c2);
+          c3 = fma(d3, d3, c3);
+        } else {
+          c0 = fma(v0, v0, c0);
+          c1 = fma(v1, v1, c1);
+          c2 = fma(v2, v2, c2);
+          c3 = fma(v3, v3, c3);
+        }
+      }
+      acc = (c0 + c1) + (c2 + c3);
+    }
+    for (; i < jb.rows; i += nt) {
       const double v = a[i];
       switch (jb.kind) {
         case RED_DOT: acc = fma(v, b[i], acc); break;
