@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AOADMM_ABI_VERSION 1
+#define AOADMM_ABI_VERSION 2
 
 typedef struct aoadmm_handle aoadmm_handle;
 
@@ -34,7 +34,7 @@ typedef struct aoadmm_handle aoadmm_handle;
 typedef enum {
   AOADMM_OK = 0,
   AOADMM_ERR_INVALID_ARG = 1,
-  AOADMM_ERR_UNSUPPORTED = 2,          /* 'custom' constraint, non-Frobenius loss, Z.miss, ... */
+  AOADMM_ERR_UNSUPPORTED = 2,          /* 'custom' constraint, non-Frobenius loss, ... */
   AOADMM_ERR_NOT_POSITIVE_DEFINITE = 3, /* chol() would have thrown (cmtf_fun_AOADMM.m:142 ...) */
   AOADMM_ERR_NON_FINITE = 4,
   AOADMM_ERR_CUDA = 5,
@@ -95,6 +95,11 @@ typedef struct {
   /* PAR2: K slices X_k (I x J_k col-major); every rank passes all slices (small objects) */
   const double *const *slices;
   int32_t n_slices;
+  /* Z.miss{p} (cmtf_AOADMM.m:68-121): NULL = no missing data; else one byte per element with the layout of
+   * `data` (CP, this rank's slab) / of each slice (PAR2): 1 = observed, 0 = missing.  Missing entries are
+   * re-imputed from the model after every outer iteration (cmtf_fun_AOADMM.m:408-441). */
+  const uint8_t *miss;
+  const uint8_t *const *miss_slices;
 } aoadmm_object;
 
 /* The problem struct Z (example_script6_matrix_matrix_CP_nonneg.m:84-92) flattened. */
@@ -155,6 +160,8 @@ typedef struct {
   double *func_val_conv, *func_coupl_conv, *func_constr_conv, *func_PAR2_coupl, *time_at_it;
   int32_t *inner_iters;
   int32_t error_mode;         /* mode id that raised NOT_POSITIVE_DEFINITE / NON_FINITE (0 if none) */
+  double f_rel_missing;       /* out.f_rel_missing (NaN without Z.miss), cmtf_fun_AOADMM.m:436-440 */
+  double *func_rel_missing;   /* out.func_rel_missing, MaxOuterIters+1 entries, or NULL */
 } aoadmm_out;
 
 /* State fields of G (init_coupled_AOADMM_CMTF.m:41-45, :62-80, :133-169) */

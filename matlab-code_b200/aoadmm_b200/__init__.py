@@ -97,8 +97,7 @@ class Solver:
         for p in range(P):
             if Z['loss_function'][p] != 'Frobenius':
                 raise AoadmmError(2, "loss function %r is not supported (Frobenius only)" % (Z['loss_function'][p],))
-        if Z.get('miss') is not None and any(x is not None for x in Z['miss']):
-            raise AoadmmError(2, 'missing data (Z.miss) is not supported')
+        miss = Z.get('miss') or [None] * P
         ranks = self._infer_ranks(Z)
         rows = np.zeros(nb_modes, dtype=np.int64)
         nsl = np.zeros(nb_modes, dtype=np.int32)
@@ -143,6 +142,16 @@ class Solver:
                     o.data = None
                 o.shard_offset, o.shard_extent = lo, hi - lo
                 o.slices, o.n_slices = None, 0
+                o.miss, o.miss_slices = None, None
+                if miss[p] is not None:   # Z.miss{p}: true = observed (example_script12_CP_PAR2_EM.m:118-124)
+                    Mk = np.asarray(miss[p])
+                    if Mk.shape[-1] == full_last and (hi - lo) != full_last:
+                        Mk = Mk[..., lo:hi]
+                    Mk = np.asfortranarray(Mk != 0, dtype=np.uint8)
+                    if X is None or Mk.shape != np.shape(X):
+                        raise AoadmmError(1, 'Z.miss{%d} size does not match Z.object{%d}.' % (p + 1, p + 1))
+                    self._keep.append(Mk)
+                    o.miss = Mk.ctypes.data_as(_capi.c_uint8_p)
             else:
                 self.shards.append(None)
                 sl = [_f64(x) for x in Z['object'][p]]
@@ -152,6 +161,17 @@ class Solver:
                 o.data = None
                 o.slices = arr
                 o.n_slices = len(sl)
+                o.miss, o.miss_slices = None, None
+                if miss[p] is not None:
+                    if not isinstance(miss[p], (list, tuple)) or len(miss[p]) != len(sl):
+                        raise AoadmmError(1, 'Z.miss{%d} must be a cell array of length %d for PAR2.' % (p + 1, len(sl)))
+                    mk = [np.asfortranarray(np.asarray(m) != 0, dtype=np.uint8) for m in miss[p]]
+                    for k, (m, x) in enumerate(zip(mk, sl)):
+                        if m.shape != x.shape:
+                            raise AoadmmError(1, 'Z.miss{%d}{%d} size does not match Z.object{%d}{%d}.' % (p + 1, k + 1, p + 1, k + 1))
+                    marr = (_capi.c_uint8_p * len(mk))(*[m.ctypes.data_as(_capi.c_uint8_p) for m in mk])
+                    self._keep += [mk, marr]
+                    o.miss_slices = marr
         lin = np.asarray(Z['coupling']['lin_coupled_modes'], dtype=np.int32)
         ctype = np.asarray(Z['coupling'].get('coupling_type', []), dtype=np.int32)
         ncoup = int(lin.max()) if lin.size else 0
@@ -369,11 +389,13 @@ class Solver:
         o.dimtree = int(options.get('dimtree', 0))
         n = o.MaxOuterIters + 1
         hist = [np.zeros(n) for _ in range(5)]
+        hmiss = np.full(n, np.nan)
         inner = np.zeros((self.nb_modes, max(o.MaxOuterIters, 1)), dtype=np.int32, order='F')
         out = _capi.Out()
         out.func_val_conv, out.func_coupl_conv, out.func_constr_conv, out.func_PAR2_coupl, out.time_at_it = \
             [_dp(h) for h in hist]
         out.inner_iters = inner.ctypes.data_as(_capi.c_int32_p)
+        out.func_rel_missing = _dp(hmiss)
         _capi.check(lib.aoadmm_run(self._h, C.byref(o), C.byref(out)), self._h)
         it = out.OuterIterations
         if out.exit_flag == 0:
@@ -382,7 +404,8 @@ class Solver:
             names = ['f_tensors', 'f_couplings', 'f_constraints', 'f_PAR2_couplings']
             flag = {nm: ('AbsFuncTol' if (out.exit_flag >> q) & 1 else 'RelFuncTol') for q, nm in enumerate(names)}
         return {'f_tensors': out.f_tensors, 'f_couplings': out.f_couplings, 'f_constraints': out.f_constraints,
-                'f_PAR2_couplings': out.f_PAR2_couplings, 'f_rel_missing': float('nan'), 'exit_flag': flag,
+                'f_PAR2_couplings': out.f_PAR2_couplings, 'f_rel_missing': out.f_rel_missing,
+                'func_rel_missing': hmiss[:it + 1].copy(), 'exit_flag': flag,
                 'OuterIterations': it, 'func_val_conv': hist[0][:it + 1].copy(),
                 'func_coupl_conv': hist[1][:it + 1].copy(), 'func_constr_conv': hist[2][:it + 1].copy(),
                 'func_PAR2_coupl': hist[3][:it + 1].copy(), 'time_at_it': hist[4][:it + 1].copy(),
@@ -465,11 +488,16 @@ def cmtf_AOADMM(Z, init, alg_options, **dist):
                     raise ValueError('Number of components for PARAFAC2 is larger than size of slice %d of data '
                                      'tensor %d.' % (k + 1, p + 1))
     zn = []
-    for p in range(P):
+    miss = Z.get('miss') or [None] * P
+    for p in range(P):                                                     # :124-156 (with Z.miss: observed entries only)
         if Z['model'][p] == 'CP':
-            zn.append(float(np.linalg.norm(np.asarray(Z['object'][p]).ravel()) ** 2))
+            X = np.asarray(Z['object'][p])
+            if miss[p] is not None:
+                X = X * (np.asarray(miss[p]) != 0)
+            zn.append(float(np.linalg.norm(X.ravel()) ** 2))
         else:
-            zn.append(float(sum(np.linalg.norm(Xk, 'fro') ** 2 for Xk in Z['object'][p])))
+            zn.append(float(sum(np.linalg.norm(Xk if miss[p] is None else Xk * (np.asarray(miss[p][k]) != 0), 'fro') ** 2
+                                for k, Xk in enumerate(Z['object'][p]))))
     Fac, out = cmtf_fun_AOADMM(Z, zn, init, None, None, None, None, alg_options, **dist)
     Zhat = []
     for p in range(P):

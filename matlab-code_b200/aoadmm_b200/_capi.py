@@ -16,6 +16,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
 
+c_uint8_p = C.POINTER(C.c_uint8)
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
@@ -46,7 +47,8 @@ class Constraint(C.Structure):
 class Object(C.Structure):
     _fields_ = [('model', C.c_int32), ('order', C.c_int32), ('modes', c_int32_p), ('weight', C.c_double),
                 ('znorm_const', C.c_double), ('data', c_double_p), ('shard_offset', C.c_int64),
-                ('shard_extent', C.c_int64), ('slices', C.POINTER(c_double_p)), ('n_slices', C.c_int32)]
+                ('shard_extent', C.c_int64), ('slices', C.POINTER(c_double_p)), ('n_slices', C.c_int32),
+                ('miss', c_uint8_p), ('miss_slices', C.POINTER(c_uint8_p))]
 
 
 class Problem(C.Structure):
@@ -78,7 +80,7 @@ class Out(C.Structure):
                 ('f_PAR2_couplings', C.c_double), ('OuterIterations', C.c_int32), ('exit_flag', C.c_int32),
                 ('func_val_conv', c_double_p), ('func_coupl_conv', c_double_p), ('func_constr_conv', c_double_p),
                 ('func_PAR2_coupl', c_double_p), ('time_at_it', c_double_p), ('inner_iters', c_int32_p),
-                ('error_mode', C.c_int32)]
+                ('error_mode', C.c_int32), ('f_rel_missing', C.c_double), ('func_rel_missing', c_double_p)]
 
 
 HandleP = C.c_void_p

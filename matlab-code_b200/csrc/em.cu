@@ -1,0 +1,149 @@
+// em.cu - EM imputation of missing entries and the masked objective terms.
+//
+// Reference: functions/cmtf_fun_AOADMM.m
+//   :408-441   after every sweep the missing entries (Z.miss == 0) of each object are overwritten by the current
+//              low-rank model; f_rel_missing = sqrt(sum (new-old)^2 / sum old^2)
+//   :1224-1226 objective of a CP object with a mask:   w (Znorm - 2 <X, M.*model> + ||M.*model||^2)
+//   :1249-1252 objective of a PARAFAC2 object with a mask: w sum_k || M_k .* (X_k - A D_k B_k') ||^2
+// One pass over the object does all of it: the model value of every element is a rank-R product
+//     m(i,j,k) = sum_r Fi(i,r) Fj(j,r) Fk(k,r)
+// evaluated by 64 x 64 output tiles (4 x 4 outputs per thread, factor tiles staged in shared memory), compared with
+// the stored element and the mask, and five sums are reduced deterministically (per-CTA partials, fixed-order final
+// sum):  [0] sum_missing (m-x)^2   [1] sum_missing x^2   [2] sum_observed x*m   [3] sum_observed m^2
+//        [4] sum_observed (x-m)^2
+// A PARAFAC2 object is the K = 1 case on the stacked I x Jtot matrix with Fj(j,:) = B(j,:) .* C(seg(j),:).
+#include "em.cuh"
+
+#include <algorithm>
+
+namespace aoadmm {
+
+namespace {
+
+constexpr int kTile = 64;
+constexpr int kRC = 32;  // rank chunk staged per pass
+
+__global__ void __launch_bounds__(256) em_kernel(EmArgs a, int kper) {
+  __shared__ double As[kRC][kTile];
+  __shared__ double Bs[kRC][kTile];
+  __shared__ double red[32];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTile;
+  const int k0 = blockIdx.z * kper, k1 = min(a.K, k0 + kper);
+  const int nchunk = (a.R + kRC - 1) / kRC;
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int k = k0; k < k1; ++k) {
+    double acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int r0 = c * kRC;
+      __syncthreads();
+      for (int e = tid; e < kRC * kTile; e += 256) {
+        const int ii = e % kTile, rr = e / kTile;
+        const int r = r0 + rr;
+        double va = 0.0;
+        if (r < a.R && i0 + ii < a.I) {
+          va = a.Fi[i0 + ii + (long long)r * a.ldFi];
+          if (a.Fk != nullptr) va *= a.Fk[k + (long long)r * a.ldFk];
+        }
+        As[rr][ii] = va;
+      }
+      if (nchunk > 1 || k == k0) {
+        for (int e = tid; e < kRC * kTile; e += 256) {
+          const int jj = e % kTile, rr = e / kTile;
+          const int r = r0 + rr;
+          Bs[rr][jj] = (r < a.R && j0 + jj < a.J) ? a.Fj[j0 + jj + (long long)r * a.ldFj] : 0.0;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int rr = 0; rr < kRC; ++rr) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) av[p] = As[rr][tx + 16 * p];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bv[q] = Bs[rr][ty + 16 * q];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long j = j0 + ty + 16 * q;
+      if (j >= a.J) continue;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const long long i = i0 + tx + 16 * p;
+        if (i >= a.I) continue;
+        const long long idx = i + a.ldI * (j + (long long)a.J * k);
+        const double x = a.X[idx], m = acc[p][q];
+        if (a.mask[idx] != 0) {
+          s[2] = fma(x, m, s[2]);
+          s[3] = fma(m, m, s[3]);
+          const double d = x - m;
+          s[4] = fma(d, d, s[4]);
+        } else {
+          const double d = m - x;
+          s[0] = fma(d, d, s[0]);
+          s[1] = fma(x, x, s[1]);
+          if (a.impute) a.X[idx] = m;
+        }
+      }
+    }
+  }
+  const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const double v = block_sum(s[t], red);
+    if (tid == 0) a.partials[cta * 5 + t] = v;
+  }
+}
+
+__global__ void em_reduce_kernel(const double* __restrict__ partials, long long nctas, double* __restrict__ out) {
+  __shared__ double red[32];
+  for (int t = 0; t < 5; ++t) {
+    double v = 0.0;
+    for (long long c = threadIdx.x; c < nctas; c += blockDim.x) v += partials[c * 5 + t];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) out[t] = v;
+  }
+}
+
+void em_grid(const EmArgs& a, dim3& grid, int& kper) {
+  const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTile);
+  // enough CTAs for a few waves of 148 SMs, but several k per CTA so that the Fj tile is reused
+  long long kz = std::min<long long>(a.K, std::max<long long>(1, (148LL * 8) / std::max<long long>(ti * tj, 1)));
+  kz = std::min<long long>(kz, 65535);
+  kper = (int)ceil_div(a.K, kz);
+  kz = ceil_div(a.K, kper);
+  grid = dim3((unsigned)ti, (unsigned)tj, (unsigned)kz);
+}
+
+}  // namespace
+
+size_t em_partials_doubles(const EmArgs& a) {
+  dim3 g;
+  int kper;
+  em_grid(a, g, kper);
+  return (size_t)g.x * g.y * g.z * 5;
+}
+
+int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
+  if (a.I <= 0 || a.J <= 0 || a.K <= 0) return 0;
+  dim3 g;
+  int kper;
+  em_grid(a, g, kper);
+  if (g.y > 65535) throw CudaError(2, "EM imputation: object too wide");
+  em_kernel<<<g, 256, 0, st>>>(a, kper);
+  AO_CHECK_LAUNCH();
+  em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
+  AO_CHECK_LAUNCH();
+  return 2;
+}
+
+}  // namespace aoadmm

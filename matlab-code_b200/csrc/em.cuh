@@ -1,0 +1,28 @@
+// em.cuh - EM imputation pass (functions/cmtf_fun_AOADMM.m:408-441) + masked objective sums (:1224-1226, :1249-1252).
+#pragma once
+#include "common.cuh"
+
+namespace aoadmm {
+
+struct EmArgs {
+  double* X;               // object data, element (i,j,k) at i + ldI*(j + J*k); missing entries are overwritten
+  const uint8_t* mask;     // same indexing; 1 = observed, 0 = missing (Z.miss)
+  long long ldI;
+  long long I, J;
+  int K;
+  const double* Fi;        // I x R column-major
+  long long ldFi;
+  const double* Fj;        // J x R
+  long long ldFj;
+  const double* Fk;        // K x R, or nullptr (matrices / PARAFAC2: K = 1, no third factor)
+  long long ldFk;
+  int R;
+  int impute;              // 0: only the sums (iteration-0 objective)
+  double* partials;        // >= em_partials_doubles(args)
+};
+
+size_t em_partials_doubles(const EmArgs& a);
+// sums_out[0..4] = sum_missing (m-x)^2, sum_missing x^2, sum_observed x*m, sum_observed m^2, sum_observed (x-m)^2
+int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st);
+
+}  // namespace aoadmm

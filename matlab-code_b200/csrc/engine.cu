@@ -343,6 +343,17 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     if (src.data != nullptr && slab > 0)
       AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
                            cudaMemcpyHostToDevice));
+    if (src.miss != nullptr) {  // Z.miss{p} (cmtf_AOADMM.m:68-121)
+      if (o.order > 3) throw CudaError(2, "missing data is supported for matrices and 3-way tensors on device");
+      if (src.data == nullptr) throw CudaError(1, "Z.miss without data");
+      const size_t mbytes = std::max<size_t>((size_t)o.ld0 * slab, 256);
+      AO_CUDA(cudaMalloc(&o.mask, mbytes));
+      AO_CUDA(cudaMemset(o.mask, 0, mbytes));
+      if (slab > 0)
+        AO_CUDA(cudaMemcpy2D(o.mask, (size_t)o.ld0, src.miss, (size_t)o.dims[0], (size_t)o.dims[0], slab,
+                             cudaMemcpyHostToDevice));
+      has_missing_ = true;
+    }
     AO_CUDA(cudaDeviceSynchronize());  // pageable H2D copies return before the DMA has finished
   }
   for (auto& m : modes_) {
@@ -476,6 +487,31 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     }
   }
   build_objective_jobs();
+  if (has_missing_) {
+    AO_CUDA(cudaMalloc(&em_sums_, sizeof(double) * 5 * n_objects_));
+    AO_CUDA(cudaMemset(em_sums_, 0, sizeof(double) * 5 * n_objects_));
+    AO_CUDA(cudaMallocHost(&em_sums_host_, sizeof(double) * 5 * n_objects_));
+    size_t need = 0;
+    for (int p = 0; p < n_objects_; ++p) {
+      ObjectState& o = objects_[p];
+      EmArgs a{};
+      a.R = mode(o.modes[0]).R;
+      if (o.model == AOADMM_MODEL_PAR2) {
+        const Par2State& s = par2_[mode(o.modes[0]).par2];
+        if (s.mask == nullptr) continue;
+        a.I = s.I;
+        a.J = s.Jtot;
+        a.K = 1;
+      } else {
+        if (o.mask == nullptr) continue;
+        a.I = o.dims[0];
+        a.J = o.dims[1];
+        a.K = o.order >= 3 ? (int)o.dims[2] : 1;
+      }
+      need = std::max(need, em_partials_doubles(a));
+    }
+    AO_CUDA(cudaMalloc(&em_partials_, std::max<size_t>(need, 8) * sizeof(double)));
+  }
 
   if (world_ > 1) {
     nccl_ = load_nccl();
@@ -501,6 +537,7 @@ Engine::~Engine() {
   for (auto& o : objects_) {
     if (o.data) cudaFree(o.data);
     if (o.Tbuf) cudaFree(o.Tbuf);
+    if (o.mask) cudaFree(o.mask);
     for (auto& v : o.views) {
       if (v.f0_own) packed_factor_free(v.f0);
       if (v.f1_own) packed_factor_free(v.f1);
@@ -510,7 +547,7 @@ Engine::~Engine() {
   free_linear_coupling();
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
-    for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
+    for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.mask, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
                     (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.Vprev, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
                     (void*)s.res_partials})
       if (q) cudaFree(q);
@@ -523,6 +560,9 @@ Engine::~Engine() {
                   prox_scratch_, (void*)krtmp_[0], (void*)krtmp_[1], (void*)ctl_dev_, (void*)jobs_dev_,
                   (void*)red_dev_, (void*)red_partials_, (void*)cp0_tmp_})
     if (p) cudaFree(p);
+  if (em_sums_) cudaFree(em_sums_);
+  if (em_partials_) cudaFree(em_partials_);
+  if (em_sums_host_) cudaFreeHost(em_sums_host_);
   if (ctl_host_) cudaFreeHost(ctl_host_);
   if (red_host_) cudaFreeHost(red_host_);
   if (run_ev_[0]) cudaEventDestroy(run_ev_[0]);
@@ -772,6 +812,17 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
     AO_CUDA(cudaMemcpy2D(s.X + (size_t)s.joff[k] * s.ldX, (size_t)s.ldX * 8, src.slices[k], (size_t)s.I * 8,
                          (size_t)s.I * 8, (size_t)jk[k], cudaMemcpyHostToDevice));
     for (int64_t j = s.joff[k]; j < s.joff[k + 1]; ++j) seg[(size_t)j] = k;
+  }
+  if (src.miss_slices != nullptr) {
+    const size_t mbytes = std::max<size_t>((size_t)s.ldX * s.Jtot, 256);
+    AO_CUDA(cudaMalloc(&s.mask, mbytes));
+    AO_CUDA(cudaMemset(s.mask, 0, mbytes));
+    for (int k = 0; k < s.K; ++k) {
+      if (src.miss_slices[k] == nullptr) throw CudaError(1, "Z.miss{p}{k} must be given for every PARAFAC2 slice");
+      AO_CUDA(cudaMemcpy2D(s.mask + (size_t)s.joff[k] * s.ldX, (size_t)s.ldX, src.miss_slices[k], (size_t)s.I, (size_t)s.I,
+                           (size_t)jk[k], cudaMemcpyHostToDevice));
+    }
+    has_missing_ = true;
   }
   AO_CUDA(cudaMalloc(&s.joff_dev, sizeof(long long) * (s.K + 1)));
   {
@@ -1084,6 +1135,61 @@ void Engine::build_objective_jobs() {
   AO_CUDA(cudaMalloc(&red_partials_, sizeof(double) * reduce_ws_doubles((int)nj + 8)));
 }
 
+void Engine::em_step(bool impute) {
+  if (!has_missing_) return;
+  for (int p = 0; p < n_objects_; ++p) {
+    ObjectState& o = objects_[p];
+    EmArgs a{};
+    a.R = mode(o.modes[0]).R;
+    a.impute = impute ? 1 : 0;
+    a.partials = em_partials_;
+    if (o.model == AOADMM_MODEL_PAR2) {
+      Par2State& s = par2_[mode(o.modes[0]).par2];
+      if (s.mask == nullptr) continue;
+      ModeState &ma = mode(s.m1), &mb = mode(s.m2), &mc = mode(s.m3);
+      // model of slice k: A diag(c_k) B_k' (:426)  =  A * W' on the stacked layout, W(j,:) = B(j,:) .* C(seg(j),:)
+      launches_ += par2_scale_rows(s.lay, s.W.p, mb.fac.p, mc.fac.p, mc.rows, 1.0, nullptr, 0.0, st_);
+      a.X = s.X;
+      a.mask = s.mask;
+      a.ldI = s.ldX;
+      a.I = s.I;
+      a.J = s.Jtot;
+      a.K = 1;
+      a.Fi = ma.fac.p;
+      a.ldFi = ma.rows;
+      a.Fj = s.W.p;
+      a.ldFj = s.Jtot;
+      a.Fk = nullptr;
+      launches_ += em_pass(a, em_sums_ + 5 * p, st_);
+      if (impute) s.T_version = 0;
+    } else {
+      if (o.mask == nullptr) continue;
+      ModeState &m0 = mode(o.modes[0]), &m1 = mode(o.modes[1]);
+      a.X = o.data;
+      a.mask = o.mask;
+      a.ldI = o.ld0;
+      a.I = o.dims[0];
+      a.J = o.dims[1];
+      a.Fi = m0.fac.p;
+      a.ldFi = m0.rows;
+      a.Fj = m1.fac.p;
+      a.ldFj = m1.rows;
+      if (o.order >= 3) {
+        ModeState& m2 = mode(o.modes[2]);
+        a.K = (int)o.dims[2];
+        a.Fk = m2.fac.p + o.shard_offset;  // this rank's rows of the (possibly sharded) last mode
+        a.ldFk = m2.rows;
+      } else {
+        a.K = 1;
+        a.Fk = nullptr;
+      }
+      launches_ += em_pass(a, em_sums_ + 5 * p, st_);
+      if (o.sharded) allreduce(em_sums_ + 5 * p, 5);
+      if (impute) o.T_version = 0;
+    }
+  }
+}
+
 void Engine::eval_objective(bool first, double f[4]) {
   const int nj = (int)jobs_host_.size();
   std::vector<double> f_obj(n_objects_, 0.0);
@@ -1092,6 +1198,7 @@ void Engine::eval_objective(bool first, double f[4]) {
     for (int p = 0; p < n_objects_; ++p) {
       ObjectState& o = objects_[p];
       if (o.model == AOADMM_MODEL_PAR2) continue;  // explicit residual below (:1262-1264)
+      if (o.mask != nullptr) continue;             // masked objective from the EM sums (:1224-1226)
       ModeState& m0 = mode(o.modes[0]);
       double* M = cp0_tmp_;
       double* scr = cp0_tmp_ + (size_t)m0.rows * m0.R;  // C | B | L | invdiag | rho
@@ -1148,6 +1255,8 @@ void Engine::eval_objective(bool first, double f[4]) {
                                  mode(s.m3).rows, s.res_partials, admm_counter_, s.res, st_);
     AO_CUDA(cudaMemcpyAsync(s.segn_host, s.segn, sizeof(double) * (s.K * 4 + 1), cudaMemcpyDeviceToHost, st_));
   }
+  if (has_missing_)
+    AO_CUDA(cudaMemcpyAsync(em_sums_host_, em_sums_, sizeof(double) * 5 * n_objects_, cudaMemcpyDeviceToHost, st_));
   launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, red_partials_, admm_counter_, st_, nullptr);
   AO_CUDA(cudaMemcpyAsync(red_host_, red_dev_, sizeof(double) * nj, cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaMemcpyAsync(ctl_host_, ctl_dev_, sizeof(InnerCtl) * n_ctl_, cudaMemcpyDeviceToHost, st_));
@@ -1171,9 +1280,23 @@ void Engine::eval_objective(bool first, double f[4]) {
       st2[q].n2 += h[0];                     // :1293-1295
     }
   }
+  if (has_missing_) {  // :436-440
+    double num = 0.0, den = 0.0;
+    for (int p = 0; p < n_objects_; ++p) {
+      num += em_sums_host_[5 * p + 0];
+      den += em_sums_host_[5 * p + 1];
+    }
+    f_rel_missing_ = (den > 0.0) ? std::sqrt(num / den) : std::sqrt(num);
+  }
   for (int p = 0; p < n_objects_; ++p) {
     ObjectState& o = objects_[p];
-    if (o.model == AOADMM_MODEL_PAR2 && (first || terms_->obj[p].idx_dot < 0)) {
+    const bool masked = has_missing_ && ((o.model == AOADMM_MODEL_PAR2) ? par2_[mode(o.modes[0]).par2].mask != nullptr
+                                                                        : o.mask != nullptr);
+    if (masked) {
+      const double* e = em_sums_host_ + 5 * p;
+      f_obj[p] = (o.model == AOADMM_MODEL_PAR2) ? o.weight * e[4]                               // :1249-1252, :1267
+                                                : o.weight * (o.znorm - 2.0 * e[2] + e[3]);     // :1224-1226
+    } else if (o.model == AOADMM_MODEL_PAR2 && (first || terms_->obj[p].idx_dot < 0)) {
       const Par2State& s = par2_[mode(o.modes[0]).par2];
       f_obj[p] = o.weight * s.segn_host[(size_t)s.K * 4];   // :1262-1267
     } else if (!first) {
@@ -1411,7 +1534,10 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
     s.T_version = 0;
   }
   double f[4];
+  em_step(false);                           // masked iteration-0 objective needs the model at the observed entries
   eval_objective(true, f);                  // :32
+  f_rel_missing_ = std::nan("");
+  if (out->func_rel_missing) out->func_rel_missing[0] = f_rel_missing_;
   if (out->func_val_conv) out->func_val_conv[0] = f[0];
   if (out->func_coupl_conv) out->func_coupl_conv[0] = f[1];
   if (out->func_constr_conv) out->func_constr_conv[0] = f[2];
@@ -1501,6 +1627,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
       }
     }
     const double f_old[4] = {f[0], f[1], f[2], f[3]};
+    em_step(true);                                                   // :408-441
     eval_objective(false, f);                                        // :447 (synchronises)
     check_errors(out);
     if (out->func_val_conv) out->func_val_conv[iter] = f[0];
@@ -1508,6 +1635,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
     if (out->func_constr_conv) out->func_constr_conv[iter] = f[2];
     if (out->func_PAR2_coupl) out->func_PAR2_coupl[iter] = f[3];
     if (out->time_at_it) out->time_at_it[iter] = now_s() - t_start;
+    if (out->func_rel_missing) out->func_rel_missing[iter] = f_rel_missing_;
     if (out->inner_iters)
       for (int i = 0; i < nb_modes_; ++i)
         out->inner_iters[(size_t)(iter - 1) * nb_modes_ + i] =
@@ -1516,6 +1644,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
            stop_one(f[1], f_old[1], opt_.AbsFuncTol, opt_.OuterRelTol) &&
            stop_one(f[2], f_old[2], opt_.AbsFuncTol, opt_.OuterRelTol) &&
            stop_one(f[3], f_old[3], opt_.AbsFuncTol, opt_.OuterRelTol);   // evaluate_stopping_conditions.m:44
+    if (has_missing_) stop = stop && (f_rel_missing_ < opt_.OuterRelTol);  // :457-459
     ++iter;
   }
   AO_CUDA(cudaEventRecord(run_ev_[1], st_));
@@ -1531,6 +1660,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
   out->f_couplings = f[1];
   out->f_constraints = f[2];
   out->f_PAR2_couplings = f[3];
+  out->f_rel_missing = has_missing_ ? f_rel_missing_ : std::nan("");
   out->OuterIterations = iter - 1;
   if (iter > opt_.MaxOuterIters) {                                   // make_exit_flag.m:4-5
     out->exit_flag = 0;

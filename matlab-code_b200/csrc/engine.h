@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/aoadmm.h"
+#include "em.cuh"
 #include "linalg.cuh"
 #include "mttkrp.cuh"
 #include "par2.cuh"
@@ -91,6 +92,7 @@ struct Par2State {
   long long* joff_dev = nullptr;
   int* seg_dev = nullptr;
   double* X = nullptr;                   // I x Jtot (leading dimension ldX)
+  uint8_t* mask = nullptr;               // Z.miss{p}{k} side by side like X (nullptr: complete data)
   Tensor3 view;                          // X as an I x Jtot x 1 tensor for the DMMA product kernels
   PackedFactor fW, fA, ones;
   DevMat W, T;                           // Jtot x R: scaled operand of the mode-A product; T = Xall' * A
@@ -125,6 +127,7 @@ struct ObjectState {
   bool sharded = false;
   std::vector<View3> views;   // one per mode position
   int last_m = 0;             // global id of the mode updated last in a sweep (static)
+  uint8_t* mask = nullptr;    // Z.miss{p}: 1 = observed, 0 = missing, same indexing as data (nullptr: complete data)
   double* Tbuf = nullptr;     // dimension tree: T(j,k,r) = sum_i X(i,j,k) F1(i,r), emitted by the mode-2 MTTKRP
   uint64_t T_version = 0;     // version of the mode-1 factor T was computed from (0 = invalid)
 };
@@ -164,6 +167,8 @@ class Engine {
   void eval_objective(bool first, double f[4]);
   void check_errors(aoadmm_out* out);
   void allreduce(double* buf, size_t count);
+  // EM imputation of missing entries + masked objective sums (cmtf_fun_AOADMM.m:408-441, :1224-1226, :1249-1252)
+  void em_step(bool impute);
   // linear couplings (cmtf_fun_AOADMM.m:278-389, :698-1075)
   void setup_linear_coupling(const aoadmm_problem* prob, int coupl_id);
   void lin_G(const LinMode& lm, const ModeState& m, const double* F, double* out, const int* skip);
@@ -223,6 +228,11 @@ class Engine {
   struct ObjTerms;
   std::unique_ptr<ObjTerms> terms_;
   double* cp0_tmp_ = nullptr;     // iteration-0 MTTKRP / Hadamard scratch
+  bool has_missing_ = false;      // any object with a Z.miss mask
+  double* em_sums_ = nullptr;     // device, 5 per object (see em.cuh)
+  double* em_sums_host_ = nullptr;  // pinned
+  double* em_partials_ = nullptr;
+  double f_rel_missing_ = 0.0;
   int64_t launches_ = 0;
   // timing
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool_;

@@ -59,6 +59,33 @@ const mxArray* dense_data(const mxArray* obj) {
   return obj;
 }
 
+// Z.miss{p} (cmtf_AOADMM.m:68-121): logical / numeric array, Tensor Toolbox tensor, or sptensor (converted with
+// full()) -> one byte per element, 1 = observed
+std::vector<uint8_t> mask_bytes(const mxArray* m, size_t expected, int p) {
+  mxArray* conv = nullptr;
+  if (std::strcmp(mxGetClassName(m), "sptensor") == 0) {
+    mxArray* in = const_cast<mxArray*>(m);
+    if (mexCallMATLAB(1, &conv, 1, &in, "full") != 0 || conv == nullptr)
+      fail("cmtf:missingData:maskTypeError", "Z.miss{" + std::to_string(p + 1) + "} cannot be converted with full()");
+    m = conv;
+  }
+  if (std::strcmp(mxGetClassName(m), "tensor") == 0) m = mxGetProperty(m, 0, "data");
+  if (m == nullptr || mxGetNumberOfElements(m) != expected)
+    fail("cmtf:missingData:maskSizeMismatch", "Z.miss{" + std::to_string(p + 1) + "} size does not match Z.object{" + std::to_string(p + 1) + "}.");
+  std::vector<uint8_t> out(expected);
+  if (mxIsLogical(m)) {
+    const mxLogical* v = mxGetLogicals(m);
+    for (size_t i = 0; i < expected; ++i) out[i] = v[i] ? 1 : 0;
+  } else if (mxIsDouble(m)) {
+    const double* v = mxGetPr(m);
+    for (size_t i = 0; i < expected; ++i) out[i] = (v[i] != 0.0) ? 1 : 0;
+  } else {
+    fail("cmtf:missingData:maskTypeError", "Z.miss{" + std::to_string(p + 1) + "} must be logical, double, tensor or sptensor");
+  }
+  if (conv != nullptr) mxDestroyArray(conv);
+  return out;
+}
+
 int constraint_kind(const std::string& n) {  // constraints_to_prox.m:13-91
   static const struct { const char* name; int kind; } table[] = {
       {"non-negativity", AOADMM_CON_NONNEG}, {"box", AOADMM_CON_BOX}, {"simplex column-wise", AOADMM_CON_SIMPLEX_COL},
@@ -117,11 +144,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const mxArray* coupling = field(Z, "coupling");
   const int P = (int)mxGetNumberOfElements(objects);
   const int nb_modes = (int)mxGetNumberOfElements(size_c);
-  if (const mxArray* miss = field(Z, "miss", false)) {
-    for (mwIndex i = 0; i < mxGetNumberOfElements(miss); ++i)
-      if (mxIsCell(miss) && mxGetCell(miss, i) != nullptr && !mxIsEmpty(mxGetCell(miss, i)))
-        fail("aoadmm:unsupported", "missing data (Z.miss) is not supported by the B200 engine");
-  }
+  const mxArray* miss = field(Z, "miss", false);
+  std::vector<std::vector<uint8_t>> miss_cp(P);
+  std::vector<std::vector<std::vector<uint8_t>>> miss_par2(P);
+  std::vector<std::vector<const uint8_t*>> miss_par2_ptr(P);
   for (int p = 0; p < P; ++p)
     if (string_of(mxGetCell(loss_c, p)) != "Frobenius")
       fail("aoadmm:unsupported", "only the Frobenius loss runs on the B200 engine");
@@ -178,6 +204,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       o.data = mxGetPr(dense_data(obj));
       o.shard_offset = 0;
       o.shard_extent = mode_rows[obj_modes[p][order - 1] - 1];
+    }
+    const mxArray* mp = (miss != nullptr && mxIsCell(miss) && p < (int)mxGetNumberOfElements(miss)) ? mxGetCell(miss, p) : nullptr;
+    if (mp != nullptr && !mxIsEmpty(mp)) {  // EM imputation of the entries with Z.miss == 0 (cmtf_fun_AOADMM.m:408-441)
+      if (par2) {
+        const int K = o.n_slices;
+        if (!mxIsCell(mp) || (int)mxGetNumberOfElements(mp) != K)
+          fail("cmtf:missingData:PAR2maskNotCell", "Z.miss{p} must be a cell array with one mask per PARAFAC2 slice");
+        miss_par2[p].resize(K);
+        miss_par2_ptr[p].resize(K);
+        for (int k = 0; k < K; ++k) {
+          miss_par2[p][k] = mask_bytes(mxGetCell(mp, k), mxGetNumberOfElements(dense_data(mxGetCell(obj, k))), p);
+          miss_par2_ptr[p][k] = miss_par2[p][k].data();
+        }
+        o.miss_slices = miss_par2_ptr[p].data();
+      } else {
+        miss_cp[p] = mask_bytes(mp, mxGetNumberOfElements(dense_data(obj)), p);
+        o.miss = miss_cp[p].data();
+      }
     }
   }
 
@@ -324,7 +368,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   o.dimtree = (int32_t)opt_scalar(opt, "b200_dimtree", 1.0);  // engine knob, results equal to rounding
 
   const int n_hist = o.MaxOuterIters + 1;
-  mxArray* hist[5];
+  mxArray* hist[6];
   for (auto& a : hist) a = mxCreateDoubleMatrix(1, n_hist, mxREAL);
   std::vector<int32_t> inner((size_t)nb_modes * (o.MaxOuterIters > 0 ? o.MaxOuterIters : 1), 0);
   aoadmm_out ro;
@@ -334,6 +378,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   ro.func_constr_conv = mxGetPr(hist[2]);
   ro.func_PAR2_coupl = mxGetPr(hist[3]);
   ro.time_at_it = mxGetPr(hist[4]);
+  ro.func_rel_missing = mxGetPr(hist[5]);
   ro.inner_iters = inner.data();
   check(aoadmm_run(h, &o, &ro), h);
 
@@ -375,13 +420,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nlhs > 1) {
     const char* names[] = {"f_tensors", "f_couplings", "f_constraints", "f_PAR2_couplings", "f_rel_missing", "exit_flag",
                            "OuterIterations", "func_val_conv", "func_coupl_conv", "func_constr_conv", "func_PAR2_coupl",
-                           "time_at_it", "innerIters"};
-    mxArray* out = mxCreateStructMatrix(1, 1, 13, names);
+                           "time_at_it", "innerIters", "func_rel_missing"};
+    mxArray* out = mxCreateStructMatrix(1, 1, 14, names);
     mxSetField(out, 0, "f_tensors", mxCreateDoubleScalar(ro.f_tensors));
     mxSetField(out, 0, "f_couplings", mxCreateDoubleScalar(ro.f_couplings));
     mxSetField(out, 0, "f_constraints", mxCreateDoubleScalar(ro.f_constraints));
     mxSetField(out, 0, "f_PAR2_couplings", mxCreateDoubleScalar(ro.f_PAR2_couplings));
-    mxSetField(out, 0, "f_rel_missing", mxCreateDoubleScalar(mxGetNaN()));
+    mxSetField(out, 0, "f_rel_missing", mxCreateDoubleScalar(ro.f_rel_missing));
     if (ro.exit_flag == 0) {  // make_exit_flag.m:4-5
       mxSetField(out, 0, "exit_flag", mxCreateString("maxIterations"));
     } else {                   // make_exit_flag.m:9-28
@@ -392,8 +437,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     }
     const int it = ro.OuterIterations;
     mxSetField(out, 0, "OuterIterations", mxCreateDoubleScalar((double)it));
-    const char* hn[] = {"func_val_conv", "func_coupl_conv", "func_constr_conv", "func_PAR2_coupl", "time_at_it"};
-    for (int q = 0; q < 5; ++q) {
+    const char* hn[] = {"func_val_conv", "func_coupl_conv", "func_constr_conv", "func_PAR2_coupl", "time_at_it",
+                        "func_rel_missing"};
+    for (int q = 0; q < 6; ++q) {
       mxSetN(hist[q], it + 1);  // histories hold it+1 entries (:450-455)
       mxSetField(out, 0, hn[q], hist[q]);
     }

@@ -3,8 +3,9 @@
 Line-by-line NumPy float64 restatement of the Frobenius / dense paths of
 functions/cmtf_fun_AOADMM.m (whole file), functions/evaluate_stopping_conditions.m,
 functions/make_exit_flag.m, functions/cp_func.m and functions/pca_func.m.
-Non-Frobenius (L-BFGS-B) branches (:128-130, :136, :612-613, :1365-1418) and EM
-imputation (:408-441) are out of scope (component 1) and raise.
+Non-Frobenius (L-BFGS-B) branches (:128-130, :136, :612-613, :1365-1418) are out of scope
+(component 1) and raise.  EM imputation of missing entries (Z.miss,
+:408-441, masked objective :1224-1226 / :1249-1252) is restated.
 
 Conventions (mirroring the MATLAB structs, 1-based labels kept where they are DATA):
   Z : dict with
@@ -119,8 +120,16 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
     for p in range(P):
         if Z['loss_function'][p] != 'Frobenius':
             raise NotImplementedError('oracle covers the Frobenius loss only (SURVEY.md section 2)')
-    if Z.get('miss') is not None and any(x is not None for x in Z['miss']):
-        raise NotImplementedError('EM imputation is out of scope for the oracle')
+    miss = Z.get('miss')
+    has_missing = miss is not None and any(x is not None for x in miss)                # :29
+    if has_missing:
+        # Z.object is modified in place by the imputation (:420, :432): work on a copy
+        Z = dict(Z)
+        Z['object'] = [([np.array(xk, copy=True) for xk in X] if isinstance(X, list) else
+                        (np.array(X, copy=True) if X is not None else None)) for X in Z['object']]
+        miss = [([np.asarray(mk, dtype=bool) for mk in M] if isinstance(M, list) else
+                 (np.asarray(M, dtype=bool) if M is not None else None)) for M in miss]
+    state_missing = {'f_rel_missing': float('nan')}
     if 'prox_operators' not in Z or Z['prox_operators'] is None:
         prox_ops, reg_func = constraints_to_prox(Z['constrained_modes'], Z['constraints'], Z['size'])
     else:
@@ -464,7 +473,17 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
         fp = np.zeros(P)
         for pp in range(P):
             U = [G['fac'][mm - 1] for mm in modes[pp]]
-            if Z['model'][pp] == 'CP':
+            if has_missing and miss[pp] is not None and Z['model'][pp] == 'CP':                # :1224-1226
+                from .tensor_ops import full_ktensor
+                Mm = miss[pp] * full_ktensor(U)
+                fp[pp] = weights[pp] * (Znorm_const[pp] - 2 * np.sum(Z['object'][pp] * Mm) + np.sum(Mm ** 2))
+            elif has_missing and miss[pp] is not None:                                           # :1249-1252
+                m1, m2, m3 = modes[pp]
+                for kk in range(K_of(pp)):
+                    Rk = Z['object'][pp][kk] - fac(m1) @ np.diag(fac(m3)[kk, :]) @ fac(m2)[kk].T
+                    fp[pp] += _fro(miss[pp][kk] * Rk) ** 2
+                fp[pp] = weights[pp] * fp[pp]
+            elif Z['model'][pp] == 'CP':
                 if first:
                     if Z['object'][pp].ndim >= 3:
                         fp[pp] = cp_func(Z['object'][pp], U, Znorm_const[pp], weights[pp])
@@ -559,6 +578,7 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
     func_coupl = [f_couplings]
     func_constr = [f_constraints]
     func_PAR2_coupl = [f_PAR2]
+    func_rel_missing = [float('nan')]                                                  # :38-40
     tstart = time.perf_counter()
     time_at_it = [0.0]
 
@@ -761,6 +781,32 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
                     if not is_par2_mode(m, 3):
                         GtG[m] = fac(m).T @ fac(m)
 
+        if has_missing:                                                                  # :408-441 EM imputation
+            from .tensor_ops import full_ktensor
+            num_sq = 0.0
+            den_sq = 0.0
+            for p in range(P):
+                if miss[p] is None:
+                    continue
+                if Z['model'][p] == 'CP':
+                    M_full = full_ktensor([G['fac'][j - 1] for j in modes[p]])
+                    mm = ~miss[p]
+                    old_vals = Z['object'][p][mm]
+                    new_vals = M_full[mm]
+                    Z['object'][p][mm] = new_vals
+                    num_sq += float(np.sum((new_vals - old_vals) ** 2))
+                    den_sq += float(np.sum(old_vals ** 2))
+                else:
+                    m1, m2, m3 = modes[p]
+                    for k in range(K_of(p)):
+                        M_k = fac(m1) @ np.diag(fac(m3)[k, :]) @ fac(m2)[k].T
+                        mk = ~miss[p][k]
+                        old_k = Z['object'][p][k][mk]
+                        new_k = M_k[mk]
+                        num_sq += float(np.sum((new_k - old_k) ** 2))
+                        den_sq += float(np.sum(old_k ** 2))
+                        Z['object'][p][k][mk] = new_k
+            state_missing['f_rel_missing'] = np.sqrt(num_sq / den_sq) if den_sq > 0 else np.sqrt(num_sq)
         f_tensors_old, f_couplings_old, f_constraints_old, f_PAR2_old = f_tensors, f_couplings, f_constraints, f_PAR2
         f_tensors, f_couplings, f_constraints, f_PAR2 = func_eval(False)
         func_val.append(f_tensors)
@@ -770,11 +816,15 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
         time_at_it.append(time.perf_counter() - tstart)
         stop = evaluate_stopping_conditions(f_tensors, f_couplings, f_constraints, f_PAR2,
                                             f_tensors_old, f_couplings_old, f_constraints_old, f_PAR2_old, options)
+        func_rel_missing.append(state_missing['f_rel_missing'])                          # :454
+        if has_missing:
+            stop = stop and (state_missing['f_rel_missing'] < options['OuterRelTol'])    # :457-459
         it += 1
 
     out = {
         'f_tensors': f_tensors, 'f_couplings': f_couplings, 'f_constraints': f_constraints,
-        'f_PAR2_couplings': f_PAR2, 'f_rel_missing': float('nan'),
+        'f_PAR2_couplings': f_PAR2, 'f_rel_missing': float(state_missing['f_rel_missing']),
+        'func_rel_missing': np.array(func_rel_missing),
         'exit_flag': make_exit_flag(it, f_tensors, f_couplings, f_constraints, f_PAR2, options, 0),
         'OuterIterations': it - 1,
         'func_val_conv': np.array(func_val), 'func_coupl_conv': np.array(func_coupl),

@@ -126,14 +126,48 @@ def normalize_objects(X, model):
 
 
 def znorm_const(Z):
-    """cmtf_AOADMM.m:124-156 (Frobenius, no missing data)."""
+    """cmtf_AOADMM.m:124-156 (Frobenius; with Z.miss the norm of the observed entries, :134-151)."""
     out = []
+    miss = Z.get('miss') or [None] * len(Z['object'])
     for p, Xp in enumerate(Z['object']):
+        Mp = miss[p]
         if Z['model'][p] == 'CP':
-            out.append(float(np.sqrt(np.sum(Xp ** 2)) ** 2))
+            Xe = Xp if Mp is None else np.asarray(Mp, dtype=np.float64) * Xp
+            out.append(float(np.sqrt(np.sum(Xe ** 2)) ** 2))
         else:
-            out.append(float(sum(np.sqrt(np.sum(Xk ** 2)) ** 2 for Xk in Xp)))
+            out.append(float(sum(np.sqrt(np.sum((Xk if Mp is None else np.asarray(Mp[k], dtype=np.float64) * Xk) ** 2)) ** 2
+                                 for k, Xk in enumerate(Xp))))
     return out
+
+
+def add_missing(Z, frac=0.2, seed=0, objects=None):
+    """example_script12_CP_PAR2_EM.m:115-146: ~frac of the entries of the chosen objects missing at random
+    (mask true = observed), missing entries initialised with 0."""
+    rng = np.random.RandomState(seed)
+    Z = dict(Z)
+    Z['object'] = list(Z['object'])
+    miss = [None] * len(Z['object'])
+    for p, Xp in enumerate(Z['object']):
+        if objects is not None and p not in objects:
+            continue
+        if Z['model'][p] == 'CP':
+            mask = np.ones(Xp.size, dtype=bool)
+            mask[rng.permutation(Xp.size)[:int(round(frac * Xp.size))]] = False
+            mask = np.asfortranarray(mask.reshape(Xp.shape, order='F'))
+            miss[p] = mask
+            Z['object'][p] = np.asfortranarray(np.where(mask, Xp, 0.0))
+        else:
+            mk, xs = [], []
+            for Xk in Xp:
+                m = np.ones(Xk.size, dtype=bool)
+                m[rng.permutation(Xk.size)[:int(round(frac * Xk.size))]] = False
+                m = np.asfortranarray(m.reshape(Xk.shape, order='F'))
+                mk.append(m)
+                xs.append(np.asfortranarray(np.where(m, Xk, 0.0)))
+            miss[p] = mk
+            Z['object'][p] = xs
+    Z['miss'] = miss
+    return Z
 
 
 def init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=None):

@@ -21,6 +21,9 @@ bool mxIsSparse(const mxArray*);
 bool mxIsEmpty(const mxArray*);
 bool mxIsLogical(const mxArray*);
 bool mxIsLogicalScalarTrue(const mxArray*);
+typedef bool mxLogical;
+mxLogical* mxGetLogicals(const mxArray*);
+int mexCallMATLAB(int nlhs, mxArray* plhs[], int nrhs, mxArray* prhs[], const char* name);
 size_t mxGetNumberOfElements(const mxArray*);
 size_t mxGetM(const mxArray*);
 size_t mxGetN(const mxArray*);

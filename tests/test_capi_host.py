@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(ab):
     for n in names:
         assert hasattr(ab._capi.lib, n), n
     assert sorted(ab._capi.EXPORTS) == names
-    assert ab._capi.lib.aoadmm_abi_version() == 1
+    assert ab._capi.lib.aoadmm_abi_version() == 2
 
 
 def test_struct_layouts_match_header(ab, tmp_path):
@@ -107,7 +107,7 @@ def test_unsupported_inputs_raise_before_touching_the_device(ab):
     with pytest.raises(ab.AoadmmError) as e:
         ab.cmtf_fun_AOADMM(Zk, pg.znorm_const(Z), G, None, None, None, None, pg.default_options())
     assert e.value.status_name == 'UNSUPPORTED'
-    Zm = dict(Z, miss=[np.ones_like(Z['object'][0]), None, None])
+    Zm = dict(Z, miss=[np.ones((3, 3, 3)), None, None])       # cmtf:missingData:maskSizeMismatch (cmtf_AOADMM.m:85-88)
     with pytest.raises(ab.AoadmmError):
         ab.cmtf_fun_AOADMM(Zm, pg.znorm_const(Z), G, None, None, None, None, pg.default_options())
 

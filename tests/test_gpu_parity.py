@@ -380,6 +380,51 @@ def test_linear_couplings_two_tensors_zero_tolerances(ab, ctype):
     assert_state_close(Gd, Go)
 
 
+def _assert_missing_close(od, oo):
+    n = oo['OuterIterations'] + 1
+    a, b = od['func_rel_missing'][1:n], oo['func_rel_missing'][1:n]
+    assert np.isnan(od['func_rel_missing'][0]) and np.max(np.abs(a - b)) < FIT_TOL
+    assert abs(od['f_rel_missing'] - oo['f_rel_missing']) < FIT_TOL
+
+
+@pytest.mark.parametrize('frac', [0.2, 0.6])
+def test_em_imputation_cp_and_matrix(ab, frac):
+    """Z.miss on a CP tensor and on its coupled matrix: EM imputation after every sweep (cmtf_fun_AOADMM.m:408-441),
+    masked objective (:1224-1226), extra stopping condition (:457-459)."""
+    Z, G, _ = pg.config_cp_matrix(45, 38, 33, 70, 4, seed=6, noise=0.1)
+    Zm = pg.add_missing(Z, frac, seed=2)
+    Go, oo, Gd, od = _both(ab, Zm, G, pg.default_options(MaxOuterIters=30))
+    _assert_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go)
+    Zm1 = pg.add_missing(Z, frac, seed=3, objects=[0])      # only the tensor has a mask
+    Go, oo, Gd, od = _both(ab, Zm1, G, pg.default_options(MaxOuterIters=15, **ZERO_TOL))
+    _assert_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_em_imputation_cp_coupled_with_parafac2(ab):
+    """example_script12_CP_PAR2_EM.m: ~20 % missing in the CP block and in every PARAFAC2 slice (:1249-1252)."""
+    Z, G, _ = pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=4, noise=0.05)
+    Zm = pg.add_missing(Z, 0.2, seed=5)
+    Go, oo, Gd, od = _both(ab, Zm, G, pg.default_options(MaxOuterIters=25))
+    _assert_par2_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+def test_em_imputation_large_ranks_and_front_end(ab):
+    Z, G, _ = pg.config_cp_matrix(70, 66, 40, 90, 40, seed=7, noise=0.1)     # R > one rank chunk of the EM kernel
+    Zm = pg.add_missing(Z, 0.3, seed=1)
+    Go, oo, Gd, od = _both(ab, Zm, G, pg.default_options(MaxOuterIters=8, **ZERO_TOL))
+    _assert_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go)
+    Zhat, Fac, _, out = ab.cmtf_AOADMM(Zm, init=G, alg_options=pg.default_options(MaxOuterIters=8, **ZERO_TOL))
+    assert abs(out['f_tensors'] - oo['f_tensors']) < FIT_TOL       # the front end computes the masked Znorm_const
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)

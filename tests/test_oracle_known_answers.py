@@ -205,3 +205,19 @@ def test_linear_coupling_oracle_satisfies_the_coupling_constraint(ctype):
         lhs = {1: lambda: H[m - 1] @ F, 2: lambda: F @ H[m - 1], 3: lambda: F, 4: lambda: F, 5: lambda: H[m - 1] @ F}[ctype]()
         rhs = {1: lambda: D, 2: lambda: D, 3: lambda: H[m - 1] @ D, 4: lambda: D @ H[m - 1], 5: lambda: D @ H2[m - 1]}[ctype]()
         assert np.linalg.norm(lhs - rhs) / np.linalg.norm(lhs) < 5e-3
+
+
+def test_em_imputation_oracle_recovers_missing_entries():
+    """Known answer for the EM restatement (cmtf_fun_AOADMM.m:408-441): with 20 % of a low-noise CP tensor hidden, the
+    model fitted on the observed entries predicts the hidden ones, and f_rel_missing decreases towards 0."""
+    Z, G, _ = pg.config_cp_matrix(30, 26, 22, 40, 3, seed=4, noise=0.02)
+    Zm = pg.add_missing(Z, 0.2, seed=1, objects=[0])
+    Go, oo = cmtf_fun_AOADMM(Zm, pg.znorm_const(Zm), G, options=pg.default_options(MaxOuterIters=150))
+    hidden = ~Zm['miss'][0]
+    Xhat = full_ktensor([Go['fac'][m] for m in range(3)])
+    assert np.corrcoef(Z['object'][0][hidden], Xhat[hidden])[0, 1] > 0.99
+    assert np.isnan(oo['func_rel_missing'][0]) and oo['func_rel_missing'][1] > 10 * oo['f_rel_missing']
+    assert oo['f_rel_missing'] < 1e-2
+    # without a mask the same call reports NaN (cmtf_fun_AOADMM.m:30)
+    _, o2 = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=pg.default_options(MaxOuterIters=3))
+    assert np.isnan(o2['f_rel_missing'])

@@ -33,6 +33,8 @@ for dims in [(64, 48, 40, 80, 8), (130, 90, 37, 100, 32), (40, 36, 30, 64, 64)]:
 # PARAFAC2 objects (replicated) next to a sharded CP tensor, and a linear coupling (type 4, type 1)
 extra = [('cp+par2', pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=3, noise=0.1)[:2]),
          ('lin4', pg.config_linear_coupling(4, seed=4)[:2]), ('lin1', pg.config_linear_coupling(1, seed=1, second='tensor')[:2])]
+Zc, Gc, _ = pg.config_cp_matrix(40, 36, 30, 64, 5, seed=8)
+extra.append(('em', (pg.add_missing(Zc, 0.25, seed=3), Gc)))       # masks are sharded with the tensor
 for name, (Z, G) in extra:
     opts = pg.default_options(MaxOuterIters=15)
     zn = pg.znorm_const(Z)
