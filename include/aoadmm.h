@@ -86,7 +86,8 @@ typedef struct {
   int32_t order;          /* number of modes of this object: 2 (matrix), >=3 (tensor); PAR2: 3 */
   const int32_t *modes;   /* `order` global 1-based mode ids (Z.modes{p}) */
   double weight;          /* Z.weights(p) */
-  double znorm_const;     /* Znorm_const{p} = ||X_p||_F^2 */
+  double znorm_const;     /* Znorm_const{p} = ||X_p||_F^2 (observed entries only with Z.miss); NaN = compute it on
+                             the device from the data (cmtf_AOADMM.m:124-156) */
   /* CP: dense column-major data of THIS RANK's slab: extents size(modes[0..order-2]) x shard_extent.
    * With one GPU shard_offset = 0 and shard_extent = size of the last mode. */
   const double *data;

@@ -114,6 +114,40 @@ __global__ void em_reduce_kernel(const double* __restrict__ partials, long long 
   }
 }
 
+// sum of squares of the (observed) elements of an object stored with leading dimension ld: Znorm_const of
+// cmtf_AOADMM.m:124-156 (with Z.miss: norm(miss.*X)^2)
+__global__ void __launch_bounds__(256) norm2_masked_kernel(const double* __restrict__ X, const uint8_t* __restrict__ mask,
+                                                            long long I, long long ld, long long slab,
+                                                            double* __restrict__ partials) {
+  __shared__ double red[32];
+  const long long n = I * slab;
+  double a0 = 0.0, a1 = 0.0;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; idx + stride < n; idx += 2 * stride) {
+    const long long i0 = idx % I + ld * (idx / I), i1 = (idx + stride) % I + ld * ((idx + stride) / I);
+    const double v0 = (mask == nullptr || mask[i0] != 0) ? X[i0] : 0.0;
+    const double v1 = (mask == nullptr || mask[i1] != 0) ? X[i1] : 0.0;
+    a0 = fma(v0, v0, a0);
+    a1 = fma(v1, v1, a1);
+  }
+  if (idx < n) {
+    const long long i0 = idx % I + ld * (idx / I);
+    const double v0 = (mask == nullptr || mask[i0] != 0) ? X[i0] : 0.0;
+    a0 = fma(v0, v0, a0);
+  }
+  const double v = block_sum(a0 + a1, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double v = 0.0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) v += partials[c];
+  v = block_sum(v, red);
+  if (threadIdx.x == 0) *out = v;
+}
+
 void em_grid(const EmArgs& a, dim3& grid, int& kper) {
   const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTile);
   // enough CTAs for a few waves of 148 SMs, but several k per CTA so that the Fj tile is reused
@@ -142,6 +176,16 @@ int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
   em_kernel<<<g, 256, 0, st>>>(a, kper);
   AO_CHECK_LAUNCH();
   em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
+  AO_CHECK_LAUNCH();
+  return 2;
+}
+
+int object_norm2(const double* X, const uint8_t* mask, long long I, long long ld, long long slab, double* partials,
+                 double* out, cudaStream_t st) {
+  const int ctas = 148 * 8;
+  norm2_masked_kernel<<<ctas, 256, 0, st>>>(X, mask, I, ld, slab, partials);
+  AO_CHECK_LAUNCH();
+  sum_partials_kernel<<<1, 256, 0, st>>>(partials, ctas, out);
   AO_CHECK_LAUNCH();
   return 2;
 }

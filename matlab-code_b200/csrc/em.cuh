@@ -25,4 +25,9 @@ size_t em_partials_doubles(const EmArgs& a);
 // sums_out[0..4] = sum_missing (m-x)^2, sum_missing x^2, sum_observed x*m, sum_observed m^2, sum_observed (x-m)^2
 int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st);
 
+// *out = sum of squares of the elements (i < I of every column of length ld, `slab` columns) with mask != 0
+// (mask == nullptr: all);  partials: >= 148*8 doubles.  Znorm_const of cmtf_AOADMM.m:124-156 on device.
+int object_norm2(const double* X, const uint8_t* mask, long long I, long long ld, long long slab, double* partials,
+                 double* out, cudaStream_t st);
+
 }  // namespace aoadmm

@@ -470,7 +470,26 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     AO_CUDA(cudaMalloc(&krtmp_[0], kr_doubles * sizeof(double)));
     AO_CUDA(cudaMalloc(&krtmp_[1], kr_doubles * sizeof(double)));
   }
-  AO_CUDA(cudaMalloc(&cp0_tmp_, (cp0 + 4 * 256 * 256 + 512) * sizeof(double)));
+  AO_CUDA(cudaMalloc(&cp0_tmp_, (cp0 + 4 * 256 * 256 + 512 + 148 * 8 + 8) * sizeof(double)));
+  // Znorm_const on device where the caller passed NaN (cmtf_AOADMM.m:124-156)
+  for (int p = 0; p < n_objects_; ++p) {
+    ObjectState& o = objects_[p];
+    if (!std::isnan(o.znorm)) continue;
+    double* part = cp0_tmp_;
+    double* res = cp0_tmp_ + 148 * 8;
+    if (o.model == AOADMM_MODEL_PAR2) {
+      Par2State& s = par2_[mode(o.modes[0]).par2];
+      launches_ += object_norm2(s.X, s.mask, s.I, s.ldX, s.Jtot, part, res, st_);
+    } else {
+      size_t slab = 1;
+      for (int d = 1; d < o.order; ++d) slab *= (size_t)o.dims[d];
+      if (o.data == nullptr) throw CudaError(1, "Znorm_const = NaN needs the object data");
+      launches_ += object_norm2(o.data, o.mask, o.dims[0], o.ld0, (long long)slab, part, res, st_);
+    }
+    AO_CUDA(cudaMemcpyAsync(&o.znorm, res, sizeof(double), cudaMemcpyDeviceToHost, st_));
+    AO_CUDA(cudaStreamSynchronize(st_));
+    o.znorm_pending_allreduce = o.sharded;
+  }
   AO_CUDA(cudaDeviceSynchronize());
 
   // static sweep order -> last updated mode of every object (cmtf_fun_AOADMM.m:121-123)
@@ -520,6 +539,13 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     ncclComm_t comm;
     AO_NCCL(nccl_->CommInitRank(&comm, world_, uid, rank_));
     comm_ = comm;
+    for (auto& o : objects_)
+      if (o.znorm_pending_allreduce) {  // partial norms of the slabs -> norm of the whole tensor
+        AO_CUDA(cudaMemcpyAsync(cp0_tmp_, &o.znorm, sizeof(double), cudaMemcpyHostToDevice, st_));
+        allreduce(cp0_tmp_, 1);
+        AO_CUDA(cudaMemcpyAsync(&o.znorm, cp0_tmp_, sizeof(double), cudaMemcpyDeviceToHost, st_));
+        AO_CUDA(cudaStreamSynchronize(st_));
+      }
   }
   AO_CUDA(cudaDeviceSynchronize());
 }

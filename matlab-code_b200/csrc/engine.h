@@ -121,6 +121,7 @@ struct ObjectState {
   std::vector<int> modes;     // global mode ids (1-based)
   std::vector<int64_t> dims;  // local dims (last one = shard extent)
   double weight = 1.0, znorm = 0.0;
+  bool znorm_pending_allreduce = false;
   double* data = nullptr;     // device, leading dimension ld0
   int64_t ld0 = 0;
   int64_t shard_offset = 0, shard_extent = 0, last_full = 0;

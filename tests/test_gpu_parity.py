@@ -425,6 +425,18 @@ def test_em_imputation_large_ranks_and_front_end(ab):
     assert abs(out['f_tensors'] - oo['f_tensors']) < FIT_TOL       # the front end computes the masked Znorm_const
 
 
+def test_znorm_const_computed_on_device(ab):
+    """Znorm_const = NaN asks the engine for ||X_p||^2 (observed entries with Z.miss), cmtf_AOADMM.m:124-156."""
+    Z, G, _ = pg.config_cp_par2(I=21, J=17, K=13, Jk=11, Kp=6, R=3, seed=6, noise=0.1)
+    Zm = pg.add_missing(Z, 0.3, seed=4)
+    for Zx in (Z, Zm):
+        opts = pg.default_options(MaxOuterIters=6)
+        zn = pg.znorm_const(Zx)
+        _, o1 = ab.cmtf_fun_AOADMM(Zx, zn, G, None, None, None, None, opts)
+        _, o2 = ab.cmtf_fun_AOADMM(Zx, [float('nan')] * 2, G, None, None, None, None, opts)
+        assert np.max(np.abs(o1['func_val_conv'] - o2['func_val_conv'])) < 1e-12
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
