@@ -387,6 +387,7 @@ class Solver:
         o.increase_factor_rhoBk = float(options.get('increase_factor_rhoBk', 1.0))
         o.mttkrp_precision = 0
         o.dimtree = int(options.get('dimtree', 0))
+        o.graph = int(options.get('graph', 0))
         n = o.MaxOuterIters + 1
         hist = [np.zeros(n) for _ in range(5)]
         hmiss = np.full(n, np.nan)

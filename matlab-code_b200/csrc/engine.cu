@@ -1217,8 +1217,15 @@ void Engine::em_step(bool impute) {
 }
 
 void Engine::eval_objective(bool first, double f[4]) {
+  enqueue_objective(first);
+  finish_objective(first, f);
+}
+
+// device part of CMTF_AOADMM_func_eval: every reduction kernel + the device->host copies of their results
+void Engine::enqueue_objective(bool first) {
   const int nj = (int)jobs_host_.size();
-  std::vector<double> f_obj(n_objects_, 0.0);
+  std::vector<double>& f_obj = f_obj_;
+  f_obj.assign(n_objects_, 0.0);
   if (first) {
     // cp_func.m:47-56 / pca_func.m:29-40: f = w*(||X||^2 - 2*sum(A1 .* mttkrp(X,A,1)) + sum(prod of all Grams))
     for (int p = 0; p < n_objects_; ++p) {
@@ -1286,6 +1293,11 @@ void Engine::eval_objective(bool first, double f[4]) {
   launches_ += reduce_jobs(jobs_dev_, nj, red_dev_, red_partials_, admm_counter_, st_, nullptr);
   AO_CUDA(cudaMemcpyAsync(red_host_, red_dev_, sizeof(double) * nj, cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaMemcpyAsync(ctl_host_, ctl_dev_, sizeof(InnerCtl) * n_ctl_, cudaMemcpyDeviceToHost, st_));
+}
+
+// host part: the scalar arithmetic of :1213-1363 on the reduced values
+void Engine::finish_objective(bool first, double f[4]) {
+  std::vector<double>& f_obj = f_obj_;
   AO_CUDA(cudaStreamSynchronize(st_));
   phase_collect();
   const double* r = red_host_;
@@ -1474,6 +1486,7 @@ void Engine::get_state(int field, int index, int slice, double* data, int64_t ro
 // timing helpers
 // ---------------------------------------------------------------------------------------------------
 void Engine::phase_begin(int phase) {
+  if (capturing_) return;  // timing events cannot be queried from inside a CUDA graph
   if (ev_used_ == ev_pool_.size()) {
     cudaEvent_t a, b;
     AO_CUDA(cudaEventCreate(&a));
@@ -1485,6 +1498,7 @@ void Engine::phase_begin(int phase) {
   AO_CUDA(cudaEventRecord(ev_pool_[ev_used_].first, st_));
 }
 void Engine::phase_end() {
+  if (capturing_) return;
   AO_CUDA(cudaEventRecord(ev_pool_[ev_used_].second, st_));
   ++ev_used_;
 }
@@ -1519,6 +1533,86 @@ void Engine::check_errors(aoadmm_out* out) {
 static bool stop_one(double f, double f_old, double abs_tol, double rel_tol) {  // evaluate_stopping_conditions.m:8-15
   const double rel = (f_old > 0.0) ? std::fabs(f_old - f) / f_old : std::fabs(f_old - f);
   return (f < abs_tol) || (rel < rel_tol);
+}
+
+// One sweep over all modes (cmtf_fun_AOADMM.m:89-406): uncoupled modes first (coupl_id 0), then every coupling group.
+void Engine::sweep(int iter, std::vector<int>& inner_fixed) {
+  std::set<int> cset;
+  for (auto& m : modes_) cset.insert(m.coupling);
+  std::fill(inner_fixed.begin(), inner_fixed.end(), 0);
+  for (int coupl_id : cset) {                                      // :89
+    std::vector<ModeState*> cm;
+    std::set<int> ps;
+    for (auto& m : modes_)
+      if (m.coupling == coupl_id) {
+        cm.push_back(&m);
+        ps.insert(m.p);
+      }
+    for (int p : ps) {                                             // :91
+      for (ModeState* mp : cm) {                                   // :93
+        ModeState& m = *mp;
+        if (m.p != p) continue;
+        if (m.par2_role != 0) {                                    // :157-250
+          const int nterms = (coupl_id == 0) ? (m.constrained ? 1 : 0) : 1 + (m.constrained ? 1 : 0);
+          if (m.par2_role == 1) {
+            par2_precompute_A(m, nterms);
+            if (coupl_id == 0) {
+              if (!m.constrained) {
+                launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :181
+                inner_fixed[m.id - 1] = 1;
+                ++m.version;
+              } else {
+                std::vector<ModeState*> g1{&m};
+                run_admm(g1, nullptr, opt_);                       // :186
+              }
+              refresh_gram(m);                                     // :190
+            }
+          } else if (m.par2_role == 2) {
+            par2_update_B(m, iter);                                // :192-218
+          } else {
+            const bool ls = (coupl_id == 0 && !m.constrained);
+            par2_precompute_C(m, nterms, ls);                      // :220-243
+            if (ls) {
+              inner_fixed[m.id - 1] = 1;
+              ++m.version;
+            } else if (coupl_id == 0) {
+              std::vector<ModeState*> g1{&m};
+              run_admm(g1, nullptr, opt_);                         // :245
+            }
+          }
+          continue;
+        }
+        if (coupl_id == 0) {
+          if (!m.constrained) {
+            precompute_mode(m, 0, true);
+            launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :134
+            inner_fixed[m.id - 1] = 1;
+            ++m.version;
+          } else {
+            precompute_mode(m, 1, true);                           // :141-142
+            std::vector<ModeState*> g1{&m};
+            run_admm(g1, nullptr, opt_);                           // :144
+          }
+          refresh_gram(m);                                         // :148
+        } else {
+          const int ct = coupling_type_[coupl_id - 1];
+          const int con = m.constrained ? 1 : 0;
+          if (ct == 0 || ct == 3 || ct == 4) precompute_mode(m, 1 + con, true);   // :269-273, :336-340, :358-362
+          else if (ct == 2) precompute_mode(m, con, true);                         // :314-318 (rho/2*H*H' + constraint)
+          else precompute_mode(m, 0, false);                                       // :288-294, :377-383: B stays w*C
+        }
+      }
+    }
+    if (coupl_id != 0) {                                           // :253
+      if (coupling_type_[coupl_id - 1] == 0) {
+        run_admm(cm, delta_[coupl_id - 1].p, opt_);                // :277
+      } else {
+        lin_prepare_group(coupl_id);
+        run_admm_linear(coupl_id, cm, opt_);                       // :300, :322, :344, :366, :389
+      }
+      for (ModeState* mp : cm) refresh_gram(*mp);                  // :393-403
+    }
+  }
 }
 
 void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
@@ -1570,91 +1664,74 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
   if (out->func_PAR2_coupl) out->func_PAR2_coupl[0] = f[3];
   if (out->time_at_it) out->time_at_it[0] = 0.0;
 
-  std::set<int> cset;
-  for (auto& m : modes_) cset.insert(m.coupling);
-  std::vector<int> inner_fixed(nb_modes_, 0);
+  std::vector<int> inner_fixed(nb_modes_, 0), fixed_captured;
   AO_CUDA(cudaEventRecord(run_ev_[2], st_));  // the outer loop starts here (iteration-0 objective done)
+
+  // CUDA graph replay for launch-bound problems (engine knob options.graph: 0 auto, 1 on, -1 off)
+  bool graph_ok = false;
+  if (world_ == 1 && opt_.graph >= 0 && opt_.MaxOuterIters >= 6) {
+    double elems = 0.0;
+    for (auto& o : objects_) {
+      double e = 1.0;
+      for (auto d : o.dims) e *= (double)d;
+      elems += e;
+    }
+    graph_ok = (opt_.graph > 0) || elems <= 33554432.0;
+  }
+  struct GraphGuard {
+    cudaGraphExec_t& g;
+    ~GraphGuard() {
+      if (g) cudaGraphExecDestroy(g);
+      g = nullptr;
+    }
+  };
+  cudaGraphExec_t gexec = nullptr;
+  GraphGuard guard{gexec};
+  int64_t graph_launches = 0;
 
   int iter = 1;
   bool stop = false;
   while (iter <= opt_.MaxOuterIters && !stop) {
-    std::fill(inner_fixed.begin(), inner_fixed.end(), 0);
-    for (int coupl_id : cset) {                                      // :89
-      std::vector<ModeState*> cm;
-      std::set<int> ps;
-      for (auto& m : modes_)
-        if (m.coupling == coupl_id) {
-          cm.push_back(&m);
-          ps.insert(m.p);
-        }
-      for (int p : ps) {                                             // :91
-        for (ModeState* mp : cm) {                                   // :93
-          ModeState& m = *mp;
-          if (m.p != p) continue;
-          if (m.par2_role != 0) {                                    // :157-250
-            const int nterms = (coupl_id == 0) ? (m.constrained ? 1 : 0) : 1 + (m.constrained ? 1 : 0);
-            if (m.par2_role == 1) {
-              par2_precompute_A(m, nterms);
-              if (coupl_id == 0) {
-                if (!m.constrained) {
-                  launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :181
-                  inner_fixed[m.id - 1] = 1;
-                  ++m.version;
-                } else {
-                  std::vector<ModeState*> g1{&m};
-                  run_admm(g1, nullptr, opt_);                       // :186
-                }
-                refresh_gram(m);                                     // :190
-              }
-            } else if (m.par2_role == 2) {
-              par2_update_B(m, iter);                                // :192-218
-            } else {
-              const bool ls = (coupl_id == 0 && !m.constrained);
-              par2_precompute_C(m, nterms, ls);                      // :220-243
-              if (ls) {
-                inner_fixed[m.id - 1] = 1;
-                ++m.version;
-              } else if (coupl_id == 0) {
-                std::vector<ModeState*> g1{&m};
-                run_admm(g1, nullptr, opt_);                         // :245
-              }
-            }
-            continue;
-          }
-          if (coupl_id == 0) {
-            if (!m.constrained) {
-              precompute_mode(m, 0, true);
-              launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :134
-              inner_fixed[m.id - 1] = 1;
-              ++m.version;
-            } else {
-              precompute_mode(m, 1, true);                           // :141-142
-              std::vector<ModeState*> g1{&m};
-              run_admm(g1, nullptr, opt_);                           // :144
-            }
-            refresh_gram(m);                                         // :148
-          } else {
-            const int ct = coupling_type_[coupl_id - 1];
-            const int con = m.constrained ? 1 : 0;
-            if (ct == 0 || ct == 3 || ct == 4) precompute_mode(m, 1 + con, true);   // :269-273, :336-340, :358-362
-            else if (ct == 2) precompute_mode(m, con, true);                         // :314-318 (rho/2*H*H' + constraint)
-            else precompute_mode(m, 0, false);                                       // :288-294, :377-383: B stays w*C
-          }
-        }
-      }
-      if (coupl_id != 0) {                                           // :253
-        if (coupling_type_[coupl_id - 1] == 0) {
-          run_admm(cm, delta_[coupl_id - 1].p, opt_);                // :277
-        } else {
-          lin_prepare_group(coupl_id);
-          run_admm_linear(coupl_id, cm, opt_);                       // :300, :322, :344, :366, :389
-        }
-        for (ModeState* mp : cm) refresh_gram(*mp);                  // :393-403
-      }
-    }
     const double f_old[4] = {f[0], f[1], f[2], f[3]};
-    em_step(true);                                                   // :408-441
-    eval_objective(false, f);                                        // :447 (synchronises)
+    if (gexec != nullptr) {
+      // steady state of a launch-bound problem: the whole outer iteration is one CUDA-graph launch
+      AO_CUDA(cudaGraphLaunch(gexec, st_));
+      launches_ += graph_launches;
+      inner_fixed = fixed_captured;
+    } else if (graph_ok && iter >= 2 && iter > opt_.iter_start_PAR2Bkconstraint + 1 && iter < opt_.MaxOuterIters) {
+      // capture this iteration (every lazy allocation / attribute call happened in iteration 1) and replay it from now on:
+      // the launch sequence of an outer iteration is static because the inner-loop exit test lives on the device
+      const int64_t l0 = launches_;
+      cudaGraph_t graph = nullptr;
+      capturing_ = true;
+      AO_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeRelaxed));
+      try {
+        sweep(iter, inner_fixed);
+        em_step(true);
+        enqueue_objective(false);
+      } catch (...) {
+        cudaStreamEndCapture(st_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        capturing_ = false;
+        throw;
+      }
+      capturing_ = false;
+      AO_CUDA(cudaStreamEndCapture(st_, &graph));
+      const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        gexec = nullptr;
+        throw CudaError(5, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+      }
+      graph_launches = launches_ - l0;
+      fixed_captured = inner_fixed;
+      AO_CUDA(cudaGraphLaunch(gexec, st_));
+    } else {
+      sweep(iter, inner_fixed);
+      em_step(true);                                                 // :408-441
+      enqueue_objective(false);                                      // :447
+    }
+    finish_objective(false, f);                                      // synchronises
     check_errors(out);
     if (out->func_val_conv) out->func_val_conv[iter] = f[0];
     if (out->func_coupl_conv) out->func_coupl_conv[iter] = f[1];

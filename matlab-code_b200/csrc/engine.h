@@ -166,6 +166,9 @@ class Engine {
   void apply_bsum(ModeState& m);
   void run_admm(std::vector<ModeState*>& group, double* Delta, const aoadmm_options& opt);
   void eval_objective(bool first, double f[4]);
+  void enqueue_objective(bool first);
+  void finish_objective(bool first, double f[4]);
+  void sweep(int iter, std::vector<int>& inner_fixed);
   void check_errors(aoadmm_out* out);
   void allreduce(double* buf, size_t count);
   // EM imputation of missing entries + masked objective sums (cmtf_fun_AOADMM.m:408-441, :1224-1226, :1249-1252)
@@ -229,6 +232,8 @@ class Engine {
   struct ObjTerms;
   std::unique_ptr<ObjTerms> terms_;
   double* cp0_tmp_ = nullptr;     // iteration-0 MTTKRP / Hadamard scratch
+  std::vector<double> f_obj_;     // per-object objective terms between enqueue_objective and finish_objective
+  bool capturing_ = false;        // inside cudaStreamBeginCapture / EndCapture
   bool has_missing_ = false;      // any object with a Z.miss mask
   double* em_sums_ = nullptr;     // device, 5 per object (see em.cuh)
   double* em_sums_host_ = nullptr;  // pinned

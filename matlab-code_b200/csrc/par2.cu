@@ -2,6 +2,7 @@
 #include "par2.cuh"
 
 #include <algorithm>
+#include <map>
 
 namespace aoadmm {
 
@@ -678,7 +679,12 @@ __global__ void __launch_bounds__(256) par2_residual_kernel(Par2Layout L, const 
 
 template <typename Kern>
 void opt_in_smem(Kern kern, size_t smem) {
-  if (smem > 48 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::map<const void*, size_t> configured;  // once per kernel and size (no attribute calls under graph capture)
+  size_t& cur = configured[reinterpret_cast<const void*>(kern)];
+  if (smem > 48 * 1024 && smem > cur) {
+    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
 }
 
 unsigned flat_grid(long long n) { return (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8); }

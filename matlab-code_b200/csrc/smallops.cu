@@ -11,6 +11,7 @@
 #include "smallops.cuh"
 
 #include <algorithm>
+#include <map>
 
 namespace aoadmm {
 
@@ -681,7 +682,13 @@ FinInfo make_fin(const AdmmGroup& g) {
 }
 template <typename K>
 void set_smem(K kern, size_t smem) {
-  if (smem > 40 * 1024) AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // once per kernel and size: no attribute calls on the steady-state path (they are not allowed inside graph capture)
+  static std::map<const void*, size_t> configured;
+  size_t& cur = configured[reinterpret_cast<const void*>(kern)];
+  if (smem > 40 * 1024 && smem > cur) {
+    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
 }
 }  // namespace
 

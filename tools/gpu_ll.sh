@@ -1,1 +1,2 @@
-timeout 300 python tools/c4_probe.py > gpurun_out/plain_c4.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_c4.csv python tools/c4_probe.py > gpurun_out/ncu_l.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
+timeout 300 python tools/bench_configs.py c1 c4 --iters 30 2>&1 | cut -c1-300
