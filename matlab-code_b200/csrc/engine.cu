@@ -1028,7 +1028,7 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
 }
 
 // third PARAFAC2 mode (:220-243): per-row right-hand sides and systems
-void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct) {
+void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out) {
   Par2State& s = par2_[m.par2];
   ObjectState& o = objects_[m.p];
   ModeState &ma = mode(s.m1), &mb = mode(s.m2);
@@ -1051,6 +1051,8 @@ void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct) {
   sa.fac_out = m.fac.p;
   sa.rho_k = s.rho3;
   sa.Binv = s.Binv3;
+  sa.Bsys = Bsys_out;
+  sa.no_factor = (Bsys_out != nullptr) ? 1 : 0;
   sa.ctl = m.ctl;
   launches_ += par2_sys_prep(s.lay, sa, st_);
   launches_ += par2_rho_max(s.rho3, s.K, m.rho, st_);
@@ -1571,7 +1573,10 @@ void Engine::sweep(int iter, std::vector<int>& inner_fixed) {
             par2_update_B(m, iter);                                // :192-218
           } else {
             const bool ls = (coupl_id == 0 && !m.constrained);
-            par2_precompute_C(m, nterms, ls);                      // :220-243
+            if (m.lin >= 0)   // coupling type 1: B{m}{k} stay w*C_k, the coupled system is assembled later (:283-297)
+              par2_precompute_C(m, 0, false, lin_modes_[m.lin].Bsys3);
+            else
+              par2_precompute_C(m, nterms, ls);                    // :220-243
             if (ls) {
               inner_fixed[m.id - 1] = 1;
               ++m.version;

@@ -67,6 +67,14 @@ struct LinMode {
   DevMat U, VB, Bwork;
   double* lam = nullptr;        // eigenvalues of H'H (rows of F)
   double* muB = nullptr;        // eigenvalues of B (R)
+  // type 1 with a PARAFAC2 third mode (:283-297, :710-722): one (K*R) x (K*R) system instead of a Sylvester equation
+  bool par2c = false;
+  DevMat HtH, B2, B2L, B2B, B2C;
+  double* B2invdiag = nullptr;
+  double* Bsys3 = nullptr;      // K x R x R: the per-row matrices B{m}{k}
+  double* rho_stats = nullptr;  // [0] mean(rho), [1] sum(rho)
+  const double* rho_A = nullptr;  // scalar rho used in A_inner  (m.rho, or mean(rho) for par2c)
+  const double* rho_D = nullptr;  // scalar weight in the Delta update (m.rho, or sum(rho) for par2c)
 };
 
 struct LinGroup {
@@ -187,7 +195,7 @@ class Engine {
   void par2_update_T(Par2State& s);
   void par2_precompute_A(ModeState& m, int n_rho_terms);
   void par2_update_B(ModeState& m, int outer_iter);
-  void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct);
+  void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out = nullptr);
   void par2_refresh_gram(Par2State& s);
   DevMat* par2_field(int field, int index, int slice, int64_t* row_off, int64_t* nrows);
 

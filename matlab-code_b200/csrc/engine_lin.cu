@@ -40,8 +40,10 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
   dev_alloc(g.Ddiff, dr, dc);
   for (auto& m : modes_) {
     if (m.coupling != c) continue;
-    if (m.par2_role != 0)
-      throw CudaError(2, "PARAFAC2 modes inside a linearly coupled group (coupling type 1..5) are not supported on device");
+    const bool par2c = (m.par2_role == 3 && ctype == 1);  // example_script14: H C = Delta with C of a PARAFAC2 model
+    if (m.par2_role != 0 && !par2c)
+      throw CudaError(2, "PARAFAC2 modes inside a linearly coupled group are supported for coupling type 1 and the third "
+                         "PARAFAC2 mode only (coupling types 2..5 with PARAFAC2 modes are not supported on device)");
     const int i = m.id - 1;
     if (prob->trafo == nullptr || prob->trafo[i] == nullptr)
       throw CudaError(1, "coupl_trafo_matrices{" + std::to_string(m.id) + "} is required for coupling type " + std::to_string(ctype));
@@ -81,7 +83,19 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
       dev_alloc(lm.HHt, m.R, m.R);
       launches_ += dgemm_small(0, 1, m.R, m.R, hc, 1.0, nullptr, lm.H.p, hr, lm.H.p, hr, 0.0, lm.HHt.p, m.R, st_, nullptr);
     }
-    if (ctype == 1 || ctype == 5) {
+    if (par2c) {
+      const int64_t n = m.rows * m.R;
+      if (n * 8 > 40 * 1024) throw CudaError(2, "coupling type 1 with a PARAFAC2 third mode: K*R must be <= 5120");
+      lm.par2c = true;
+      dev_alloc(lm.HtH, m.rows, m.rows);
+      launches_ += dgemm_small(1, 0, m.rows, m.rows, hr, 1.0, nullptr, lm.H.p, hr, lm.H.p, hr, 0.0, lm.HtH.p, m.rows, st_, nullptr);
+      for (DevMat* d : {&lm.B2, &lm.B2L, &lm.B2B, &lm.B2C}) dev_alloc(*d, n, n);
+      AO_CUDA(cudaMalloc(&lm.B2invdiag, sizeof(double) * n));
+      AO_CUDA(cudaMalloc(&lm.Bsys3, sizeof(double) * m.rows * m.R * m.R));
+      AO_CUDA(cudaMalloc(&lm.rho_stats, sizeof(double) * 2));
+      lm.rho_A = lm.rho_stats;       // mean(rho{mm})  (:712)
+      lm.rho_D = lm.rho_stats + 1;   // sum(rho{jj})   (:742)
+    } else if (ctype == 1 || ctype == 5) {
       // eigen-decomposition H'H = U diag(lam) U' once: one-sided Jacobi on H (q x I)
       if (m.rows > 4096) throw CudaError(2, "coupling types 1/5 support at most 4096 rows in the coupled factor");
       dev_alloc(lm.U, m.rows, m.rows);
@@ -102,8 +116,8 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
   }
   if (g.modes.empty()) throw CudaError(1, "coupling id without modes");
   if ((int)g.modes.size() > 5) throw CudaError(2, "more than 5 modes in a linearly coupled group");
-  AO_CUDA(cudaMalloc(&g.scal, sizeof(double) * 4));
-  AO_CUDA(cudaMemset(g.scal, 0, sizeof(double) * 4));
+  AO_CUDA(cudaMalloc(&g.scal, sizeof(double) * 8));
+  AO_CUDA(cudaMemset(g.scal, 0, sizeof(double) * 8));
   // small normal equations of the Delta update (:875-881, :941-962, :1028-1053)
   int64_t q = 0;
   const ModeState& m0 = mode(g.modes[0]);
@@ -144,6 +158,7 @@ void Engine::lin_build_jobs(int c) {
   for (size_t t = 0; t < g.modes.size(); ++t) {
     ModeState& m = mode(g.modes[t]);
     LinMode& lm = lin_modes_[m.lin];
+    if (!lm.par2c) lm.rho_A = lm.rho_D = m.rho;   // (m.rho exists only now: per-mode buffers are allocated after the groups)
     LinFinMode& f = g.fin.m[t];
     f.i_pr_num = add(RED_DIFF2, lm.S1.p, lm.S2.p, lm.S1.rows, lm.S1.cols);
     const int i_f = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R);
@@ -173,6 +188,9 @@ void Engine::free_linear_coupling() {
       dev_free(*d);
     if (lm.lam) cudaFree(lm.lam);
     if (lm.muB) cudaFree(lm.muB);
+    for (DevMat* d : {&lm.HtH, &lm.B2, &lm.B2L, &lm.B2B, &lm.B2C}) dev_free(*d);
+    for (void* q : {(void*)lm.B2invdiag, (void*)lm.Bsys3, (void*)lm.rho_stats})
+      if (q) cudaFree(q);
   }
   for (auto& g : lin_groups_) {
     for (DevMat* d : {&g.Dold, &g.Ddiff, &g.AA, &g.AAL, &g.AAB, &g.AAC, &g.BB, &g.Dt}) dev_free(*d);
@@ -240,15 +258,38 @@ void Engine::lin_prepare_group(int c) {
   LinGroup& g = lin_groups_[c - 1];
   const int n = (int)g.modes.size();
   InnerCtl* ctl = mode(g.modes[0]).ctl;
+  for (int i = 0; i < n; ++i) {
+    ModeState& m = mode(g.modes[i]);
+    LinMode& lm = lin_modes_[m.lin];
+    if (!lm.par2c) continue;
+    Par2State& s = par2_[m.par2];
+    launches_ += par2_rho_stats(s.rho3, s.K, lm.rho_stats, st_);
+    launches_ += par2_assemble_B2(lm.Bsys3, lm.HtH.p, lm.rho_stats, m.constrained ? 1 : 0, s.K, s.R, lm.B2.p, st_);
+    PrepArgs a{};   // L{m} = chol(B2{m},'lower')  (:296)
+    a.nhad = 1;
+    a.had[0] = lm.B2.p;
+    a.R = (int)lm.B2.rows;
+    a.weight = 1.0;
+    a.rho_scale = 1.0;
+    a.do_chol = 1;
+    a.C = lm.B2C.p;
+    a.B = lm.B2B.p;
+    a.L = lm.B2L.p;
+    a.invdiag = lm.B2invdiag;
+    a.rho = g.scal + 3;
+    a.ctl = ctl;
+    launches_ += prep_system(a, st_, nullptr);
+  }
   if (g.ctype == 1 || g.ctype == 2) {
     LinTerm t[5];
-    for (int i = 0; i < n; ++i) t[i] = LinTerm{nullptr, 1.0, mode(g.modes[i]).rho};
+    for (int i = 0; i < n; ++i) t[i] = LinTerm{nullptr, 1.0, lin_modes_[mode(g.modes[i]).lin].rho_D};
     launches_ += sum_recip(g.scal, t, n, st_);
   }
   if (g.ctype == 1 || g.ctype == 5) {
     for (int i = 0; i < n; ++i) {  // B = VB diag(muB) VB'
       ModeState& m = mode(g.modes[i]);
       LinMode& lm = lin_modes_[m.lin];
+      if (lm.par2c) continue;
       AO_CUDA(cudaMemcpyAsync(lm.Bwork.p, m.B.p, m.B.bytes(), cudaMemcpyDeviceToDevice, st_));
       launches_ += jacobi_onesided(lm.Bwork.p, m.R, m.R, lm.VB.p, lm.muB, st_);
     }
@@ -307,10 +348,13 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
       }
       lin_Gt(lm, m, lm.S2.p, lm.tmpF.p, skip);
       {
-        LinTerm t[4] = {{m.A.p, 1.0, nullptr}, {lm.tmpF.p, 0.5, m.rho}, {m.Z.p, 0.5, m.rho}, {m.muZ.p, -0.5, m.rho}};
+        LinTerm t[4] = {{m.A.p, 1.0, nullptr}, {lm.tmpF.p, 0.5, lm.rho_A}, {m.Z.p, 0.5, lm.rho_A}, {m.muZ.p, -0.5, lm.rho_A}};
         launches_ += lincomb(lm.tmpF.p, nF, t, m.constrained ? 4 : 2, st_, skip);
       }
-      if (g.ctype == 1 || g.ctype == 5) {
+      if (lm.par2c) {
+        // Gfacmm_vec = L'\(L\A_inner) on the (K*R) system, rows of C in the order k*R + r (:721-722)
+        launches_ += par2_chol_solve_vec(lm.B2L.p, (int)m.rows, m.R, lm.tmpF.p, m.fac.p, st_, skip);
+      } else if (g.ctype == 1 || g.ctype == 5) {
         // sylvester(B2,B,A_inner) (:728, :1016) with B2 = rho/2 (H'H [+ I]) = U (rho/2 (lam [+1])) U', B = VB muB VB'
         launches_ += dgemm_small(1, 0, m.rows, m.R, m.rows, 1.0, nullptr, lm.U.p, m.rows, lm.tmpF.p, m.rows, 0.0, lm.tmpF2.p, m.rows, st_, skip);
         launches_ += dgemm_small(0, 0, m.rows, m.R, m.R, 1.0, nullptr, lm.tmpF2.p, m.rows, lm.VB.p, m.R, 0.0, lm.tmpF.p, m.rows, st_, skip);
@@ -332,10 +376,10 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
       lin_G(lm, m, m.fac.p, lm.S1.p, skip);
       if (g.ctype == 1 || g.ctype == 2) {  // :738-749, :808-815 rho-weighted mean
         if (i == 0) {
-          LinTerm t[2] = {{lm.S1.p, 1.0, m.rho}, {m.muD.p, 1.0, m.rho}};
+          LinTerm t[2] = {{lm.S1.p, 1.0, lm.rho_D}, {m.muD.p, 1.0, lm.rho_D}};
           launches_ += lincomb(D.p, nD, t, 2, st_, skip);
         } else {
-          LinTerm t[3] = {{D.p, 1.0, nullptr}, {lm.S1.p, 1.0, m.rho}, {m.muD.p, 1.0, m.rho}};
+          LinTerm t[3] = {{D.p, 1.0, nullptr}, {lm.S1.p, 1.0, lm.rho_D}, {m.muD.p, 1.0, lm.rho_D}};
           launches_ += lincomb(D.p, nD, t, 3, st_, skip);
         }
       } else {

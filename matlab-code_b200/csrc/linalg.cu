@@ -373,6 +373,7 @@ int sum_recip(double* out, const LinTerm* terms, int nterms, cudaStream_t st) {
   LinArgs a{};
   a.n = nterms;
   for (int t = 0; t < nterms; ++t) {
+    if (terms[t].coef_dev == nullptr) throw CudaError(1, "sum_recip: device scalar missing");
     a.coef[t] = terms[t].coef;
     a.coef_dev[t] = terms[t].coef_dev;
   }

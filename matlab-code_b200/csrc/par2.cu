@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
       if (a.bsum_half != 0.0) b += a.bsum_half;
     }
     W[e] = b;
+    if (a.Bsys != nullptr) a.Bsys[(size_t)k * RR + e] = b;
   }
   if (a.mode == 3) {
     // a_k(r) = w * sum_j T(j,r) B_k(j,r)   (= w * diag(A' X_k B_k), :221)  [+ bsum/2 * C(k,r), :231]
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
     }
   }
   __syncthreads();
+  if (a.no_factor) return;
   const bool ok = cta_cholesky(W, R);
   if (!ok) {
     if (tid == 0 && a.ctl != nullptr) a.ctl->err = 3;
@@ -191,6 +193,59 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
     return;
   }
   cta_inverse_from_chol(W, V, R, a.Binv + (size_t)k * RR);
+}
+
+__global__ void par2_rho_stats_kernel(const double* __restrict__ rho_k, int K, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s += rho_k[k];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    out[0] = s / (double)K;
+    out[1] = s;
+  }
+}
+
+__global__ void par2_assemble_B2_kernel(const double* __restrict__ Bsys, const double* __restrict__ HtH,
+                                        const double* __restrict__ rhoC_dev, int constrained, int K, int R,
+                                        double* __restrict__ B2) {
+  const long long n = (long long)K * R;
+  const double half = *rhoC_dev / 2.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e % n, col = e / n;
+    const int k = (int)(row / R), r = (int)(row % R), k2 = (int)(col / R), s = (int)(col % R);
+    double v = 0.0;
+    if (k == k2) v = Bsys[(size_t)k * R * R + r + (size_t)s * R];
+    if (r == s) v += half * HtH[k + (size_t)k2 * K];
+    if (constrained && row == col) v += half;
+    B2[e] = v;
+  }
+}
+
+// forward / backward substitution with the lower Cholesky factor L (n x n, column-major) for ONE right-hand side
+__global__ void __launch_bounds__(256) par2_chol_solve_vec_kernel(const double* __restrict__ L, int K, int R,
+                                                                   const double* __restrict__ a, double* __restrict__ x,
+                                                                   const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ double xs[];
+  const int n = K * R, tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < n; i += nt) xs[i] = a[(i / R) + (size_t)(i % R) * K];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {            // L y = a
+    const double yj = xs[j] / L[j + (size_t)j * n];
+    __syncthreads();
+    if (tid == 0) xs[j] = yj;
+    for (int i = j + 1 + tid; i < n; i += nt) xs[i] = fma(-L[i + (size_t)j * n], yj, xs[i]);
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {       // L' x = y
+    const double xj = xs[j] / L[j + (size_t)j * n];
+    __syncthreads();
+    if (tid == 0) xs[j] = xj;
+    for (int i = tid; i < j; i += nt) xs[i] = fma(-L[j + (size_t)i * n], xj, xs[i]);
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt) x[(i / R) + (size_t)(i % R) * K] = xs[i];
 }
 
 __global__ void par2_rho_max_kernel(const double* __restrict__ rho_k, int K, double* __restrict__ out) {
@@ -722,6 +777,28 @@ int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st) {
   const size_t smem = ((size_t)2 * L.R * L.R + L.R) * sizeof(double);
   opt_in_smem(par2_sys_prep_kernel, smem);
   par2_sys_prep_kernel<<<L.K, 128, smem, st>>>(L, a);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rho_stats(const double* rho_k, int K, double* out, cudaStream_t st) {
+  par2_rho_stats_kernel<<<1, 256, 0, st>>>(rho_k, K, out);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_assemble_B2(const double* Bsys, const double* HtH, const double* rhoC_dev, int constrained, int K, int R,
+                     double* B2, cudaStream_t st) {
+  const long long n = (long long)K * R;
+  par2_assemble_B2_kernel<<<flat_grid(n * n), 256, 0, st>>>(Bsys, HtH, rhoC_dev, constrained, K, R, B2);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_chol_solve_vec(const double* L, int K, int R, const double* a, double* x, cudaStream_t st, const int* skip) {
+  const size_t smem = (size_t)K * R * sizeof(double);
+  if (smem > 40 * 1024) throw CudaError(2, "coupling type 1 with a PARAFAC2 third mode: K*R too large");
+  par2_chol_solve_vec_kernel<<<1, 256, smem, st>>>(L, K, R, a, x, skip);
   AO_CHECK_LAUNCH();
   return 1;
 }

@@ -52,9 +52,19 @@ struct Par2SysArgs {
   // outputs
   double* rho_k;           // K
   double* Binv;            // K x R x R
+  double* Bsys;            // optional: the assembled system matrices themselves (K x R x R)
+  int no_factor;           // only assemble (rho_k, Bsys, rhs): the caller factors a larger system (coupling type 1)
   InnerCtl* ctl;           // err = 3 when a system is not positive definite
 };
 int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st);
+
+// out[0] = mean_k rho_k, out[1] = sum_k rho_k  (the scalars the type-1 coupling uses for a vector rho, :712, :742)
+int par2_rho_stats(const double* rho_k, int K, double* out, cudaStream_t st);
+// B2 (n x n, n = K*R, index k*R + r) = blkdiag(Bsys_k) + rhoC/2 * kron(HtH, I_R) [+ rhoC/2 * I]   (:283-293)
+int par2_assemble_B2(const double* Bsys, const double* HtH, const double* rhoC_dev, int constrained, int K, int R,
+                     double* B2, cudaStream_t st);
+// x = (L L') \ a for one right-hand side stored as a K x R column-major matrix read in the order k*R + r (:721-722)
+int par2_chol_solve_vec(const double* L, int K, int R, const double* a, double* x, cudaStream_t st, const int* skip);
 
 // rho_max = max_k rho_k (update_constraint uses max(rho) when rho is a vector, :1423-1424)
 int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st);

@@ -509,3 +509,21 @@ def config_tparafac2(I=16, J=14, K=9, R=3, seed=0, noise=0.05, eta=0.05, drift=0
     init_options = {'lambdas_init': [[1.0] * R], 'nvecs': 0, 'distr': [d_rand, d_rand, d_rand01], 'normalize': 1}
     G = init_coupled_AOADMM_CMTF(Z, init_options, rng)
     return Z, G, {}
+
+
+def config_script14(I=20, J=14, K=12, I2=16, Jk=10, Kp=40, R=3, seed=0, noise=0.05, constrained_c=True):
+    """example_script14_CP_PAR2_couplC_doublesamplingrate.m:24-38: a CP tensor whose first mode is coupled (type 1,
+    H C = Delta) with the THIRD mode of a PARAFAC2 model sampled at twice the rate (H picks every second row)."""
+    rng = np.random.RandomState(seed)
+    sz = [I, J, K, I2, [Jk] * Kp, Kp]
+    modes = [[1, 2, 3], [4, 5, 6]]
+    H6 = np.zeros((I, Kp))
+    H6[np.arange(I), 2 * np.arange(I)] = 1.0
+    trafo = [np.eye(I), None, None, None, None, H6]
+    coupling = {'lin_coupled_modes': [1, 0, 0, 0, 0, 1], 'coupling_type': [1], 'coupl_trafo_matrices': trafo}
+    lambdas = [[1.0] * R] * 2
+    distr = [d_rand, d_randn, d_randn, d_rand, d_rand, d_rand01]
+    nn = ('non-negativity',)
+    cm = [1, 0, 0, 1, 0, 1 if constrained_c else 0]
+    cons = [nn, None, None, nn, None, nn if constrained_c else None]
+    return _finish(['CP', 'PAR2'], sz, modes, lambdas, [noise] * 2, coupling, distr, cm, cons, [0.5, 0.5], rng)

@@ -437,6 +437,16 @@ def test_znorm_const_computed_on_device(ab):
         assert np.max(np.abs(o1['func_val_conv'] - o2['func_val_conv'])) < 1e-12
 
 
+@pytest.mark.parametrize('constrained_c', [True, False])
+def test_example_script14_type1_coupling_with_parafac2_mode_c(ab, constrained_c):
+    """example_script14: CP mode 1 coupled (H C = Delta) with the third PARAFAC2 mode at twice the sampling rate: the
+    (K*R) x (K*R) system of cmtf_fun_AOADMM.m:283-297 / :710-722 next to a Sylvester-type CP mode."""
+    Z, G, _ = pg.config_script14(seed=1, constrained_c=constrained_c)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=25))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
