@@ -447,6 +447,21 @@ def test_example_script14_type1_coupling_with_parafac2_mode_c(ab, constrained_c)
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
+def test_example_script1a_smooth_bk_and_l2_balls(ab):
+    """example_script1a_CP_PAR2_smooth_l2ball.m: l2-ball on the coupled modes, GL smoothness on every B_k (per-slice
+    deferred prox), non-negative l2-ball on the PARAFAC2 C mode."""
+    Z, G, _ = pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=11, noise=0.05)
+    cons = [('l2-ball', 1.0), None, None, ('l2-ball', 1.0), ('GL smoothness', 1.0), ('non-negative l2-ball', 1.0)]
+    Z = dict(Z, constraints=cons, constrained_modes=[1, 0, 0, 1, 1, 1])
+    rng = np.random.RandomState(5)
+    init_options = {'lambdas_init': [[1.0] * 3] * 2, 'nvecs': 0, 'normalize': 1,
+                    'distr': [pg.d_rand, pg.d_randn, pg.d_randn, pg.d_rand, pg.d_rand, pg.d_rand01]}
+    G = pg.init_coupled_AOADMM_CMTF(Z, init_options, rng)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=20))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
