@@ -148,6 +148,8 @@ typedef struct {
   /* engine-only knobs (0 = default) */
   int32_t mttkrp_precision;   /* 0: FP64 DMMA (default, the parity mode) */
   int32_t dimtree;            /* 0: three independent MTTKRP passes (reference flop/byte count) */
+  int32_t fuse_inner;         /* 0 (default): run the whole inner ADMM loop of a group in one cooperative launch when
+                                 possible; -1: one launch per inner iteration; results are identical */
   int32_t graph;              /* CUDA-graph replay of the outer iteration: 0 auto (launch-bound problems on one GPU),
                                  1 on, -1 off; results are identical */
 } aoadmm_options;

@@ -388,6 +388,7 @@ class Solver:
         o.mttkrp_precision = 0
         o.dimtree = int(options.get('dimtree', 0))
         o.graph = int(options.get('graph', 0))
+        o.fuse_inner = int(options.get('fuse_inner', 0))
         n = o.MaxOuterIters + 1
         hist = [np.zeros(n) for _ in range(5)]
         hmiss = np.full(n, np.nan)

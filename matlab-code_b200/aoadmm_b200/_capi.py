@@ -72,7 +72,7 @@ class Options(C.Structure):
                 ('innerRelDualTol_coupl', C.c_double), ('innerRelDualTol_constr', C.c_double), ('bsum', C.c_int32),
                 ('bsum_weight', C.c_double), ('iter_start_PAR2Bkconstraint', C.c_int32),
                 ('has_increase_factor_rhoBk', C.c_int32), ('increase_factor_rhoBk', C.c_double),
-                ('mttkrp_precision', C.c_int32), ('dimtree', C.c_int32), ('graph', C.c_int32)]
+                ('mttkrp_precision', C.c_int32), ('dimtree', C.c_int32), ('fuse_inner', C.c_int32), ('graph', C.c_int32)]
 
 
 class Out(C.Structure):

@@ -1095,6 +1095,12 @@ void Engine::run_admm(std::vector<ModeState*>& group, double* Delta, const aoadm
   for (ModeState* mp : group) ++mp->version;
   InnerCtl* ctl = group[0]->ctl;
   InnerTol tol{opt.innerRelPrTol_coupl, opt.innerRelDualTol_coupl, opt.innerRelPrTol_constr, opt.innerRelDualTol_constr};
+  if (deferred.empty() && opt.MaxInnerIters > 1 && opt_.fuse_inner >= 0 && admm_can_fuse_inner(g)) {
+    // every prox of the group is element-wise and all CTAs fit on the GPU at once: the whole inner loop is one
+    // cooperative launch (grid barrier + device-side exit test between the iterations)
+    launches_ += admm_iteration(g, tol, ctl, admm_sums_, admm_partials_, admm_counter_, 1, st_, opt.MaxInnerIters);
+    return;
+  }
   for (int it = 0; it < opt.MaxInnerIters; ++it) {
     launches_ += admm_iteration(g, tol, ctl, admm_sums_, admm_partials_, admm_counter_, deferred.empty() ? 1 : 0, st_);
     for (size_t d = 0; d < deferred.size(); ++d) {

@@ -10,6 +10,8 @@
 //   reduce_jobs          :1235-1241, :1272-1300, :1311, :1341 (objective reductions)
 #include "smallops.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <map>
 
@@ -258,8 +260,9 @@ __device__ __forceinline__ void solve_row(double* row_s, int BT, int R, const do
 // explicit inverse is as accurate as the two triangular solves it replaces and turns the solve into a GEMM tile).
 template <bool BSMEM>
 __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup g, FinInfo fin, InnerTol tol, InnerCtl* ctl, double* sums, double* partials,
-                                 unsigned* counter, int finalize) {
-  if (ctl->done != 0) return;
+                                 unsigned* counter, int finalize, int max_iters) {
+  // max_iters > 1 (cooperative launch, every CTA resident): the whole inner ADMM loop of :600 / :633 runs inside one
+  // launch, with a grid-wide barrier after every iteration so that all CTAs see the exit test of the last CTA.
   extern __shared__ double sm[];
   __shared__ double red[32];
   __shared__ bool s_last;
@@ -270,9 +273,12 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
   const bool active = i < g.rows;
   const int e0 = w * 8;
   const int NS = 6 * g.nmodes + 1;
+  const bool coupled = g.Delta != nullptr;
+  for (int inner = 0; inner < max_iters; ++inner) {
+  if (inner > 0) cooperative_groups::this_grid().sync();
+  if (*reinterpret_cast<volatile int*>(&ctl->done) != 0) return;  // uniform over the grid
   double lsum[6 * kMaxGroup + 1];
   for (int s = 0; s < NS; ++s) lsum[s] = 0.0;
-  const bool coupled = g.Delta != nullptr;
   double dsum[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) dsum[c] = 0.0;
@@ -437,8 +443,11 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     if (tid == 0) {
       *counter = 0u;
       if (finalize) finalize_ctl(sums, fin, tol, ctl);
+      __threadfence();
     }
   }
+  __syncthreads();
+  }  // inner iterations
 }
 
 // deferred constraint update for a mode whose prox is not element-wise
@@ -699,21 +708,50 @@ size_t admm_ws_doubles(long long rows, int R, int nmodes) {
 }
 
 int admm_iteration(const AdmmGroup& g, const InnerTol& tol, InnerCtl* ctl, double* sums, double* partials,
-                   unsigned* counter, int finalize, cudaStream_t st) {
+                   unsigned* counter, int finalize, cudaStream_t st, int max_iters) {
   const int nw = (int)ceil_div(g.R, 8);
   const unsigned ctas = (unsigned)ceil_div(std::max<long long>(g.rows, 1), 32);
   const bool bsmem = g.R <= 64;
   const size_t smem = ((size_t)g.R * 32 + (bsmem ? (size_t)g.R * g.R : 0)) * sizeof(double);
   const FinInfo fin = make_fin(g);
-  if (bsmem) {
-    set_smem(admm_tile_kernel<true>, smem);
-    admm_tile_kernel<true><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
-  } else {
-    set_smem(admm_tile_kernel<false>, smem);
-    admm_tile_kernel<false><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize);
+  if (bsmem) set_smem(admm_tile_kernel<true>, smem);
+  else set_smem(admm_tile_kernel<false>, smem);
+  if (max_iters > 1) {
+    AdmmGroup gg = g;
+    FinInfo ff = fin;
+    InnerTol tt = tol;
+    void* args[] = {&gg, &ff, &tt, &ctl, &sums, &partials, &counter, &finalize, &max_iters};
+    const void* fn = bsmem ? reinterpret_cast<const void*>(admm_tile_kernel<true>)
+                           : reinterpret_cast<const void*>(admm_tile_kernel<false>);
+    AO_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(nw * 32), args, smem, st));
+    return 1;
   }
+  if (bsmem)
+    admm_tile_kernel<true><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize, 1);
+  else
+    admm_tile_kernel<false><<<ctas, nw * 32, smem, st>>>(g, fin, tol, ctl, sums, partials, counter, finalize, 1);
   AO_CHECK_LAUNCH();
   return 1;
+}
+
+// true when all CTAs of the ADMM tile kernel for this group can be resident at once (cooperative launch possible)
+bool admm_can_fuse_inner(const AdmmGroup& g) {
+  const int nw = (int)ceil_div(g.R, 8);
+  const long long ctas = ceil_div(std::max<long long>(g.rows, 1), 32);
+  const bool bsmem = g.R <= 64;
+  const size_t smem = ((size_t)g.R * 32 + (bsmem ? (size_t)g.R * g.R : 0)) * sizeof(double);
+  if (bsmem) set_smem(admm_tile_kernel<true>, smem);
+  else set_smem(admm_tile_kernel<false>, smem);
+  int per_sm = 0, dev = 0, sms = 0, coop = 0;
+  AO_CUDA(cudaGetDevice(&dev));
+  AO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  AO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return false;
+  if (bsmem)
+    AO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, admm_tile_kernel<true>, nw * 32, smem));
+  else
+    AO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, admm_tile_kernel<false>, nw * 32, smem));
+  return ctas <= (long long)per_sm * sms;
 }
 
 int admm_constraint_update(const AdmmGroup& g, int which, const double* Znew, const InnerTol& tol, InnerCtl* ctl,

@@ -117,8 +117,11 @@ size_t admm_ws_doubles(long long rows, int R, int nmodes);
 // are scratch; `ctl` is updated by the last CTA (residuals, exit test, iteration count).
 // `sums` (6*nmodes+1 doubles, device) holds the reduced norms of the current inner iteration; `finalize` != 0
 // makes the kernel evaluate the exit test (set it on the LAST kernel of the inner iteration).
+// max_iters > 1: ONE cooperative launch runs up to max_iters inner iterations (grid barrier between them); only valid
+// when admm_can_fuse_inner(g) and every constrained mode of the group has an element-wise prox.
 int admm_iteration(const AdmmGroup& g, const InnerTol& tol, InnerCtl* ctl, double* sums, double* partials,
-                   unsigned* counter, int finalize, cudaStream_t st);
+                   unsigned* counter, int finalize, cudaStream_t st, int max_iters = 1);
+bool admm_can_fuse_inner(const AdmmGroup& g);
 // the deferred constraint part for modes whose prox is not element-wise:  Z = prox(F+muZ) computed by
 // prox_apply into Znew, then this kernel forms muZ, the residual sums and copies Znew -> Z.
 // `finalize` recomputes ctl from the partial sums (same test as admm_iteration).
