@@ -462,6 +462,21 @@ def test_example_script1a_smooth_bk_and_l2_balls(ab):
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
+def test_references_own_dataset_example_script11(ab):
+    """The reference's own data (noisy_dataset.mat, committed as tests/golden/script11_tparafac2.npz) with the
+    configuration of example_script11_tPARAFAC2.m: engine == committed oracle state after 30 outer iterations."""
+    import os
+    import make_script11_fixture as mk
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'script11_tparafac2.npz'))
+    Z, G = mk.script11_problem(fx['dataset'])
+    Gd, od = ab.cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, None, None, None, None, mk.script11_options(30))
+    assert rel(Gd['fac'][0], fx['oracle_A']) < FAC_TOL and rel(Gd['fac'][2], fx['oracle_C']) < FAC_TOL
+    assert rel(np.stack(Gd['fac'][1]), fx['oracle_B']) < FAC_TOL
+    # unnormalised data: the objective is ~4e6, so the 1e-10 fit tolerance is relative here
+    assert rel(od['func_val_conv'], fx['oracle_func_val']) < FIT_TOL
+    assert np.max(np.abs(od['func_PAR2_coupl'] - fx['oracle_func_par2'])) < 1e-9
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
