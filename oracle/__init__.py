@@ -13,5 +13,7 @@ TV_Condat_v2) and ships no tests, golden vectors or expected outputs
 container, so the reference cannot be executed to pin this oracle.  The oracle
 is instead validated by known-answer checks (tests/test_oracle_*.py): MTTKRP vs
 einsum, the shortcut objective vs the explicit residual, every prox vs its
-variational definition (brute force / KKT), and noise-free recovery.
+variational definition (brute force / KKT), noise-free recovery, and recovery of the
+ground-truth factors that the reference ships for its own example_script11 dataset
+(tests/golden/script11_tparafac2.npz) - the only fixture with a known answer.
 """
