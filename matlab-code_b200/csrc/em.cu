@@ -72,26 +72,38 @@ __global__ void __launch_bounds__(256) em_kernel(EmArgs a, int kper) {
           for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
       }
     }
+    // epilogue: all loads of the tile first (independent, so their DRAM latencies overlap), then compare / impute
+    double xv[4][4];
+    uint8_t mk[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long j = j0 + ty + 16 * q;
-      if (j >= a.J) continue;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const long long i = i0 + tx + 16 * p;
-        if (i >= a.I) continue;
-        const long long idx = i + a.ldI * (j + (long long)a.J * k);
-        const double x = a.X[idx], m = acc[p][q];
-        if (a.mask[idx] != 0) {
+        const bool in = (i < a.I) && (j < a.J);
+        const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
+        xv[p][q] = in ? a.X[idx] : 0.0;
+        mk[p][q] = in ? a.mask[idx] : (uint8_t)2;   // 2 = outside the object
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long j = j0 + ty + 16 * q;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const long long i = i0 + tx + 16 * p;
+        const double x = xv[p][q], m = acc[p][q];
+        if (mk[p][q] == 1) {
           s[2] = fma(x, m, s[2]);
           s[3] = fma(m, m, s[3]);
           const double d = x - m;
           s[4] = fma(d, d, s[4]);
-        } else {
+        } else if (mk[p][q] == 0) {
           const double d = m - x;
           s[0] = fma(d, d, s[0]);
           s[1] = fma(x, x, s[1]);
-          if (a.impute) a.X[idx] = m;
+          if (a.impute) a.X[i + a.ldI * (j + (long long)a.J * k)] = m;
         }
       }
     }
