@@ -345,13 +345,18 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     }
     if (active) {
       double sF2 = 0.0;
+      // loads first, stores last: the compiler cannot move a global load above a possibly aliasing global store, so
+      // interleaving them would serialise one memory round trip per column
+      double mud[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mud[c] = (coupled && e0 + c < R) ? md.muD[(long long)(e0 + c) * g.rows + i] : 0.0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int e = e0 + c;
         if (e < R) {
           md.F[(long long)e * md.ldF + i] = x[c];
           sF2 = fma(x[c], x[c], sF2);
-          if (coupled) dsum[c] += rho * (x[c] + md.muD[(long long)e * g.rows + i]);
+          if (coupled) dsum[c] += rho * (x[c] + mud[c]);
         }
       }
       lsum[6 * mi + 0] = sF2;
@@ -362,13 +367,16 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     if (coupled) {
       const double inv = 1.0 / sum_rho;
       double sDD = 0.0;
+      double dold[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dold[c] = (e0 + c < R) ? g.Delta[(long long)(e0 + c) * g.rows + i] : 0.0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int e = e0 + c;
         if (e < R) {
           const long long idx = (long long)e * g.rows + i;
           const double dn = inv * dsum[c];
-          const double df = dn - g.Delta[idx];
+          const double df = dn - dold[c];
           g.Delta[idx] = dn;
           dsum[c] = dn;
           sDD = fma(df, df, sDD);
@@ -381,23 +389,34 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
       const double rho = *md.rho;  // for a vector rho the prox uses max(rho) (update_constraint, :1423-1424)
       double sFD = 0.0, sMuD = 0.0, sFZ = 0.0, sZZ = 0.0, sMuZ = 0.0;
       const bool do_con = md.constrained && prox_is_elementwise(md.prox_kind);
+      double xf[8], vmd[8], vmz[8], vz[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // all loads of this mode first (see above)
+        const int e = e0 + c;
+        const bool ok = e < R;
+        const long long idx = (long long)e * g.rows + i;
+        xf[c] = ok ? md.F[(long long)e * md.ldF + i] : 0.0;
+        vmd[c] = (ok && coupled) ? md.muD[idx] : 0.0;
+        vmz[c] = (ok && do_con) ? md.muZ[idx] : 0.0;
+        vz[c] = (ok && do_con) ? md.Z[idx] : 0.0;
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int e = e0 + c;
         if (e >= R) continue;
         const long long idx = (long long)e * g.rows + i;
-        const double x = md.F[(long long)e * md.ldF + i];
+        const double x = xf[c];
         if (coupled) {
           const double dn = dsum[c];
-          const double mu = md.muD[idx] + x - dn;
+          const double mu = vmd[c] + x - dn;
           md.muD[idx] = mu;
           const double fd = x - dn;
           sFD = fma(fd, fd, sFD);
           sMuD = fma(mu, mu, sMuD);
         }
         if (do_con) {
-          const double muz = md.muZ[idx];
-          const double zold = md.Z[idx];
+          const double muz = vmz[c];
+          const double zold = vz[c];
           const double z = prox_elem(md.prox_kind, x + muz, md.p0, md.p1, rho);
           const double munew = muz + x - z;
           md.Z[idx] = z;

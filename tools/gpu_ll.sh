@@ -1,2 +1,4 @@
-timeout 600 python tools/em_probe.py 512 32 && timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread --clock-control none -k regex:em_kernel -c 3 python tools/em_probe.py 512 32 2>&1 | grep -E "em_kernel|duration|dram__|warps_active|issue_active|registers" | head -24
-timeout 300 python -m pytest tests -m gpu -q -k "em_imputation or znorm" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 300 python tools/bench_configs.py c1 c4 --iters 30 2>&1 | cut -c1-200
+timeout 300 python tools/perf_probe.py 1000 1000 1000 5000 32 20 2>&1 | grep -E "run|phase"
+timeout 300 python tools/perf_probe.py 4096 4096 128 8192 64 10 2>&1 | grep -E "run|phase"
