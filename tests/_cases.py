@@ -36,7 +36,10 @@ def assert_state_close(Gd, Go, tol=FAC_TOL, keys=('fac', 'constraint_fac', 'cons
                 continue
             if isinstance(ref, list):
                 for k, rk in enumerate(ref):
-                    assert rel(Gd[key][i][k], rk) < tol, (key, i, k, rel(Gd[key][i][k], rk))
+                    # per-slice duals can be pure rounding noise (K = 1: mu_DeltaB is exactly 0 in exact arithmetic)
+                    err = np.linalg.norm(np.asarray(Gd[key][i][k]) - rk)
+                    scale = max(np.linalg.norm(rk), 1e-300)
+                    assert err < tol * max(scale, 1.0) or err / scale < tol, (key, i, k, err, scale)
             else:
                 # duals can be exactly zero (inactive prox): compare absolutely then
                 scale = max(np.linalg.norm(ref), 1e-300)

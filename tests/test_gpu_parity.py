@@ -477,6 +477,50 @@ def test_references_own_dataset_example_script11(ab):
     assert np.max(np.abs(od['func_PAR2_coupl'] - fx['oracle_func_par2'])) < 1e-9
 
 
+def test_degenerate_shapes(ab):
+    """Edge cases the reference never exercises: rank 1, single-row modes, a single PARAFAC2 slice, matrices only."""
+    nn = ('non-negativity',)
+    Z, G, _ = pg.config_single_cp(sz=(1, 5, 3), R=1, seed=1, noise=0.1, constraints=[nn, None, nn])
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=8))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+    Z, G, _ = pg.config_single_par2(seed=3, Jk=(5,), R=2, constrained=(1, 0, 1))          # K = 1
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=8))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+    Z, G, _ = pg.config_script6(seed=4, sz=(7, 9, 1, 7, 5, 9, 6), R=2)                    # a 7 x 9 x 1 "tensor"
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=10))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
+def test_full_size_config2_properties(ab):
+    """BASELINE configs[1] at full size (1000^3, R=32, 1000 x 5000 matrix; tensor generated on device): properties that
+    need no oracle - the dimension-tree sweep equals the three-pass sweep, a fused-inner-loop run equals the plain one,
+    the objective decreases, and the run is bit-reproducible."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    from perf_probe import build
+    Z, G, facs = build(1000, 1000, 1000, 5000, 32)
+    runs = {}
+    for name, kw in (('tree', dict(dimtree=1)), ('three', dict(dimtree=0)), ('plain', dict(dimtree=1, fuse_inner=-1, graph=-1)),
+                     ('tree2', dict(dimtree=1))):
+        with ab.Solver(Z, [1.0, float(np.sum(Z['object'][1] ** 2))]) as s:
+            s.generate_cp_data(1, list(facs), 0.2, 99)
+            s.set_state(G)
+            out = s.run(pg.default_options(MaxOuterIters=6, graph=kw.pop('graph', 0), **dict(ZERO_TOL, **kw)))
+            runs[name] = (s.get_state(), out)
+    f = runs['tree'][1]['func_val_conv']
+    assert np.all(np.isfinite(f)) and f[-1] < 0.01 * f[0]     # (the random, unnormalised init makes the start erratic)
+    for other in ('three', 'plain'):
+        for m in range(5):
+            assert rel(runs[other][0]['fac'][m], runs['tree'][0]['fac'][m]) < 1e-10, (other, m)
+        assert np.max(np.abs(runs[other][1]['func_val_conv'] - f)) < 1e-12
+    for m in range(5):
+        assert np.array_equal(runs['tree2'][0]['fac'][m], runs['tree'][0]['fac'][m])      # deterministic reductions
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)
