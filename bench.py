@@ -277,6 +277,14 @@ def main():
         n3 = max(3, args.steps // 2)
         three_ms = timed_run(lambda it: dict(zero_tol_options(it), dimtree=0), n3)[0] / n3
 
+    # the opt-in reduced-precision MTTKRP (options.mttkrp_precision=1: TF32 operands, FP32 tile accumulation); reported
+    # beside the FP64 number, never as `value`
+    n32 = max(3, args.steps // 2)
+    tf32_ms, _, _, _, out32 = timed_run(lambda it: dict(zero_tol_options(it), mttkrp_precision=1), n32)
+    tf32_ms /= n32
+    tf32_mode_ms = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
+    solver.run(dict(zero_tol_options(1)))      # back to FP64 for the roofline timings below
+
     # ---- per-mode MTTKRP kernel times (CUDA events on the engine's stream) for the roofline ----
     flops_mode = 2.0 * I * J * Kloc * R
     bytes_mode = 8.0 * I * J * Kloc
@@ -373,6 +381,12 @@ def main():
                 'three_pass': ({'value': 1e3 / three_ms, 'ms_per_step': three_ms,
                                 'note': 'same step with options.dimtree=0: three independent tensor passes, the '
                                         "reference's flop and byte count"} if three_ms else None),
+                'tf32_opt_in': {'value': 1e3 / tf32_ms, 'ms_per_step': tf32_ms, 'mttkrp_ms_per_mode': tf32_mode_ms,
+                                'mttkrp_gbs': [bytes_mode / (t * 1e-3) / 1e9 for t in tf32_mode_ms],
+                                'final_f_tensors': out32['f_tensors'],
+                                'note': 'options.mttkrp_precision=1 (opt-in, not the parity mode): TF32 operands on '
+                                        'HMMA.1688.F32.TF32, FP32 accumulation per tile, FP64 across tiles; the pass '
+                                        'becomes HBM-bound'},
                 'final_f_tensors': out['f_tensors'],
                 'call_ms': call_ms,
                 'timing': 'CUDA events on the engine stream around exactly `steps` outer iterations (cmtf_fun_AOADMM.m:87-476), '

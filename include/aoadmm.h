@@ -146,7 +146,9 @@ typedef struct {
   int32_t has_increase_factor_rhoBk;
   double increase_factor_rhoBk;
   /* engine-only knobs (0 = default) */
-  int32_t mttkrp_precision;   /* 0: FP64 DMMA (default, the parity mode) */
+  int32_t mttkrp_precision;   /* 0: FP64 DMMA (default, the parity mode); 1: opt-in TF32 tensor cores for the tensor
+                                 MTTKRPs (inputs rounded to TF32, FP32 accumulate per tile, FP64 across tiles; ~1e-3
+                                 relative accuracy, the pass becomes HBM bound); everything else stays FP64 */
   int32_t dimtree;            /* 0: three independent MTTKRP passes (reference flop/byte count) */
   int32_t fuse_inner;         /* 0 (default): run the whole inner ADMM loop of a group in one cooperative launch when
                                  possible; -1: one launch per inner iteration; results are identical */
@@ -227,6 +229,10 @@ int aoadmm_generate_cp_data(aoadmm_handle *h, int32_t object, const double *cons
  * takes (dims of the leading modes x shard_extent, column-major, no padding).  bench.py uses it to obtain the
  * device-generated tensor as a HOST buffer for the end-to-end leg. */
 int aoadmm_get_object_data(aoadmm_handle *h, int32_t object, double *out, int64_t n_elements);
+/* MTTKRP of the resident CP object `object` in mode position `pos` (1-based) with the factors currently in the handle
+ * (cmtf_fun_AOADMM.m:97), at `precision` (0 FP64, 1 TF32 opt-in: see aoadmm_options.mttkrp_precision), summed over
+ * ranks; out: rows(mode) x R host buffer. */
+int aoadmm_object_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t precision, double *out);
 /* one timed MTTKRP of object `object` in mode position `pos` (1-based position inside the object)
  * using the factors currently resident in the handle; returns device milliseconds (CUDA events). */
 int aoadmm_time_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t reps, float *ms_out);

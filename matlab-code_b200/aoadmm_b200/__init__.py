@@ -385,7 +385,7 @@ class Solver:
         o.iter_start_PAR2Bkconstraint = int(options.get('iter_start_PAR2Bkconstraint', 0))
         o.has_increase_factor_rhoBk = int('increase_factor_rhoBk' in options)
         o.increase_factor_rhoBk = float(options.get('increase_factor_rhoBk', 1.0))
-        o.mttkrp_precision = 0
+        o.mttkrp_precision = int(options.get('mttkrp_precision', 0))
         o.dimtree = int(options.get('dimtree', 0))
         o.graph = int(options.get('graph', 0))
         o.fuse_inner = int(options.get('fuse_inner', 0))
@@ -423,6 +423,13 @@ class Solver:
         """This rank's slab of CP object `obj` (1-based) into the F-contiguous float64 array `out`."""
         assert out.dtype == np.float64 and out.flags['F_CONTIGUOUS']
         _capi.check(lib.aoadmm_get_object_data(self._h, obj, _dp(out), out.size), self._h)
+        return out
+
+    def object_mttkrp(self, obj, pos, precision=0):
+        """MTTKRP of resident CP object `obj` (1-based) in mode position `pos` with the current factors."""
+        m = self.Z['modes'][obj - 1][pos - 1]
+        out = np.zeros((int(self.Z['size'][m - 1]), int(self._infer_ranks(self.Z)[m - 1])), order='F')
+        _capi.check(lib.aoadmm_object_mttkrp(self._h, obj, pos, int(precision), _dp(out)), self._h)
         return out
 
     def time_mttkrp(self, obj, pos, reps=3):

@@ -134,6 +134,11 @@ int aoadmm_get_object_data(aoadmm_handle* h, int32_t object, double* out, int64_
   return guard(h, [&] { h->eng->object_to_host(object, out, n_elements); });
 }
 
+int aoadmm_object_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t precision, double* out) {
+  if (!h || !out || precision < 0 || precision > 1) return AOADMM_ERR_INVALID_ARG;
+  return guard(h, [&] { h->eng->mttkrp_to_host(object, pos, out, precision); });
+}
+
 int aoadmm_time_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t reps, float* ms_out) {
   if (!h || !ms_out) return AOADMM_ERR_INVALID_ARG;
   return guard(h, [&] { *ms_out = h->eng->time_mttkrp(object, pos, reps); });

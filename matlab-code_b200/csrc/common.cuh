@@ -84,6 +84,19 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+// D(16x8) += A(16x8) * B(8x8), TF32 inputs, FP32 accumulate (opt-in reduced-precision MTTKRP).  SASS: HMMA.1688.F32.TF32
+__device__ __forceinline__ void mma_tf32_1688(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a1,
+                                              uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3},{%4,%5,%6,%7},{%8,%9},{%0,%1,%2,%3};"
+               : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t f64_to_tf32(double x) {
+  uint32_t r;
+  const float f = (float)x;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));

@@ -755,7 +755,8 @@ void Engine::compute_mttkrp(ObjectState& o, int pos, double scale, double* out, 
   pack_operand(v, 1);
   phase_begin(o.order >= 3 ? 0 : 1);
   if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
-  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit);
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit,
+                       opt_.mttkrp_precision);
   if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
   phase_end();
 }
@@ -1849,14 +1850,22 @@ void Engine::object_to_host(int object, double* out, int64_t n_elements) {
                        cudaMemcpyDeviceToHost));
 }
 
-void Engine::mttkrp_to_host(int object, int pos, double* out) {
+void Engine::mttkrp_to_host(int object, int pos, double* out, int precision) {
   AO_CUDA(cudaSetDevice(device_));
   if (object < 1 || object > n_objects_) throw CudaError(1, "mttkrp: object out of range");
   ObjectState& o = objects_[object - 1];
   if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "mttkrp: not a CP object");
   if (pos < 1 || pos > o.order) throw CudaError(1, "mttkrp: position out of range");
   ModeState& m = mode(o.modes[pos - 1]);
-  compute_mttkrp(o, pos - 1, 1.0, m.A.p, m.rows);
+  const int saved = opt_.mttkrp_precision;
+  if (precision >= 0) opt_.mttkrp_precision = precision;
+  try {
+    compute_mttkrp(o, pos - 1, 1.0, m.A.p, m.rows);
+  } catch (...) {
+    opt_.mttkrp_precision = saved;
+    throw;
+  }
+  opt_.mttkrp_precision = saved;
   AO_CUDA(cudaMemcpyAsync(out, m.A.p, m.A.bytes(), cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
   phase_collect();
@@ -1876,10 +1885,11 @@ float Engine::time_mttkrp(int object, int pos, int reps) {
   AO_CUDA(cudaEventCreate(&a));
   AO_CUDA(cudaEventCreate(&b));
   const int R = m.R;
-  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr);  // warm-up
+  const int prec = opt_.mttkrp_precision;  // precision of the last aoadmm_run (0 before any run)
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, prec);  // warm-up
   AO_CUDA(cudaEventRecord(a, st_));
   for (int r = 0; r < reps; ++r)
-    launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr);
+    launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, prec);
   AO_CUDA(cudaEventRecord(b, st_));
   AO_CUDA(cudaEventSynchronize(b));
   float ms = 0.f;

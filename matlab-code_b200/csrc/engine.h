@@ -151,7 +151,7 @@ class Engine {
   void generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed);
   float time_mttkrp(int object, int pos, int reps);
   void object_to_host(int object, double* out, int64_t n_elements);
-  void mttkrp_to_host(int object, int pos, double* out);  // unweighted MTTKRP of the resident factors
+  void mttkrp_to_host(int object, int pos, double* out, int precision = -1);  // unweighted MTTKRP of the resident factors (-1: precision of the last run)
   int64_t launches() const { return launches_; }
   void phase_ms(double ms[3]);
   double last_run_ms() const { return last_run_ms_; }

@@ -60,7 +60,10 @@ struct Cfg {
 // LEAD kernel
 // grid: x = m tile (128 rows of i), y = split of the (k, j-tile) stage sequence, z = column chunk
 // ---------------------------------------------------------------------------------------------
-template <int NT, int WARPS_N>
+// PREC = 0: FP64 DMMA (the parity path).  PREC = 1 (opt-in, options.mttkrp_precision): the FP64 tiles are rounded to TF32
+// fragment by fragment and multiplied with mma.m16n8k8.tf32 (FP32 accumulate, flushed into the FP64 accumulators once per
+// stage): one TF32 MMA covers two 8-row m-tiles and two k4-steps of the FP64 fragment layout, so the data path is unchanged.
+template <int NT, int WARPS_N, int PREC>
 __global__ void __launch_bounds__(kThreads, 1)
 mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Ft_j,
                    const double* __restrict__ Ft_k, double* __restrict__ ws, int I, int J, int K, long long Jpad,
@@ -141,20 +144,56 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
     double ck[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) ck[nt] = lds_f64(cs + (wn * C::WN + 8 * nt + m) * 8);
+    if (PREC == 0) {
 #pragma unroll
-    for (int tt = 0; tt < TCOUNT; ++tt) {
-      const int t = t0 + tt;
-      const uint32_t rowoff = (uint32_t)(t * 512);        // 4 rows of 128 B per k4-step
-      const uint32_t flip = (uint32_t)((t & 1) << 6);     // (row & 4) toggles chunk bit 2
-      double a[4], b[NT];
+      for (int tt = 0; tt < TCOUNT; ++tt) {
+        const int t = t0 + tt;
+        const uint32_t rowoff = (uint32_t)(t * 512);        // 4 rows of 128 B per k4-step
+        const uint32_t flip = (uint32_t)((t & 1) << 6);     // (row & 4) toggles chunk bit 2
+        double a[4], b[NT];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(xs + abase[mi] + rowoff + (axor[mi] ^ flip));
+        for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(xs + abase[mi] + rowoff + (axor[mi] ^ flip));
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)) * ck[nt];
+        for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)) * ck[nt];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mi][nt][0], acc[mi][nt][1], a[mi], b[nt]);
+      }
+    } else {
+      float fa[4][NT][2];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mi][nt][0], acc[mi][nt][1], a[mi], b[nt]);
+        for (int nt = 0; nt < NT; ++nt) fa[mi][nt][0] = fa[mi][nt][1] = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < TCOUNT; tt += 2) {
+        uint32_t a[2][4], b[2][NT];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int t = t0 + tt + h;
+          const uint32_t rowoff = (uint32_t)(t * 512);
+          const uint32_t flip = (uint32_t)((t & 1) << 6);
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) a[h][mi] = f64_to_tf32(lds_f64(xs + abase[mi] + rowoff + (axor[mi] ^ flip)));
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+            b[h][nt] = f64_to_tf32(lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)) * ck[nt]);
+        }
+#pragma unroll
+        for (int mp = 0; mp < 4; mp += 2)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+            mma_tf32_1688(fa[mp][nt][0], fa[mp][nt][1], fa[mp + 1][nt][0], fa[mp + 1][nt][1], a[0][mp], a[0][mp + 1],
+                          a[1][mp], a[1][mp + 1], b[0][nt], b[1][nt]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          acc[mi][nt][0] += (double)fa[mi][nt][0];
+          acc[mi][nt][1] += (double)fa[mi][nt][1];
+        }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(sBar + (kStages + s) * 8);
@@ -206,7 +245,7 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
 // ---------------------------------------------------------------------------------------------
 // EMIT (epilogue 0 only): additionally stores the un-scaled partial contraction T(j,k,r) = sum_i X(i,j,k) Fi(i,r)
 //          to Tbuf[(k*Rp + r)*ldt + j]; a later mode-3 MTTKRP is then a cheap pass over T (dimension tree).
-template <int NT, int WARPS_N, int EPI, bool EMIT>
+template <int NT, int WARPS_N, int EPI, bool EMIT, int PREC>
 __global__ void __launch_bounds__(kThreads, 1)
 mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ Ft_i,
                     const double* __restrict__ Ft_e, double* __restrict__ ws, int I, int J, int K, long long Ipad,
@@ -258,11 +297,15 @@ mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __re
   const int m = lane >> 2, kk = lane & 3;
 
   double T[4][NT][2];
+  float Tf[4][NT][2];  // PREC == 1: FP32 accumulators of the TF32 MMAs for one (j tile, k) (I terms each)
   double O[4][NT][2];  // EPI 0: running output; EPI 1: the epilogue factor values Fe(j(mi,m), cols)
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < NT; ++b) T[a][b][0] = T[a][b][1] = O[a][b][0] = O[a][b][1] = 0.0;
+    for (int b = 0; b < NT; ++b) {
+      T[a][b][0] = T[a][b][1] = O[a][b][0] = O[a][b][1] = 0.0;
+      Tf[a][b][0] = Tf[a][b][1] = 0.f;
+    }
 
   uint32_t abase[4], arm[4];
   int jrow[4];
@@ -298,25 +341,58 @@ mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __re
       const uint32_t ph = (uint32_t)((ql / kStages) & 1);
       mbar_wait(sBar + s * 8, ph);
       const uint32_t xs = sX + s * kXBytes, fs = sF + s * C::FBYTES + boff;
+      if (PREC == 0) {
 #pragma unroll
-      for (int tt = 0; tt < TCOUNT; ++tt) {
-        const int t = t0 + tt;
-        const uint32_t box = (uint32_t)((t >> 2) * 16384);
-        const uint32_t ch = (uint32_t)(2 * (t & 3) + (kk >> 1));
-        double a[4], b[NT];
+        for (int tt = 0; tt < TCOUNT; ++tt) {
+          const int t = t0 + tt;
+          const uint32_t box = (uint32_t)((t >> 2) * 16384);
+          const uint32_t ch = (uint32_t)(2 * (t & 3) + (kk >> 1));
+          double a[4], b[NT];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(xs + box + abase[mi] + ((ch ^ arm[mi]) << 4));
+          for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(xs + box + abase[mi] + ((ch ^ arm[mi]) << 4));
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8));
+          for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8));
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+          for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) dmma884(T[mi][nt][0], T[mi][nt][1], a[mi], b[nt]);
+            for (int nt = 0; nt < NT; ++nt) dmma884(T[mi][nt][0], T[mi][nt][1], a[mi], b[nt]);
+        }
+      } else {
+#pragma unroll
+        for (int tt = 0; tt < TCOUNT; tt += 2) {
+          uint32_t a[2][4], b[2][NT];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int t = t0 + tt + h;
+            const uint32_t box = (uint32_t)((t >> 2) * 16384);
+            const uint32_t ch = (uint32_t)(2 * (t & 3) + (kk >> 1));
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[h][mi] = f64_to_tf32(lds_f64(xs + box + abase[mi] + ((ch ^ arm[mi]) << 4)));
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) b[h][nt] = f64_to_tf32(lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)));
+          }
+#pragma unroll
+          for (int mp = 0; mp < 4; mp += 2)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+              mma_tf32_1688(Tf[mp][nt][0], Tf[mp][nt][1], Tf[mp + 1][nt][0], Tf[mp + 1][nt][1], a[0][mp], a[0][mp + 1],
+                            a[1][mp], a[1][mp + 1], b[0][nt], b[1][nt]);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sBar + (kStages + s) * 8);
     }
     // ---- per-(j tile, k) epilogue
+    if (PREC == 1) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          T[mi][nt][0] = (double)Tf[mi][nt][0];
+          T[mi][nt][1] = (double)Tf[mi][nt][1];
+          Tf[mi][nt][0] = Tf[mi][nt][1] = 0.f;
+        }
+    }
     if (EPI == 0) {
       if (EMIT) {
         double* sc = reinterpret_cast<double*>(smem_raw + (sS - smem_u32(smem_raw)));
@@ -572,7 +648,7 @@ int choose_splits(long long tiles, long long max_splits) {
   return best;
 }
 
-template <int NT, int WARPS_N>
+template <int NT, int WARPS_N, int PREC>
 int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk, int R, double scale, double* out,
                 int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip) {
   using C = Cfg<NT, WARPS_N>;
@@ -582,7 +658,7 @@ int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk
   const int Rp_total = nchunk * C::NC;
   const long long ldo = round_up(t.I, 2);
   if ((size_t)nsplit * Rp_total * ldo * 8 > w.ws_bytes) throw CudaError(1, "mttkrp workspace too small (lead)");
-  auto kern = mttkrp_lead_kernel<NT, WARPS_N>;
+  auto kern = mttkrp_lead_kernel<NT, WARPS_N, PREC>;
   static bool attr_done = false;
   if (!attr_done) {
     AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -598,7 +674,7 @@ int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk
   return 2;
 }
 
-template <int NT, int WARPS_N, int EPI, bool EMIT>
+template <int NT, int WARPS_N, int EPI, bool EMIT, int PREC>
 int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& fe, int R, double scale, double* out,
                  int64_t ldout, const MttkrpWorkspace& w, double* Tbuf, cudaStream_t st, const int* skip) {
   using C = Cfg<NT, WARPS_N>;
@@ -609,7 +685,7 @@ int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& f
   const long long ldo = round_up(rows, 2);
   const int nparts = (EPI == 0) ? nsplit : jtiles;
   if ((size_t)nparts * Rp_total * ldo * 8 > w.ws_bytes) throw CudaError(1, "mttkrp workspace too small (inner)");
-  auto kern = mttkrp_inner_kernel<NT, WARPS_N, EPI, EMIT>;
+  auto kern = mttkrp_inner_kernel<NT, WARPS_N, EPI, EMIT, PREC>;
   static bool attr_done = false;
   if (!attr_done) {
     AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -703,23 +779,31 @@ int mttkrp3_from_T(const Tensor3& t, const double* Tbuf, int R, const double* Fj
 }
 
 int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFactor& f1, int R, double scale,
-            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip, double* Tbuf) {
+            double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip, double* Tbuf,
+            int precision) {
   const int NC = mttkrp_chunk_cols(R);
   if (f0.NC != NC || f1.NC != NC || f0.R != R || f1.R != R) throw CudaError(1, "packed factor / rank mismatch");
-#define AO_DISPATCH(NT, WNN)                                                                                       \
-  do {                                                                                                             \
-    if (pos == 0) return launch_lead<NT, WNN>(t, f0, f1, R, scale, out, ldout, w, st, skip);                       \
-    if (pos == 1 && Tbuf != nullptr)                                                                               \
-      return launch_inner<NT, WNN, 0, true>(t, f0, f1, R, scale, out, ldout, w, Tbuf, st, skip);                   \
-    if (pos == 1) return launch_inner<NT, WNN, 0, false>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);   \
-    return launch_inner<NT, WNN, 1, false>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);                 \
+#define AO_DISPATCH_P(NT, WNN, P)                                                                                     \
+  do {                                                                                                                \
+    if (pos == 0) return launch_lead<NT, WNN, P>(t, f0, f1, R, scale, out, ldout, w, st, skip);                       \
+    if (pos == 1 && Tbuf != nullptr)                                                                                  \
+      return launch_inner<NT, WNN, 0, true, P>(t, f0, f1, R, scale, out, ldout, w, Tbuf, st, skip);                   \
+    if (pos == 1) return launch_inner<NT, WNN, 0, false, P>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);   \
+    return launch_inner<NT, WNN, 1, false, P>(t, f0, f1, R, scale, out, ldout, w, nullptr, st, skip);                 \
   } while (0)
+#define AO_DISPATCH(NT, WNN)                 \
+  do {                                       \
+    if (precision == 1) AO_DISPATCH_P(NT, WNN, 1); \
+    AO_DISPATCH_P(NT, WNN, 0);               \
+  } while (0)
+  if (precision != 0 && precision != 1) throw CudaError(2, "mttkrp_precision: 0 (FP64) or 1 (TF32 opt-in)");
   switch (NC) {
     case 8: AO_DISPATCH(1, 1);
     case 16: AO_DISPATCH(2, 1);
     case 32: AO_DISPATCH(4, 1);
     default: AO_DISPATCH(4, 2);
   }
+#undef AO_DISPATCH_P
 #undef AO_DISPATCH
 }
 

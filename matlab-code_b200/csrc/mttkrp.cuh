@@ -62,7 +62,7 @@ size_t mttkrp_workspace_bytes(const Tensor3& t, int R);
 // (mttkrp_T_bytes bytes) for a later mttkrp3_from_T (dimension-tree reuse: one tensor pass serves modes 2 and 3).
 int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFactor& f1, int R, double scale,
             double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip,
-            double* Tbuf = nullptr);
+            double* Tbuf = nullptr, int precision = 0);  // precision 1: opt-in TF32 tensor-core path (FP32 accumulate)
 size_t mttkrp_T_bytes(const Tensor3& t, int R);
 // out(k,r) = scale * sum_j T(j,k,r) * Fj(j,r)   (Fj: J x R column-major, leading dimension ldf)
 int mttkrp3_from_T(const Tensor3& t, const double* Tbuf, int R, const double* Fj, int64_t ldf, double scale,

@@ -521,6 +521,39 @@ def test_full_size_config2_properties(ab):
         assert np.array_equal(runs['tree2'][0]['fac'][m], runs['tree'][0]['fac'][m])      # deterministic reductions
 
 
+@pytest.mark.parametrize('dims', [(130, 90, 70, 200, 8), (96, 80, 72, 120, 32), (129, 257, 65, 64, 64), (40, 36, 30, 64, 100)])
+def test_opt_in_tf32_mttkrp_mode(ab, dims):
+    """options.mttkrp_precision = 1 (north_star: TF32 opt-in): the tensor MTTKRPs round their operands to TF32 and
+    accumulate in FP32 per tile; everything else stays FP64.  Not a parity mode: the kernel must match the FP64 MTTKRP
+    to TF32 accuracy (2^-11 per operand), the run must track the FP64 run and still be deterministic."""
+    Z, G, _ = pg.config_cp_matrix(*dims, seed=5)
+    zn = pg.znorm_const(Z)
+    with ab.Solver(ab._with_rank(Z, G), zn) as s:
+        s.set_state(G)
+        for pos in (1, 2, 3):
+            M64, M32 = s.object_mttkrp(1, pos, 0), s.object_mttkrp(1, pos, 1)
+            others = [G['fac'][q] for q in range(3) if q != pos - 1]
+            ref = np.einsum('ijk,jr,kr->ir', np.moveaxis(Z['object'][0], pos - 1, 0), *others)
+            assert rel(M64, ref) < 1e-13
+            # error scale: products of three TF32-rounded numbers, summed with random signs
+            bound = np.einsum('ijk,jr,kr->ir', np.abs(np.moveaxis(Z['object'][0], pos - 1, 0)), *[np.abs(u) for u in others])
+            assert 1e-8 < np.max(np.abs(M32 - ref) / bound) < 3 * 2.0 ** -11, (pos, np.max(np.abs(M32 - ref) / bound))
+    opts = pg.default_options(MaxOuterIters=8, **ZERO_TOL)
+    G64, o64 = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts)
+    G32, o32 = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, dict(opts, mttkrp_precision=1))
+    G32b, _ = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, dict(opts, mttkrp_precision=1, dimtree=1))
+    # over-factored cases (R close to a dimension) amplify the perturbation through the ill-conditioned Grams
+    ftol = 2e-2 if dims[4] <= 32 else 0.3
+    for m in range(5):
+        assert 1e-9 < rel(G32['fac'][m], G64['fac'][m]) < ftol, (m, rel(G32['fac'][m], G64['fac'][m]))
+        assert rel(G32b['fac'][m], G64['fac'][m]) < ftol
+    assert np.max(np.abs(o32['func_val_conv'] - o64['func_val_conv']) / o64['func_val_conv']) < 5e-2
+    G32c, _ = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, dict(opts, mttkrp_precision=1))
+    assert all(np.array_equal(G32c['fac'][m], G32['fac'][m]) for m in range(5))
+    with pytest.raises(ab.AoadmmError):
+        ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, dict(opts, mttkrp_precision=7))
+
+
 def test_warm_restart_equals_continuous_run(ab):
     """checkpoint/resume of the reference = pass Fac back as 'init' (cmtf_AOADMM.m:15,:44-45)."""
     Z, G, _ = pg.config_cp_matrix(30, 24, 20, 40, 4, seed=11)

@@ -34,6 +34,11 @@ if __name__ == '__main__':
     s.set_state(G)
     print('setup %.2fs' % (time.time() - t))
     flops = 2.0 * I * J * K * R; bytes_ = 8.0 * I * J * K
+    prec = int(os.environ.get('PROBE_PREC', '0'))   # 1: opt-in TF32 MTTKRP
+    if prec:
+        s.run(dict(MaxOuterIters=1, MaxInnerIters=1, AbsFuncTol=0, OuterRelTol=0, innerRelPrTol_coupl=0, innerRelPrTol_constr=0,
+                   innerRelDualTol_coupl=0, innerRelDualTol_constr=0, mttkrp_precision=prec))
+        s.set_state(G)
     for pos in (1, 2, 3):
         ms = s.time_mttkrp(1, pos, 5)
         print('mttkrp mode %d: %.3f ms  %.2f TFLOP/s  %.1f GB/s' % (pos, ms, flops / ms * 1e-9, bytes_ / ms * 1e-6))
@@ -41,7 +46,7 @@ if __name__ == '__main__':
         ms = s.time_mttkrp(2, pos, 5)
         print('matrix mode %d: %.3f ms' % (pos, ms))
     opts = dict(MaxOuterIters=3, MaxInnerIters=5, AbsFuncTol=0, OuterRelTol=0, innerRelPrTol_coupl=0, innerRelPrTol_constr=0,
-                innerRelDualTol_coupl=0, innerRelDualTol_constr=0)
+                innerRelDualTol_coupl=0, innerRelDualTol_constr=0, mttkrp_precision=prec, dimtree=int(os.environ.get('PROBE_DIMTREE', '0')))
     s.run(opts)
     opts['MaxOuterIters'] = iters
     l0 = s.launch_count(); p0 = s.phase_ms().copy()
