@@ -229,6 +229,15 @@ int aoadmm_generate_cp_data(aoadmm_handle *h, int32_t object, const double *cons
  * takes (dims of the leading modes x shard_extent, column-major, no padding).  bench.py uses it to obtain the
  * device-generated tensor as a HOST buffer for the end-to-end leg. */
 int aoadmm_get_object_data(aoadmm_handle *h, int32_t object, double *out, int64_t n_elements);
+/* Leading eigenvectors for the 'nvecs' initialisation (cmtf_nvecs.m:33-58; init_coupled_AOADMM_CMTF.m:50-69):
+ * out (rows x r, column-major host buffer) = eigs(Y, r, 'LM') with Y = X_(mode) X_(mode)' of the first object that
+ * contains global mode id `mode` (1-based), computed from the data resident in the handle.  PARAFAC2 objects: mode A uses
+ * the slices side by side, a B_k mode needs `slice` (1-based; Y = X_k' X_k), mode C is ones in the reference and is
+ * refused.  slice = 0 otherwise.  Columns come in descending eigenvalue order, each signed so that its entry of
+ * largest magnitude is positive (eigs leaves the sign open).  info (may be NULL): [0] subspace iterations,
+ * [1] max ||Y u - theta u|| / theta_1 over the returned pairs.  With more than one GPU the sharded (last) mode of a
+ * tensor returns AOADMM_ERR_UNSUPPORTED. */
+int aoadmm_nvecs(aoadmm_handle *h, int32_t mode, int32_t slice, int32_t r, double *out, int64_t rows, double *info);
 /* MTTKRP of the resident CP object `object` in mode position `pos` (1-based) with the factors currently in the handle
  * (cmtf_fun_AOADMM.m:97), at `precision` (0 FP64, 1 TF32 opt-in: see aoadmm_options.mttkrp_precision), summed over
  * ranks; out: rows(mode) x R host buffer. */

@@ -20,7 +20,8 @@ import numpy as np
 from . import _capi
 from ._capi import AoadmmError, lib
 
-__all__ = ['cmtf_fun_AOADMM', 'cmtf_AOADMM', 'Solver', 'AoadmmError', 'mttkrp', 'prox', 'chol_solve', 'gram',
+__all__ = ['cmtf_fun_AOADMM', 'cmtf_AOADMM', 'cmtf_nvecs', 'init_coupled_AOADMM_CMTF', 'Solver', 'AoadmmError', 'mttkrp',
+           'prox', 'chol_solve', 'gram',
            'shard_range', 'device_count', 'nccl_unique_id']
 
 
@@ -425,6 +426,23 @@ class Solver:
         _capi.check(lib.aoadmm_get_object_data(self._h, obj, _dp(out), out.size), self._h)
         return out
 
+    def nvecs(self, mode, r, slice=0, return_info=False):
+        """cmtf_nvecs(Z,n,r) (cmtf_nvecs.m:33-58) on the resident data: r leading eigenvectors of X_(n) X_(n)'.
+        `mode` is the 1-based global mode id; `slice` (1-based) selects B_k of a PARAFAC2 object."""
+        if not 1 <= mode <= len(self.Z['size']):
+            raise AoadmmError(1, 'nvecs: mode out of range')
+        s = self.Z['size'][mode - 1]
+        if isinstance(s, (list, tuple, np.ndarray)):
+            if not 1 <= slice <= len(s):
+                raise AoadmmError(1, 'nvecs: a PARAFAC2 B_k mode needs slice = 1..K')
+            rows = int(s[slice - 1])
+        else:
+            rows = int(s)
+        out = np.zeros((rows, int(r)), order='F')
+        info = np.zeros(2)
+        _capi.check(lib.aoadmm_nvecs(self._h, int(mode), int(slice), int(r), _dp(out), rows, _dp(info)), self._h)
+        return (out, {'iterations': int(info[0]), 'residual': float(info[1])}) if return_info else out
+
     def object_mttkrp(self, obj, pos, precision=0):
         """MTTKRP of resident CP object `obj` (1-based) in mode position `pos` with the current factors."""
         m = self.Z['modes'][obj - 1][pos - 1]
@@ -483,12 +501,19 @@ def cmtf_fun_AOADMM(Z, Znorm_const, G, fh=None, gh=None, lscalar=None, uscalar=N
     return Gout, out
 
 
-def cmtf_AOADMM(Z, init, alg_options, **dist):
+def cmtf_AOADMM(Z, init, alg_options, init_options=None, **dist):
     """[Zhat,Fac,G,out] = cmtf_AOADMM(Z,'init',G,'alg_options',options)  (cmtf_AOADMM.m:1-207), Frobenius loss.
+    init: the state struct G, or 'random' together with init_options (:44-53).
 
     The front end only computes Znorm_const (:124-156) and packs Zhat (:197-206); constraints stay named specs
     because the device cannot call MATLAB/Python function handles ('custom' -> AoadmmError UNSUPPORTED)."""
     P = len(Z['object'])
+    if isinstance(init, str):                                              # :44-53
+        if init.lower() != 'random':
+            raise ValueError('Initialization type not supported')
+        if not init_options:
+            raise ValueError('init_options are missing as input in cmtf_AOADMM.')
+        init = init_coupled_AOADMM_CMTF(Z, init_options, **dist)
     for p in range(P):                                                     # :55-65 PARAFAC2 rank check
         if Z['model'][p] == 'PAR2':
             R = init['fac'][Z['modes'][p][0] - 1].shape[1]
@@ -554,3 +579,131 @@ def gram(F, device=0):
     out = np.zeros((Ff.shape[1], Ff.shape[1]), order='F')
     _capi.check(lib.aoadmm_gram(_dp(Ff), Ff.shape[0], Ff.shape[1], _dp(out), device))
     return out
+
+
+# ---- initialisation front end (the caller side of the boundary) -------------------
+def cmtf_nvecs(Z, n, r, solver=None, **dist):
+    """U = cmtf_nvecs(Z,n,r)  (cmtf_nvecs.m:33-58): r leading eigenvectors of X_(n) X_(n)', computed on the device from
+    the tensor resident in `solver` (or in a temporary handle), so a large tensor never has to be unfolded on the host."""
+    if solver is not None:
+        return solver.nvecs(n, r)
+    P = len(Z['object'])
+    with Solver(dict(Z, rank=[int(r)] * P), [float('nan')] * P, **dist) as s:
+        return s.nvecs(n, r)
+
+
+def init_coupled_AOADMM_CMTF(Z, init_options, rng=None, Delta=None, **dist):
+    """G = init_coupled_AOADMM_CMTF(Z,'init_options',init_options)  (init_coupled_AOADMM_CMTF.m:37-169).
+
+    init_options: 'lambdas_init' (per object, its length is the rank), 'distr' (per mode, callable (rows, cols) ->
+    array, the @(x,y) rand(x,y) handles of the example scripts), 'normalize', 'nvecs'.  With nvecs the factors are the
+    leading eigenvectors of X_(n) X_(n)' (:50-69), computed on the device; constraint factors go through the device
+    prox (:99-124); duals and coupling factors are uniform random (:126-169) from `rng` (numpy RandomState)."""
+    rng = rng if rng is not None else np.random.RandomState()
+    sz, modes, model = Z['size'], Z['modes'], Z['model']
+    lambdas, distr = init_options['lambdas_init'], init_options['distr']
+    normalize, use_nvecs = bool(init_options.get('normalize', 0)), bool(init_options.get('nvecs', 0))
+    lin = list(Z['coupling']['lin_coupled_modes'])
+    ctype = list(Z['coupling'].get('coupling_type', []))
+    trafo = Z['coupling'].get('coupl_trafo_matrices') or [None] * len(sz)
+    constrained, constraints = Z['constrained_modes'], Z['constraints']
+    P, nb_modes = len(modes), len(sz)
+    if max(max(m) for m in modes) != nb_modes:
+        raise ValueError('Mismatch between size and modes inputs')                       # :33-35
+    nb_c = max(lin) if lin else 0
+    G = {'fac': [None] * nb_modes, 'coupling_fac': [None] * nb_c, 'constraint_fac': [None] * nb_modes,
+         'coupling_dual_fac': [None] * nb_modes, 'constraint_dual_fac': [None] * nb_modes,
+         'P': [None] * P, 'DeltaB': [None] * P, 'mu_DeltaB': [None] * P}
+
+    def normcols(M):
+        return M / np.sqrt(np.sum(M * M, axis=0))[None, :]
+
+    def rows_of(n):
+        return int(sz[n - 1])
+
+    solver = None
+    try:
+        if use_nvecs:
+            solver = Solver(dict(Z, rank=[len(l) for l in lambdas]), [float('nan')] * P, **dist)
+        for p in range(P):
+            R = len(lambdas[p])
+            for n in modes[p]:
+                pos = list(modes[p]).index(n)
+                par2_b = model[p] == 'PAR2' and pos == 1
+                if par2_b:
+                    K = len(sz[n - 1])
+                    G['DeltaB'][p] = rng.rand(R, R)
+                    G['P'][p] = [np.eye(int(sz[n - 1][k]), R) for k in range(K)]
+                    facs, mus = [], []
+                    for k in range(K):
+                        jk = int(sz[n - 1][k])
+                        if use_nvecs:
+                            Fk = solver.nvecs(n, R, slice=k + 1)                        # :61-66
+                        else:
+                            Fk = np.asarray(distr[n - 1](jk, R), dtype=np.float64)
+                            if normalize:
+                                Fk = normcols(Fk)
+                        mus.append(rng.rand(jk, R))
+                        facs.append(Fk)
+                    G['fac'][n - 1], G['mu_DeltaB'][p] = facs, mus
+                elif use_nvecs:
+                    if model[p] == 'PAR2' and pos == 2:
+                        G['fac'][n - 1] = np.ones((rows_of(n), R))                       # :68
+                    else:
+                        G['fac'][n - 1] = solver.nvecs(n, R)                             # :52, :55-60
+                else:
+                    F = np.asarray(distr[n - 1](rows_of(n), R), dtype=np.float64)
+                    G['fac'][n - 1] = normcols(F) if normalize else F
+    finally:
+        if solver is not None:
+            solver.close()
+    for p in range(P):                                                                    # :99-124
+        for n in modes[p]:
+            if not constrained[n - 1]:
+                continue
+            if not constraints[n - 1]:
+                raise ValueError('No constraint provided for mode %d.' % n)
+            name = constraints[n - 1][0]
+            if model[p] == 'PAR2' and list(modes[p]).index(n) == 1:
+                zs, ds = [], []
+                for Fk in G['fac'][n - 1]:
+                    Zk = np.asarray(distr[n - 1](*Fk.shape), dtype=np.float64)
+                    if name != 'tPARAFAC2':
+                        Zk = prox(constraints[n - 1], Zk, 1.0, device=dist.get('device', 0))
+                    zs.append(Zk)
+                    ds.append(rng.rand(*Fk.shape))
+                G['constraint_fac'][n - 1], G['constraint_dual_fac'][n - 1] = zs, ds
+            else:
+                if name == 'tPARAFAC2':
+                    raise ValueError('The tPARAFAC2 constraint can only be imposed on the second mode of a PARAFAC2 model')
+                F = G['fac'][n - 1]
+                Zc = np.asarray(distr[n - 1](*F.shape), dtype=np.float64)
+                G['constraint_fac'][n - 1] = prox(constraints[n - 1], Zc, 1.0, device=dist.get('device', 0))
+                G['constraint_dual_fac'][n - 1] = rng.rand(*F.shape)
+    for c in range(1, nb_c + 1):                                                          # :126-169
+        cmodes = [m for m in range(1, nb_modes + 1) if lin[m - 1] == c]
+        F1, H1 = G['fac'][cmodes[0] - 1], trafo[cmodes[0] - 1]
+        ct = ctype[c - 1]
+        if ct == 0:
+            shape = F1.shape
+        elif ct == 1:
+            shape = (np.shape(H1)[0], F1.shape[1])
+        elif ct == 2:
+            shape = (F1.shape[0], np.shape(H1)[1])
+        elif ct == 3:
+            shape = (np.shape(H1)[1], F1.shape[1])
+        elif ct == 4:
+            shape = (F1.shape[0], np.shape(H1)[0])
+        elif ct == 5:
+            shape = np.shape(Delta[c - 1])
+        else:
+            raise ValueError('coupling type %r' % (ct,))
+        G['coupling_fac'][c - 1] = rng.rand(*shape)
+        for m in cmodes:
+            if ct in (0, 1, 2):
+                G['coupling_dual_fac'][m - 1] = rng.rand(*shape)
+            elif ct in (3, 4):
+                G['coupling_dual_fac'][m - 1] = rng.rand(*G['fac'][m - 1].shape)
+            else:
+                G['coupling_dual_fac'][m - 1] = rng.rand(shape[0], G['fac'][m - 1].shape[1])
+    return G

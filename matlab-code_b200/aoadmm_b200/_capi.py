@@ -89,7 +89,7 @@ HandleP = C.c_void_p
 EXPORTS = ['aoadmm_abi_version', 'aoadmm_device_count', 'aoadmm_nccl_unique_id', 'aoadmm_create', 'aoadmm_destroy',
            'aoadmm_last_error', 'aoadmm_set_state', 'aoadmm_get_state', 'aoadmm_run', 'aoadmm_mttkrp', 'aoadmm_prox',
            'aoadmm_chol_solve', 'aoadmm_gram', 'aoadmm_generate_cp_data', 'aoadmm_time_mttkrp', 'aoadmm_launch_count',
-           'aoadmm_phase_ms', 'aoadmm_last_run_ms', 'aoadmm_get_object_data', 'aoadmm_last_loop_ms', 'aoadmm_object_mttkrp']
+           'aoadmm_phase_ms', 'aoadmm_last_run_ms', 'aoadmm_get_object_data', 'aoadmm_last_loop_ms', 'aoadmm_object_mttkrp', 'aoadmm_nvecs']
 
 lib.aoadmm_abi_version.restype = C.c_int
 lib.aoadmm_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -109,6 +109,7 @@ lib.aoadmm_gram.argtypes = [c_double_p, C.c_int64, C.c_int32, c_double_p, C.c_in
 lib.aoadmm_generate_cp_data.argtypes = [HandleP, C.c_int32, C.POINTER(c_double_p), C.c_double, C.c_uint64]
 lib.aoadmm_time_mttkrp.argtypes = [HandleP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
 lib.aoadmm_object_mttkrp.argtypes = [HandleP, C.c_int32, C.c_int32, C.c_int32, c_double_p]
+lib.aoadmm_nvecs.argtypes = [HandleP, C.c_int32, C.c_int32, C.c_int32, c_double_p, C.c_int64, c_double_p]
 lib.aoadmm_launch_count.argtypes = [HandleP, C.POINTER(C.c_int64)]
 lib.aoadmm_phase_ms.argtypes = [HandleP, c_double_p]
 lib.aoadmm_last_run_ms.argtypes = [HandleP, c_double_p]

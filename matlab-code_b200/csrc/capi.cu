@@ -134,6 +134,11 @@ int aoadmm_get_object_data(aoadmm_handle* h, int32_t object, double* out, int64_
   return guard(h, [&] { h->eng->object_to_host(object, out, n_elements); });
 }
 
+int aoadmm_nvecs(aoadmm_handle* h, int32_t mode, int32_t slice, int32_t r, double* out, int64_t rows, double* info) {
+  if (!h || !out || r < 1 || rows < 1) return AOADMM_ERR_INVALID_ARG;
+  return guard(h, [&] { h->eng->nvecs_to_host(mode, slice, r, out, rows, info); });
+}
+
 int aoadmm_object_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t precision, double* out) {
   if (!h || !out || precision < 0 || precision > 1) return AOADMM_ERR_INVALID_ARG;
   return guard(h, [&] { h->eng->mttkrp_to_host(object, pos, out, precision); });

@@ -1850,6 +1850,105 @@ void Engine::object_to_host(int object, double* out, int64_t n_elements) {
                        cudaMemcpyDeviceToHost));
 }
 
+void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t rows, double* info) {
+  AO_CUDA(cudaSetDevice(device_));
+  if (mode_id < 1 || mode_id > nb_modes_) throw CudaError(1, "nvecs: mode out of range");
+  // the first object that contains the mode (cmtf_nvecs.m:36-51)
+  int p = -1, pos = -1;
+  for (int q = 0; q < n_objects_ && p < 0; ++q)
+    for (int d = 0; d < objects_[q].order; ++d)
+      if (objects_[q].modes[d] == mode_id) {
+        p = q;
+        pos = d;
+        break;
+      }
+  if (p < 0) throw CudaError(1, "nvecs: no object contains this mode");
+  ObjectState& o = objects_[p];
+  UnfoldSpec s;
+  bool reduce_over_ranks = false;
+  if (o.model == AOADMM_MODEL_CP) {
+    if (slice != 0) throw CudaError(1, "nvecs: slice given for a CP mode");
+    if (o.sharded && pos == o.order - 1)
+      throw CudaError(2, "nvecs of the sharded (last) mode of a tensor is not supported with more than one GPU");
+    const View3& v = o.views[pos];
+    const Tensor3& t = v.t;
+    s.X = t.X;
+    if (v.kernel_pos == 0) {
+      s.layout = 0;
+      s.n = t.I;
+      s.ld = t.ldI;
+      s.ncols = t.J * t.K;
+    } else if (v.kernel_pos == 1) {
+      s.layout = 1;
+      s.n = t.J;
+      s.I = t.I;
+      s.cs = t.ldI;
+      s.bs = t.ldI * t.J;
+      s.nb = t.K;
+    } else {
+      s.layout = 1;
+      s.n = t.K;
+      s.I = t.I;
+      s.cs = t.ldI * t.J;
+      s.bs = t.ldI;
+      s.nb = t.J;
+    }
+    reduce_over_ranks = o.sharded;
+  } else {
+    Par2State* ps = nullptr;
+    for (auto& c : par2_)
+      if (c.p == p) ps = &c;
+    if (ps == nullptr) throw CudaError(1, "nvecs: PARAFAC2 state missing");
+    if (pos == 0) {          // init_coupled_AOADMM_CMTF.m:55-60: slices side by side
+      if (slice != 0) throw CudaError(1, "nvecs: slice given for PARAFAC2 mode A");
+      s.X = ps->X;
+      s.layout = 0;
+      s.n = ps->I;
+      s.ld = ps->ldX;
+      s.ncols = ps->Jtot;
+    } else if (pos == 1) {   // :61-66: X_k' X_k
+      if (slice < 1 || slice > ps->K) throw CudaError(1, "nvecs: PARAFAC2 slice out of range");
+      s.X = ps->X + ps->joff[slice - 1] * ps->ldX;
+      s.layout = 1;
+      s.n = ps->joff[slice] - ps->joff[slice - 1];
+      s.I = ps->I;
+      s.cs = ps->ldX;
+      s.bs = 0;
+      s.nb = 1;
+    } else {
+      throw CudaError(1, "nvecs: PARAFAC2 mode C is initialised with ones (init_coupled_AOADMM_CMTF.m:68)");
+    }
+  }
+  if (rows != s.n) throw CudaError(1, "nvecs: output rows do not match the mode size");
+  if (r < 1 || r > s.n) throw CudaError(1, "nvecs: the number of vectors must be between 1 and the mode size");
+  double *Y = nullptr, *work = nullptr, *U = nullptr;
+  const size_t nn = (size_t)s.n * (size_t)s.n;
+  try {
+    AO_CUDA(cudaMalloc(&Y, std::max<size_t>(nn * sizeof(double), 256)));
+    AO_CUDA(cudaMalloc(&work, std::max<size_t>(unfold_gram_workspace(s) * sizeof(double), 256)));
+    AO_CUDA(cudaMalloc(&U, std::max<size_t>((size_t)s.n * r * sizeof(double), 256)));
+    launches_ += unfold_gram(s, Y, work, st_);
+    if (reduce_over_ranks) allreduce(Y, nn);
+    std::vector<double> theta(r);
+    const EigInfo ei = top_eigvecs(Y, s.n, r, U, theta.data(), st_);
+    launches_ += ei.launches;
+    if (info != nullptr) {
+      info[0] = ei.iterations;
+      info[1] = ei.residual;
+    }
+    AO_CUDA(cudaMemcpyAsync(out, U, (size_t)s.n * r * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    AO_CUDA(cudaStreamSynchronize(st_));
+  } catch (...) {
+    cudaFree(Y);
+    cudaFree(work);
+    cudaFree(U);
+    throw;
+  }
+  cudaFree(Y);
+  cudaFree(work);
+  cudaFree(U);
+}
+
 void Engine::mttkrp_to_host(int object, int pos, double* out, int precision) {
   AO_CUDA(cudaSetDevice(device_));
   if (object < 1 || object > n_objects_) throw CudaError(1, "mttkrp: object out of range");

@@ -170,8 +170,37 @@ def add_missing(Z, frac=0.2, seed=0, objects=None):
     return Z
 
 
+def _leading_eigvecs(Y, r):
+    """[U,~] = eigs(Y, r, 'LM') for a symmetric positive semi-definite Y: eigenvectors of the r largest eigenvalues in
+    descending order.  eigs leaves the sign of a vector open; it is fixed here (entry of largest magnitude positive,
+    first one on ties) so that results can be compared."""
+    w, V = np.linalg.eigh((Y + Y.T) * 0.5)
+    idx = np.argsort(-w, kind='stable')[:r]
+    U = V[:, idx].copy()
+    for c in range(U.shape[1]):
+        i = int(np.argmax(np.abs(U[:, c])))
+        if U[i, c] < 0:
+            U[:, c] = -U[:, c]
+    return U, w[idx]
+
+
+def cmtf_nvecs(Z, n, r):
+    """cmtf_nvecs.m:33-58: A = mode-n unfolding of the first object containing mode n (objects sharing the mode id
+    are concatenated, :36-51 -- mode ids are unique per object in this framework); Y = A*A' (:55); eigs(Y,r,'LM') (:57)."""
+    blocks = []
+    for p, ms in enumerate(Z['modes']):
+        if n in ms:
+            if Z['model'][p] != 'CP':
+                raise ValueError('cmtf_nvecs works on CP objects (double(Z.object{p}) at cmtf_nvecs.m:44-48)')
+            i = list(ms).index(n)
+            X = np.asarray(Z['object'][p], dtype=np.float64)
+            blocks.append(np.moveaxis(X, i, 0).reshape(X.shape[i], -1, order='F'))
+    A = np.concatenate(blocks, axis=1)
+    return _leading_eigvecs(A @ A.T, r)[0]
+
+
 def init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=None):
-    """init_coupled_AOADMM_CMTF.m:37-169 with nvecs = 0."""
+    """init_coupled_AOADMM_CMTF.m:37-169 (init_options['nvecs']: :50-69)."""
     sz = Z['size']
     lambdas = init_options['lambdas_init']
     distr = init_options['distr']
@@ -193,9 +222,27 @@ def init_coupled_AOADMM_CMTF(Z, init_options, rng, Delta=None):
     def normcols(M):
         return M / np.sqrt(np.sum(M * M, axis=0))[None, :]
 
+    nvecs = bool(init_options.get('nvecs', 0))
     for p in range(P):
         R = len(lambdas[p])
         for n in modes[p]:
+            if nvecs:                                                   # :50-69
+                if model[p] == 'CP':
+                    G['fac'][n - 1] = cmtf_nvecs(Z, n, R)
+                elif modes[p].index(n) == 0:
+                    M = np.concatenate([np.asarray(Xk) for Xk in Z['object'][p]], axis=1)
+                    G['fac'][n - 1] = _leading_eigvecs(M @ M.T, R)[0]
+                elif modes[p].index(n) == 1:
+                    G['DeltaB'][p] = rng.rand(R, R)
+                    G['fac'][n - 1], G['P'][p], G['mu_DeltaB'][p] = [], [], []
+                    for k in range(len(sz[n - 1])):
+                        Xk = np.asarray(Z['object'][p][k])
+                        G['fac'][n - 1].append(_leading_eigvecs(Xk.T @ Xk, R)[0])
+                        G['P'][p].append(np.eye(int(sz[n - 1][k]), R))
+                        G['mu_DeltaB'][p].append(rng.rand(int(sz[n - 1][k]), R))
+                else:
+                    G['fac'][n - 1] = np.ones((_size1(sz[n - 1]), R))
+                continue
             if model[p] == 'PAR2' and modes[p].index(n) == 1:
                 G['DeltaB'][p] = rng.rand(R, R)
                 G['fac'][n - 1] = []

@@ -26,6 +26,8 @@ mxLogical* mxGetLogicals(const mxArray*);
 int mexCallMATLAB(int nlhs, mxArray* plhs[], int nrhs, mxArray* prhs[], const char* name);
 size_t mxGetNumberOfElements(const mxArray*);
 size_t mxGetM(const mxArray*);
+mwSize mxGetNumberOfDimensions(const mxArray*);
+const mwSize* mxGetDimensions(const mxArray*);
 size_t mxGetN(const mxArray*);
 void mxSetN(mxArray*, mwSize);
 double mxGetScalar(const mxArray*);

@@ -126,12 +126,15 @@ def test_mex_gateway_compiles_against_stub_mex_header():
     declarations-only mex.h, and must bind only symbols that include/aoadmm.h declares."""
     import re
     import subprocess
-    src = os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'aoadmm_mex.cpp')
-    subprocess.check_call(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-I', os.path.join(ROOT, 'tests', 'stubs'),
-                           '-I', os.path.join(ROOT, 'include'), src])
     header = open(os.path.join(ROOT, 'include', 'aoadmm.h')).read()
     declared = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', header))
-    used = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', open(src).read())) - {'aoadmm_mex'}
-    assert used and used <= declared, used - declared
+    for name in ('aoadmm_mex.cpp', 'aoadmm_nvecs_mex.cpp'):
+        src = os.path.join(ROOT, 'matlab-code_b200', 'matlab', name)
+        subprocess.check_call(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-I', os.path.join(ROOT, 'tests', 'stubs'),
+                               '-I', os.path.join(ROOT, 'include'), src])
+        used = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', open(src).read())) - {'aoadmm_mex', 'aoadmm_nvecs_mex'}
+        assert used and used <= declared, used - declared
+    nv = open(os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'cmtf_nvecs.m')).read()
+    assert nv.startswith('function U = cmtf_nvecs(Z,n,r)')
     shim = open(os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'cmtf_fun_AOADMM.m')).read()
     assert shim.startswith('function [G,out] = cmtf_fun_AOADMM(Z,Znorm_const,G,fh,gh,lscalar,uscalar,options)')

@@ -595,3 +595,97 @@ def test_solver_reports_launches_and_times(ab):
         assert out['OuterIterations'] == 3
         assert s.launch_count() > 50 and s.last_run_ms() > 0
         assert s.time_mttkrp(1, 2, 2) > 0
+
+
+# ---- nvecs initialisation on the device (cmtf_nvecs.m, init_coupled_AOADMM_CMTF.m:50-69) ----------------
+def _nvecs_close(Ud, Uo, Z=None, n=None, tol=1e-8):
+    """Columns agree to `tol`, loosened by the conditioning of the eigenvector (rounding level / relative gap to the
+    nearest other eigenvalue) when the unfolding is available."""
+    assert Ud.shape == Uo.shape
+    assert np.linalg.norm(Ud.T @ Ud - np.eye(Ud.shape[1])) < 1e-12          # orthonormal columns
+    tols = np.full(Ud.shape[1], tol)
+    if Z is not None:
+        p = [q for q, ms in enumerate(Z['modes']) if n in ms][0]
+        X = np.asarray(Z['object'][p])
+        i = list(Z['modes'][p]).index(n)
+        A = np.moveaxis(X, i, 0).reshape(X.shape[i], -1, order='F')
+        w = np.sort(np.linalg.eigvalsh(A @ A.T))[::-1]
+        for c in range(Ud.shape[1]):
+            gap = min(abs(w[c] - w[d]) for d in range(len(w)) if d != c) if len(w) > 1 else w[0]
+            tols[c] += 2e-13 * w[0] / max(gap, 1e-300)
+    for c in range(Ud.shape[1]):
+        assert np.linalg.norm(Ud[:, c] - Uo[:, c]) < tols[c], (c, np.linalg.norm(Ud[:, c] - Uo[:, c]), tols[c])
+
+
+@pytest.mark.parametrize('shape,R', [((30, 20, 25), 3), ((33, 65, 17), 4), ((130, 90, 70), 5), ((300, 40, 9), 6),
+                                     ((8, 9, 10), 8), ((7, 6, 5, 4), 2), ((20, 12, 6, 10, 5), 3), ((64, 50), 4),
+                                     ((131, 259), 7)])
+def test_nvecs_matches_oracle_every_mode(ab, shape, R):
+    """Leading eigenvectors of X_(n) X_(n)' from the resident object, every mode position of 2..5-way objects (odd
+    sizes: padded leading dimension, partial tiles), against numpy eigh of the explicit unfolding."""
+    rng = np.random.RandomState(3)
+    N = len(shape)
+    facs = [rng.rand(s, R) * (1.0 + np.arange(R))[None, :] for s in shape]
+    X = np.einsum(','.join(chr(97 + d) + 'r' for d in range(N)) + '->' + ''.join(chr(97 + d) for d in range(N)), *facs)
+    X = X + 0.2 * np.linalg.norm(X) / np.sqrt(X.size) * rng.randn(*shape)
+    Z = {'loss_function': ['Frobenius'], 'model': ['CP'], 'modes': [list(range(1, N + 1))], 'size': list(shape),
+         'coupling': {'lin_coupled_modes': [0] * N, 'coupling_type': [], 'coupl_trafo_matrices': [None] * N},
+         'constrained_modes': [0] * N, 'constraints': [None] * N, 'weights': [1.0], 'object': [X]}
+    with ab.Solver(dict(Z, rank=[R]), [float('nan')]) as s:
+        for n in range(1, N + 1):
+            Ud, info = s.nvecs(n, min(R, shape[n - 1]), return_info=True)
+            _nvecs_close(Ud, pg.cmtf_nvecs(Z, n, min(R, shape[n - 1])), Z, n)
+            assert info['residual'] < 1e-12 and info['iterations'] < 3000, info
+        with pytest.raises(ab.AoadmmError):
+            s.nvecs(1, shape[0] + 1)
+        with pytest.raises(ab.AoadmmError):
+            s.nvecs(N + 1, 1)
+    assert rel(ab.cmtf_nvecs(Z, 2, 2), pg.cmtf_nvecs(Z, 2, 2)) < 1e-8
+
+
+def test_nvecs_rank_deficient_data(ab):
+    """Noise-free rank-3 tensor: Y has 3 non-zero eigenvalues, the oversampled block of the subspace iteration is rank
+    deficient.  The three vectors must span the range of the true factor."""
+    rng = np.random.RandomState(11)
+    A, B, Cc = rng.rand(90, 3), rng.rand(40, 3), rng.rand(50, 3)
+    X = np.einsum('ir,jr,kr->ijk', A, B, Cc)
+    Z = {'loss_function': ['Frobenius'], 'model': ['CP'], 'modes': [[1, 2, 3]], 'size': [90, 40, 50],
+         'coupling': {'lin_coupled_modes': [0, 0, 0], 'coupling_type': [], 'coupl_trafo_matrices': [None] * 3},
+         'constrained_modes': [0, 0, 0], 'constraints': [None] * 3, 'weights': [1.0], 'object': [X]}
+    for n, F in ((1, A), (2, B), (3, Cc)):
+        U = ab.cmtf_nvecs(Z, n, 3)
+        _nvecs_close(U, pg.cmtf_nvecs(Z, n, 3))
+        assert np.linalg.norm(F - U @ (U.T @ F)) < 1e-10 * np.linalg.norm(F)
+
+
+@pytest.mark.parametrize('nvecs', [0, 1])
+def test_init_front_end_matches_oracle(ab, nvecs):
+    """init_coupled_AOADMM_CMTF mirror of the product package (device nvecs + device prox) against the oracle's, same
+    random stream; then the solver started from the device-made state tracks the oracle run."""
+    Z, _, _ = pg.config_cp_par2(seed=4, noise=0.1)
+    R = 3
+    r1, r2 = np.random.RandomState(21), np.random.RandomState(21)
+    distr_o = [pg.d_rand] * len(Z['size'])
+    distr_d = [lambda a, b: r1.rand(a, b)] * len(Z['size'])
+    io = {'lambdas_init': [[1.0] * R] * 2, 'nvecs': nvecs, 'normalize': 1}
+    Gd = ab.init_coupled_AOADMM_CMTF(Z, dict(io, distr=distr_d), rng=r1)
+    Go = pg.init_coupled_AOADMM_CMTF(Z, dict(io, distr=distr_o), r2)
+    assert_state_close(Gd, Go, keys=('fac', 'constraint_fac', 'constraint_dual_fac', 'coupling_dual_fac', 'coupling_fac',
+                                     'P', 'DeltaB', 'mu_DeltaB'))
+    opts = pg.default_options(MaxOuterIters=5, **ZERO_TOL)
+    _, Fd, _, od = ab.cmtf_AOADMM(Z, Gd, opts)
+    Fo, oo = oracle_solve(Z, pg.znorm_const(Z), Go, options=opts)
+    assert_state_close(Fd, Fo, tol=1e-7)
+    assert abs(od['f_tensors'] - oo['f_tensors']) <= 1e-8 * abs(oo['f_tensors'])
+    with pytest.raises(ValueError):
+        ab.cmtf_AOADMM(Z, 'random', opts)
+    _, _, _, o2 = ab.cmtf_AOADMM(Z, 'random', opts, init_options=dict(io, distr=distr_d))
+    assert np.isfinite(o2['f_tensors'])
+
+
+def test_nvecs_medium_size_uses_large_tiles(ab):
+    """700 x 300 x 40: 128-wide Gram tiles with a partial last tile, split reduction; and the matrix modes."""
+    Z, G, _ = pg.config_cp_matrix(700, 300, 40, 500, 6, seed=8)
+    with ab.Solver(ab._with_rank(Z, G), pg.znorm_const(Z)) as s:
+        for n in (1, 2, 3, 4, 5):
+            _nvecs_close(s.nvecs(n, 6), pg.cmtf_nvecs(Z, n, 6), Z, n)

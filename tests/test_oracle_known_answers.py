@@ -248,3 +248,28 @@ def test_oracle_recovers_the_references_own_ground_truth_script11():
     # and the committed oracle state is reproducible
     Go30, oo30 = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=mk.script11_options(30))
     assert rel(Go30['fac'][0], fx['oracle_A']) < 1e-9 and rel(oo30['func_val_conv'], fx['oracle_func_val']) < 1e-10
+
+
+def test_oracle_nvecs_known_answers():
+    """cmtf_nvecs.m:33-58 restatement: (i) equals the left singular vectors of the explicit unfolding, (ii) spans the
+    range of the true factor for noise-free low-rank data, (iii) the nvecs branch of the init (:50-69) gives
+    orthonormal factors, ones for PARAFAC2 mode C."""
+    rng = np.random.RandomState(0)
+    A, B, C = rng.rand(12, 3), rng.rand(9, 3), rng.rand(7, 3)
+    X = np.einsum('ir,jr,kr->ijk', A, B, C)
+    Z = {'model': ['CP'], 'modes': [[1, 2, 3]], 'size': [12, 9, 7], 'object': [X]}
+    for n, F in ((1, A), (2, B), (3, C)):
+        U = pg.cmtf_nvecs(Z, n, 3)
+        Xn = np.moveaxis(X, n - 1, 0).reshape(X.shape[n - 1], -1, order='F')
+        Us = np.linalg.svd(Xn, full_matrices=False)[0][:, :3]
+        assert np.allclose(np.abs(U.T @ Us), np.eye(3), atol=1e-8)
+        assert np.linalg.norm(F - U @ (U.T @ F)) < 1e-10
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-12)
+    Zp, _, _ = pg.config_cp_par2(seed=1, noise=0.05)
+    io = {'lambdas_init': [[1.0] * 3] * 2, 'nvecs': 1, 'distr': [pg.d_rand] * len(Zp['size']), 'normalize': 1}
+    G = pg.init_coupled_AOADMM_CMTF(Zp, io, np.random.RandomState(2))
+    pm = Zp['modes'][1]
+    assert np.allclose(G['fac'][pm[2] - 1], 1.0)
+    for Fk in G['fac'][pm[1] - 1]:
+        assert np.allclose(Fk.T @ Fk, np.eye(3), atol=1e-12)
+    assert np.allclose(G['fac'][pm[0] - 1].T @ G['fac'][pm[0] - 1], np.eye(3), atol=1e-12)
