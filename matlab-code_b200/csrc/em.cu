@@ -160,6 +160,20 @@ __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, 
   if (threadIdx.x == 0) *out = v;
 }
 
+__global__ void em_khatri_rao_kernel(KrArgs a, double* __restrict__ out, long long K, int R) {
+  const long long n = K * R;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    long long k = idx % K;
+    const long long r = idx / K;
+    double v = 1.0;
+    for (int q = 0; q < a.n; ++q) {
+      v *= a.F[q][k % a.d[q] + r * a.ld[q]];
+      k /= a.d[q];
+    }
+    out[idx] = v;
+  }
+}
+
 void em_grid(const EmArgs& a, dim3& grid, int& kper) {
   const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTile);
   // enough CTAs for a few waves of 148 SMs, but several k per CTA so that the Fj tile is reused
@@ -190,6 +204,14 @@ int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
   em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
   AO_CHECK_LAUNCH();
   return 2;
+}
+
+int em_khatri_rao(const KrArgs& a, double* out, long long K, int R, cudaStream_t st) {
+  if (K <= 0) return 0;
+  const unsigned blocks = (unsigned)std::min<long long>(ceil_div(K * R, 256), 148 * 8);
+  em_khatri_rao_kernel<<<blocks, 256, 0, st>>>(a, out, K, R);
+  AO_CHECK_LAUNCH();
+  return 1;
 }
 
 int object_norm2(const double* X, const uint8_t* mask, long long I, long long ld, long long slab, double* partials,

@@ -21,6 +21,17 @@ struct EmArgs {
   double* partials;        // >= em_partials_doubles(args)
 };
 
+// Khatri-Rao product of the trailing factors of an N-way (N > 3) object, first factor fastest:
+//   out(k, r) = prod_q F_q(k_q, r),  k = k_0 + d_0*(k_1 + d_1*(...)),  out: K x R (ld = K), K = prod d_q
+// so that the object can be treated as I x J x K by em_pass (the merged index is exactly the memory order).
+struct KrArgs {
+  int n;                   // number of factors (<= 6)
+  const double* F[6];
+  long long ld[6];
+  long long d[6];
+};
+int em_khatri_rao(const KrArgs& a, double* out, long long K, int R, cudaStream_t st);
+
 size_t em_partials_doubles(const EmArgs& a);
 // sums_out[0..4] = sum_missing (m-x)^2, sum_missing x^2, sum_observed x*m, sum_observed m^2, sum_observed (x-m)^2
 int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st);

@@ -344,7 +344,7 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
       AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
                            cudaMemcpyHostToDevice));
     if (src.miss != nullptr) {  // Z.miss{p} (cmtf_AOADMM.m:68-121)
-      if (o.order > 3) throw CudaError(2, "missing data is supported for matrices and 3-way tensors on device");
+      if (o.order > 8) throw CudaError(2, "missing data is supported for objects with up to 8 modes");
       if (src.data == nullptr) throw CudaError(1, "Z.miss without data");
       const size_t mbytes = std::max<size_t>((size_t)o.ld0 * slab, 256);
       AO_CUDA(cudaMalloc(&o.mask, mbytes));
@@ -525,7 +525,11 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
         if (o.mask == nullptr) continue;
         a.I = o.dims[0];
         a.J = o.dims[1];
-        a.K = o.order >= 3 ? (int)o.dims[2] : 1;
+        long long kk = 1;
+        for (int d = 2; d < o.order; ++d) kk *= o.dims[d];
+        if (kk > 0x7fffffffLL) throw CudaError(2, "missing data: trailing extent too large");
+        a.K = (int)kk;
+        if (o.order > 3) AO_CUDA(cudaMalloc(&o.em_kr, std::max<size_t>((size_t)kk * a.R * sizeof(double), 256)));
       }
       need = std::max(need, em_partials_doubles(a));
     }
@@ -564,6 +568,7 @@ Engine::~Engine() {
     if (o.data) cudaFree(o.data);
     if (o.Tbuf) cudaFree(o.Tbuf);
     if (o.mask) cudaFree(o.mask);
+    if (o.em_kr) cudaFree(o.em_kr);
     for (auto& v : o.views) {
       if (v.f0_own) packed_factor_free(v.f0);
       if (v.f1_own) packed_factor_free(v.f1);
@@ -1209,7 +1214,23 @@ void Engine::em_step(bool impute) {
       a.ldFi = m0.rows;
       a.Fj = m1.fac.p;
       a.ldFj = m1.rows;
-      if (o.order >= 3) {
+      if (o.order > 3) {
+        // trailing modes merged: K = prod dims[2..], third factor = their Khatri-Rao product (memory order)
+        KrArgs kr{};
+        kr.n = o.order - 2;
+        long long kk = 1;
+        for (int d = 2; d < o.order; ++d) {
+          ModeState& md = mode(o.modes[d]);
+          kr.F[d - 2] = md.fac.p + (d == o.order - 1 ? o.shard_offset : 0);
+          kr.ld[d - 2] = md.rows;
+          kr.d[d - 2] = o.dims[d];
+          kk *= o.dims[d];
+        }
+        launches_ += em_khatri_rao(kr, o.em_kr, kk, a.R, st_);
+        a.K = (int)kk;
+        a.Fk = o.em_kr;
+        a.ldFk = kk;
+      } else if (o.order == 3) {
         ModeState& m2 = mode(o.modes[2]);
         a.K = (int)o.dims[2];
         a.Fk = m2.fac.p + o.shard_offset;  // this rank's rows of the (possibly sharded) last mode

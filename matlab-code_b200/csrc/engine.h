@@ -138,6 +138,7 @@ struct ObjectState {
   std::vector<View3> views;   // one per mode position
   int last_m = 0;             // global id of the mode updated last in a sweep (static)
   uint8_t* mask = nullptr;    // Z.miss{p}: 1 = observed, 0 = missing, same indexing as data (nullptr: complete data)
+  double* em_kr = nullptr;    // masked objects of order > 3: Khatri-Rao product of the factors of modes 3..N
   double* Tbuf = nullptr;     // dimension tree: T(j,k,r) = sum_i X(i,j,k) F1(i,r), emitted by the mode-2 MTTKRP
   uint64_t T_version = 0;     // version of the mode-1 factor T was computed from (0 = invalid)
 };

@@ -11,11 +11,11 @@ namespace aoadmm {
 namespace {
 
 constexpr int kBK = 16;      // reduction depth of one pipeline stage
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 8 : 0;   // src-size 0: nothing is read, the 8 bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+// 16-byte asynchronous copy of two doubles; only the first `bytes` (0, 8 or 16) are read, the rest is zero-filled
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -45,20 +45,22 @@ __device__ __forceinline__ void load_tile(const GramArgs& g, uint32_t dst, long 
   if (L == 0) {
     const long long c0 = chunk * kBK;
 #pragma unroll 4
-    for (int p = tid; p < BMT * kBK; p += 256) {
-      const int kk = p / BMT, a = p % BMT;
-      const bool ok = (a0 + a < s.n) && (c0 + kk < s.ncols);
-      const double* src = ok ? s.X + (a0 + a) + s.ld * (c0 + kk) : s.X;
-      cp_async8(dst + (uint32_t)(kk * G::pitch + a) * 8u, src, ok);
+    for (int p = tid; p < (BMT / 2) * kBK; p += 256) {
+      const int kk = p / (BMT / 2), a = 2 * (p % (BMT / 2));
+      const long long left = s.n - (a0 + a);
+      const int bytes = (c0 + kk < s.ncols && left > 0) ? (left > 1 ? 16 : 8) : 0;
+      const double* src = bytes ? s.X + (a0 + a) + s.ld * (c0 + kk) : s.X;
+      cp_async16(dst + (uint32_t)(kk * G::pitch + a) * 8u, src, bytes);
     }
   } else {
     const long long b = chunk / g.cpi, i0 = (chunk % g.cpi) * kBK;
 #pragma unroll 4
-    for (int p = tid; p < BMT * kBK; p += 256) {
-      const int a = p / kBK, kk = p % kBK;
-      const bool ok = (a0 + a < s.n) && (i0 + kk < s.I);
-      const double* src = ok ? s.X + (i0 + kk) + s.cs * (a0 + a) + s.bs * b : s.X;
-      cp_async8(dst + (uint32_t)(a * G::pitch + kk) * 8u, src, ok);
+    for (int p = tid; p < BMT * (kBK / 2); p += 256) {
+      const int a = p / (kBK / 2), kk = 2 * (p % (kBK / 2));
+      const long long left = s.I - (i0 + kk);
+      const int bytes = (a0 + a < s.n && left > 0) ? (left > 1 ? 16 : 8) : 0;
+      const double* src = bytes ? s.X + (i0 + kk) + s.cs * (a0 + a) + s.bs * b : s.X;
+      cp_async16(dst + (uint32_t)(a * G::pitch + kk) * 8u, src, bytes);
     }
   }
 }
@@ -290,6 +292,9 @@ size_t unfold_gram_workspace(const UnfoldSpec& s) {
 
 int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st) {
   if (s.n <= 0) return 0;
+  // the operand tiles are fetched in 16-byte pieces: base and all strides must keep pairs of doubles aligned
+  if ((reinterpret_cast<uintptr_t>(s.X) & 15) != 0 || (s.layout == 0 ? (s.ld & 1) : ((s.cs | s.bs) & 1)) != 0)
+    throw CudaError(1, "nvecs: object storage must be 16-byte aligned with an even leading dimension");
   const GramPlan p = plan_gram(s);
   GramArgs g{};
   g.s = s;

@@ -18,6 +18,7 @@ namespace aoadmm {
 // Which elements form the unfolding.  layout 0 ("NT"): A(a, c) = X[a + ld*c], a < n, c < ncols (mode is the
 // contiguous one).  layout 1 ("TN"): A(a, (i,b)) = X[i + cs*a + bs*b], i < I, b < nb (reduction over the contiguous
 // index i and a batch index b).
+// X must be 16-byte aligned and ld / cs / bs even (the engine pads every leading dimension to an even length).
 struct UnfoldSpec {
   const double* X = nullptr;
   int layout = 0;

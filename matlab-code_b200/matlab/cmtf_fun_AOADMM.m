@@ -9,7 +9,7 @@ function [G,out] = cmtf_fun_AOADMM(Z,Znorm_const,G,fh,gh,lscalar,uscalar,options
 % the user script, constraints_to_prox and init_coupled_AOADMM_CMTF still run in MATLAB (cmtf_AOADMM.m:30-53).
 %
 % fh, gh, lscalar, uscalar are [] for the Frobenius loss (cmtf_AOADMM.m:158-161) and are not used.  Problems the device
-% engine does not cover ('custom' constraints, non-Frobenius losses, masks on tensors of order > 3) raise the MATLAB error
+% engine does not cover ('custom' constraints, non-Frobenius losses) raise the MATLAB error
 % 'aoadmm:unsupported' (there is deliberately no CPU fallback: remove this directory from the path to run the
 % reference's MATLAB solver).
     [G,out] = aoadmm_mex(Z, Znorm_const, G, options);

@@ -404,6 +404,19 @@ def test_em_imputation_cp_and_matrix(ab, frac):
     assert_state_close(Gd, Go)
 
 
+@pytest.mark.parametrize('sz', [(11, 9, 7, 6), (8, 7, 5, 4, 3)])
+def test_em_imputation_higher_order_tensors(ab, sz):
+    """Z.miss on 4- and 5-way CP tensors: the trailing modes are merged and their Khatri-Rao product is the third
+    factor of the EM pass."""
+    nn = ('non-negativity',)
+    Z, G, _ = pg.config_single_cp(sz=sz, R=3, seed=9, noise=0.05, constraints=[nn] + [None] * (len(sz) - 1))
+    Zm = pg.add_missing(Z, 0.3, seed=4)
+    Go, oo, Gd, od = _both(ab, Zm, G, pg.default_options(MaxOuterIters=12, **ZERO_TOL))
+    _assert_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
 def test_em_imputation_cp_coupled_with_parafac2(ab):
     """example_script12_CP_PAR2_EM.m: ~20 % missing in the CP block and in every PARAFAC2 slice (:1249-1252)."""
     Z, G, _ = pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=4, noise=0.05)
