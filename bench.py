@@ -341,11 +341,15 @@ def main():
         s2 = ab.Solver(Zh, zn, rank=rank, world_size=world, device=local_rank, unique_id=uid2, shard=[(lo, hi), None])
         if host is None:
             s2.generate_cp_data(1, facs, 0.2, 20261018)
+        t1 = time.perf_counter()
         s2.set_state(G)
+        t2 = time.perf_counter()
         o2 = s2.run(zero_tol_options(args.steps))
+        t3 = time.perf_counter()
         G2 = s2.get_state()
         barrier()
         e2e_s = time.perf_counter() - t0
+        e2e_parts = {'create_s': t1 - t0, 'set_state_s': t2 - t1, 'run_s': t3 - t2, 'get_state_s': t0 + e2e_s - t3}
         s2.close()
         assert o2['OuterIterations'] == args.steps and np.isfinite(o2['f_tensors'])
         tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
@@ -357,6 +361,7 @@ def main():
         h2d = state_bytes + Z['object'][1].nbytes + (8.0 * n_loc if host is not None else sum(f.nbytes for f in facs))
         e2e = {'value': args.steps / e2e_s, 'unit': 'outer_iters/s', 'h2d_bytes_per_step': h2d / args.steps,
                'd2h_bytes_per_step': state_bytes / args.steps, 'seconds': e2e_s, 'host_tensor': how or 'none',
+               'parts_rank0': e2e_parts,
                'note': ('one cmtf_fun_AOADMM call of %d outer iterations through the C ABI, host wall clock, max over ranks: '
                         'create (tensor slab %.1f GB + matrix host->device from %s host memory) + set_state + run + get_state '
                         '+ destroy; the solver is iterative, so the data cross PCIe once per call, not once per step'
