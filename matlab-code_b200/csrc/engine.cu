@@ -340,9 +340,14 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     const size_t bytes = std::max<size_t>((size_t)o.ld0 * slab * sizeof(double), 256);
     AO_CUDA(cudaMalloc(&o.data, bytes));
     if (o.ld0 != o.dims[0] || src.data == nullptr) AO_CUDA(cudaMemset(o.data, 0, bytes));
-    if (src.data != nullptr && slab > 0)
-      AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
-                           cudaMemcpyHostToDevice));
+    if (src.data != nullptr && slab > 0) {
+      // no padding: one linear copy (a pitched copy of narrow rows runs at ~2/3 of the PCIe rate, profiles/r01_h2d_probe.log)
+      if (o.ld0 == o.dims[0])
+        AO_CUDA(cudaMemcpy(o.data, src.data, (size_t)o.dims[0] * slab * 8, cudaMemcpyHostToDevice));
+      else
+        AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
+                             cudaMemcpyHostToDevice));
+    }
     if (src.miss != nullptr) {  // Z.miss{p} (cmtf_AOADMM.m:68-121)
       if (o.order > 8) throw CudaError(2, "missing data is supported for objects with up to 8 modes");
       if (src.data == nullptr) throw CudaError(1, "Z.miss without data");
@@ -946,7 +951,7 @@ void Engine::apply_bsum(ModeState& m) {
 }
 
 // first PARAFAC2 mode (:159-178): A = w * sum_k X_k B_k diag(c_k),  C = sum_k diag(c_k) B_k'B_k diag(c_k)
-void Engine::par2_precompute_A(ModeState& m, int n_rho_terms) {
+void Engine::par2_precompute_A(ModeState& m, int n_rho_terms, bool do_chol) {
   Par2State& s = par2_[m.par2];
   ObjectState& o = objects_[m.p];
   ModeState &mb = mode(s.m2), &mc = mode(s.m3);
@@ -960,7 +965,7 @@ void Engine::par2_precompute_A(ModeState& m, int n_rho_terms) {
   PrepArgs a{};
   a.nhad = 1;
   a.had[0] = s.Csum;
-  fill_prep(m, a, n_rho_terms, true);
+  fill_prep(m, a, n_rho_terms, do_chol);
   launches_ += prep_system(a, st_, nullptr);
   apply_bsum(m);
 }
@@ -1585,7 +1590,13 @@ void Engine::sweep(int iter, std::vector<int>& inner_fixed) {
         if (m.par2_role != 0) {                                    // :157-250
           const int nterms = (coupl_id == 0) ? (m.constrained ? 1 : 0) : 1 + (m.constrained ? 1 : 0);
           if (m.par2_role == 1) {
-            par2_precompute_A(m, nterms);
+            // :159-178, then the generic (non-third-mode) branches of the coupled precompute (:269-273, :288-294,
+            // :314-318, :336-340, :358-362, :377-383): the first PARAFAC2 mode behaves like a CP mode there
+            const int ct = (coupl_id == 0) ? 0 : coupling_type_[coupl_id - 1];
+            const int con = m.constrained ? 1 : 0;
+            if (coupl_id == 0 || ct == 0 || ct == 3 || ct == 4) par2_precompute_A(m, nterms, true);
+            else if (ct == 2) par2_precompute_A(m, con, true);
+            else par2_precompute_A(m, 0, false);
             if (coupl_id == 0) {
               if (!m.constrained) {
                 launches_ += ls_solve(m.A.p, m.rows, m.L.p, m.invdiag, m.fac.p, m.rows, m.rows, m.R, m.ctl, st_, nullptr);  // :181

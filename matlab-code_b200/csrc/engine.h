@@ -198,7 +198,7 @@ class Engine {
   // PARAFAC2 block (cmtf_fun_AOADMM.m:157-250, :509-589)
   void setup_par2(const aoadmm_problem* prob, int p);
   void par2_update_T(Par2State& s);
-  void par2_precompute_A(ModeState& m, int n_rho_terms);
+  void par2_precompute_A(ModeState& m, int n_rho_terms, bool do_chol = true);
   void par2_update_B(ModeState& m, int outer_iter);
   void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out = nullptr);
   void par2_refresh_gram(Par2State& s);

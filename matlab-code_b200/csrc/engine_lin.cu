@@ -41,9 +41,12 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
   for (auto& m : modes_) {
     if (m.coupling != c) continue;
     const bool par2c = (m.par2_role == 3 && ctype == 1);  // example_script14: H C = Delta with C of a PARAFAC2 model
-    if (m.par2_role != 0 && !par2c)
-      throw CudaError(2, "PARAFAC2 modes inside a linearly coupled group are supported for coupling type 1 and the third "
-                         "PARAFAC2 mode only (coupling types 2..5 with PARAFAC2 modes are not supported on device)");
+    // the first PARAFAC2 mode goes through the generic branches of :278-389 like a CP mode; the second one cannot be
+    // coupled (:191); the third one has its own (K*R)^2 system for type 1 and per-slice Delta updates for types 4/5
+    if (m.par2_role == 2) throw CudaError(1, "the second PARAFAC2 mode cannot be coupled");
+    if (m.par2_role == 3 && !par2c)
+      throw CudaError(2, "the third PARAFAC2 mode inside a linearly coupled group is supported for coupling type 1 only "
+                         "(coupling types 2..5 are not supported on device)");
     const int i = m.id - 1;
     if (prob->trafo == nullptr || prob->trafo[i] == nullptr)
       throw CudaError(1, "coupl_trafo_matrices{" + std::to_string(m.id) + "} is required for coupling type " + std::to_string(ctype));

@@ -484,6 +484,9 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
     if second == 'matrix':
         sz = [I1, 14, 12, I4, 18]
         modes = [[1, 2, 3], [4, 5]]
+    elif second == 'par2':       # the first (A) mode of a PARAFAC2 object takes the place of the second tensor's mode
+        sz = [I1, 14, 12, I4, [11] * 7, 7]
+        modes = [[1, 2, 3], [4, 5, 6]]
     else:
         sz = [I1, 14, 12, I4, 11, 9]
         modes = [[1, 2, 3], [4, 5, 6]]
@@ -501,9 +504,13 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
         coupling['coupl_trafo_matrices2'] = trafo2
     lambdas = [[1.0] * R1, [1.0] * R2]
     distr = [d_rand] * nm
-    model = ['CP', 'CP']
+    model = ['CP', 'PAR2' if second == 'par2' else 'CP']
     Delta_shapes = None
-    if ctype == 5:
+    if ctype == 5 and second == 'par2':
+        Delta_shapes = [rng.rand(20, 4)]
+        free = {'lin_coupled_modes': [0] * nm, 'coupling_type': [], 'coupl_trafo_matrices': [None] * nm}
+        X, _, _ = create_coupled_data(model, sz, modes, lambdas, [noise] * 2, free, 0, distr, rng)
+    elif ctype == 5:
         # ground truth: Delta (q1 x q2); F1 = Delta H2_1 (H1_1 = I); rows of F4 picked by H1_4 equal Delta H2_4
         Delta = rng.rand(20, 4)
         A = [None] * nm
@@ -524,7 +531,7 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
     cm = [0] * nm
     cons = [None] * nm
     if constrained:
-        for m in (1, 4, 5):
+        for m in ((1, 4, 6) if second == 'par2' else (1, 4, 5)):
             cm[m - 1] = 1
             cons[m - 1] = nn
     Z = {'loss_function': ['Frobenius'] * 2, 'model': model, 'modes': modes, 'size': sz, 'coupling': coupling,

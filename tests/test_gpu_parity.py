@@ -380,6 +380,17 @@ def test_linear_couplings_two_tensors_zero_tolerances(ab, ctype):
     assert_state_close(Gd, Go)
 
 
+@pytest.mark.parametrize('ctype', [1, 2, 3, 4, 5])
+@pytest.mark.parametrize('constrained', [True, False])
+def test_linear_couplings_with_first_parafac2_mode(ab, ctype, constrained):
+    """A CP mode linearly coupled (types 1..5) with the first (A) mode of a PARAFAC2 object: A{m}, B{m} come from
+    :159-178, the coupled precompute and ADMM loops treat the mode like a CP mode (generic branches of :278-389)."""
+    Z, G, _ = pg.config_linear_coupling(ctype, seed=20 + ctype, constrained=constrained, second='par2')
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=12))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def _assert_missing_close(od, oo):
     n = oo['OuterIterations'] + 1
     a, b = od['func_rel_missing'][1:n], oo['func_rel_missing'][1:n]

@@ -1,1 +1,1 @@
-timeout 1200 python bench.py > gpurun_out/bench_c3k1024_v6.json 2> gpurun_out/bench_c3k1024_v6.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_c3k1024_v6.err
+timeout 900 python -m pytest tests -m gpu -q -k "linear_coupl or script14 or par2" 2>&1 | tail -25
