@@ -97,6 +97,16 @@ __device__ __forceinline__ uint32_t f64_to_tf32(double x) {
   asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
   return r;
 }
+__device__ __forceinline__ uint32_t f32_to_tf32(float f) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));

@@ -165,13 +165,26 @@ __global__ void gen_cp_kernel(GenArgs g, double* __restrict__ X, uint64_t seed, 
   if (pass == 2) return;
   s0 = block_sum(s0, red);
   s1 = block_sum(s1, red);
+  // per-CTA partials, summed in CTA order by gen_sum_kernel: the generated tensor is bit-reproducible
   if (threadIdx.x == 0) {
-    if (pass == 0) {
-      atomicAdd(&sums[0], s0);
-      atomicAdd(&sums[1], s1);
-    } else {
-      atomicAdd(&sums[2], s0);
-    }
+    sums[4 + 2 * blockIdx.x] = s0;
+    sums[4 + 2 * blockIdx.x + 1] = s1;
+  }
+}
+
+// sums[dst0] (and sums[dst0 + 1] when two) = fixed-order sums of the per-CTA partials stored behind sums[4]
+__global__ void gen_sum_kernel(double* __restrict__ sums, int ctas, int dst0, int two) {
+  __shared__ double red[32];
+  double a = 0.0, b = 0.0;
+  for (int c = threadIdx.x; c < ctas; c += blockDim.x) {
+    a += sums[4 + 2 * c];
+    b += sums[4 + 2 * c + 1];
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) {
+    sums[dst0] = a;
+    if (two) sums[dst0 + 1] = b;
   }
 }
 
@@ -763,6 +776,10 @@ void Engine::compute_mttkrp(ObjectState& o, int pos, double scale, double* out, 
   }
   pack_operand(v, 0);
   pack_operand(v, 1);
+  if (opt_.mttkrp_precision == 1) {
+    packed_factor_to_tf32(v.f0, st_, nullptr);
+    ++launches_;
+  }
   phase_begin(o.order >= 3 ? 0 : 1);
   if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
   launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit,
@@ -1844,11 +1861,13 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   g.shard_offset = o.shard_offset;
   g.ld0 = o.ld0;
   double* sums = nullptr;
-  AO_CUDA(cudaMalloc(&sums, 4 * sizeof(double)));
-  AO_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), st_));
   const int ctas = 148 * 8;
+  AO_CUDA(cudaMalloc(&sums, (4 + 2 * ctas) * sizeof(double)));
+  AO_CUDA(cudaMemsetAsync(sums, 0, (4 + 2 * ctas) * sizeof(double), st_));
   double h[4];
   gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 0, 0.0, 1.0, sums);
+  AO_CHECK_LAUNCH();
+  gen_sum_kernel<<<1, 256, 0, st_>>>(sums, ctas, 0, 1);
   AO_CHECK_LAUNCH();
   if (o.sharded) allreduce(sums, 2);
   AO_CUDA(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st_));
@@ -1856,13 +1875,15 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   const double sigma = (noise > 0.0) ? noise * std::sqrt(h[0]) / std::sqrt(h[1]) : 0.0;  // create_coupled_data.m:161
   gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 1, sigma, 1.0, sums);
   AO_CHECK_LAUNCH();
+  gen_sum_kernel<<<1, 256, 0, st_>>>(sums, ctas, 2, 0);
+  AO_CHECK_LAUNCH();
   if (o.sharded) allreduce(sums + 2, 1);
   AO_CUDA(cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
   gen_cp_kernel<<<ctas, 256, 0, st_>>>(g, o.data, seed, 2, 0.0, 1.0 / std::sqrt(h[2]), sums);  // script6 :101-102
   AO_CHECK_LAUNCH();
   AO_CUDA(cudaStreamSynchronize(st_));
-  launches_ += 3;
+  launches_ += 5;
   o.znorm = 1.0;
   o.T_version = 0;  // cached partial contractions refer to the old data
   for (auto p : tmp) cudaFree(p);
@@ -2017,6 +2038,10 @@ float Engine::time_mttkrp(int object, int pos, int reps) {
   AO_CUDA(cudaEventCreate(&b));
   const int R = m.R;
   const int prec = opt_.mttkrp_precision;  // precision of the last aoadmm_run (0 before any run)
+  if (prec == 1) {
+    packed_factor_to_tf32(v.f0, st_, nullptr);
+    ++launches_;
+  }
   launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, prec);  // warm-up
   AO_CUDA(cudaEventRecord(a, st_));
   for (int r = 0; r < reps; ++r)

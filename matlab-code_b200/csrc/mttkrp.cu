@@ -134,6 +134,11 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
     axor[mi] = (uint32_t)(((cbase + 2 * (mi & 1)) ^ kk) << 4);
   }
   const uint32_t boff = (uint32_t)((kk * C::LDC + wn * C::WN + m) * 8);
+  float fa[4][NT][2];  // PREC == 1: FP32 accumulators of the TF32 MMAs
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) fa[mi][nt][0] = fa[mi][nt][1] = 0.f;
 
   for (long long q = q0; q < q1; ++q) {
     const long long ql = q - q0;
@@ -161,11 +166,11 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[mi][nt][0], acc[mi][nt][1], a[mi], b[nt]);
       }
     } else {
-      float fa[4][NT][2];
+      // operand 0 arrives in the TF32 operand format (packed_factor_to_tf32: the high word of every 8-byte slot is the
+      // TF32-rounded float), so the Khatri-Rao row is one 32-bit load and one FP32 multiply per fragment element
+      float ckf[NT];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) fa[mi][nt][0] = fa[mi][nt][1] = 0.f;
+      for (int nt = 0; nt < NT; ++nt) ckf[nt] = (float)ck[nt];
 #pragma unroll
       for (int tt = 0; tt < TCOUNT; tt += 2) {
         uint32_t a[2][4], b[2][NT];
@@ -178,7 +183,7 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
           for (int mi = 0; mi < 4; ++mi) a[h][mi] = f64_to_tf32(lds_f64(xs + abase[mi] + rowoff + (axor[mi] ^ flip)));
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt)
-            b[h][nt] = f64_to_tf32(lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)) * ck[nt]);
+            b[h][nt] = f32_to_tf32(__uint_as_float(lds_u32(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8 + 4))) * ckf[nt]);
         }
 #pragma unroll
         for (int mp = 0; mp < 4; mp += 2)
@@ -187,13 +192,17 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
             mma_tf32_1688(fa[mp][nt][0], fa[mp][nt][1], fa[mp + 1][nt][0], fa[mp + 1][nt][1], a[0][mp], a[0][mp + 1],
                           a[1][mp], a[1][mp + 1], b[0][nt], b[1][nt]);
       }
+      // FP32 partial sums are folded into the FP64 accumulators every 4 stages (128 terms) and at the end
+      if ((ql & 3) == 3 || q + 1 == q1) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          acc[mi][nt][0] += (double)fa[mi][nt][0];
-          acc[mi][nt][1] += (double)fa[mi][nt][1];
-        }
+          for (int nt = 0; nt < NT; ++nt) {
+            acc[mi][nt][0] += (double)fa[mi][nt][0];
+            acc[mi][nt][1] += (double)fa[mi][nt][1];
+            fa[mi][nt][0] = fa[mi][nt][1] = 0.f;
+          }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(sBar + (kStages + s) * 8);
@@ -369,7 +378,7 @@ mttkrp_inner_kernel(const __grid_constant__ CUtensorMap tmap, const double* __re
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) a[h][mi] = f64_to_tf32(lds_f64(xs + box + abase[mi] + ((ch ^ arm[mi]) << 4)));
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) b[h][nt] = f64_to_tf32(lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)));
+            for (int nt = 0; nt < NT; ++nt) b[h][nt] = lds_u32(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8 + 4));
           }
 #pragma unroll
           for (int mp = 0; mp < 4; mp += 2)
@@ -568,6 +577,17 @@ __global__ void pack_factor_kernel(double* __restrict__ dst, long long rows_pad,
   }
 }
 
+// in place: every 8-byte slot becomes {low word 0, high word = TF32-rounded float of the value} (operand 0 of the
+// PREC == 1 kernels)
+__global__ void packed_to_tf32_kernel(double* __restrict__ data, long long total, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const uint32_t hi = f64_to_tf32(data[idx]);
+    reinterpret_cast<unsigned long long*>(data)[idx] = (unsigned long long)hi << 32;
+  }
+}
+
 __global__ void pack_kr_kernel(double* __restrict__ dst, long long rows_pad, int ldc, int NC, int nchunk,
                                const double* __restrict__ Fa, long long rows_a, long long lda,
                                const double* __restrict__ Fb, long long rows_b, long long ldb, int R,
@@ -737,6 +757,13 @@ void packed_factor_pack(const PackedFactor& p, const double* F, int64_t ld, cuda
   const long long total = (long long)p.nchunk * p.rows_pad * p.ldc;
   const int blocks = (int)std::min<long long>(ceil_div(total, 256), 148 * 8);
   pack_factor_kernel<<<blocks, 256, 0, st>>>(p.data, p.rows_pad, p.ldc, p.NC, p.nchunk, F, p.rows, ld, p.R, skip);
+  AO_CHECK_LAUNCH();
+}
+
+void packed_factor_to_tf32(const PackedFactor& p, cudaStream_t st, const int* skip) {
+  const long long total = (long long)p.nchunk * p.rows_pad * p.ldc;
+  const int blocks = (int)std::min<long long>(ceil_div(total, 256), 148 * 8);
+  packed_to_tf32_kernel<<<blocks, 256, 0, st>>>(p.data, total, skip);
   AO_CHECK_LAUNCH();
 }
 

@@ -45,6 +45,9 @@ void packed_factor_alloc(PackedFactor& p, int64_t rows, int R);
 void packed_factor_free(PackedFactor& p);
 // pack F (rows x R, leading dimension ld) into p; if F == nullptr fills ones (used for matrices: K = 1)
 void packed_factor_pack(const PackedFactor& p, const double* F, int64_t ld, cudaStream_t st, const int* skip);
+// In-place conversion of a freshly packed factor into the operand format of the opt-in TF32 kernels (precision = 1):
+// high word of every 8-byte slot = TF32-rounded float, low word 0.  Only operand 0 (f0) of mttkrp3 takes this format.
+void packed_factor_to_tf32(const PackedFactor& p, cudaStream_t st, const int* skip);
 // pack the Khatri-Rao product of two factors (first varies fastest): KR(a + Ra*b, r) = Fa(a,r)*Fb(b,r)
 void packed_factor_pack_kr(const PackedFactor& p, const double* Fa, int64_t rows_a, int64_t lda, const double* Fb,
                            int64_t rows_b, int64_t ldb, cudaStream_t st, const int* skip);

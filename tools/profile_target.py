@@ -20,7 +20,8 @@ if __name__ == '__main__':
     s.generate_cp_data(1, [A, B, C], 0.2, 1234)
     s.set_state(G)
     opts = dict(MaxOuterIters=1, MaxInnerIters=5, AbsFuncTol=0, OuterRelTol=0, innerRelPrTol_coupl=0, innerRelPrTol_constr=0,
-                innerRelDualTol_coupl=0, innerRelDualTol_constr=0, dimtree=1)
+                innerRelDualTol_coupl=0, innerRelDualTol_constr=0, dimtree=1,
+                mttkrp_precision=int(os.environ.get('PROBE_PREC', '0')))
     s.run(opts)
     for pos in (1, 2, 3):
         ms = s.time_mttkrp(1, pos, 0)
