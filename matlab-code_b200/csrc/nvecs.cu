@@ -10,8 +10,8 @@ namespace aoadmm {
 
 namespace {
 
-constexpr int kBK = 16;      // reduction depth of one pipeline stage
-constexpr int kStages = 4;
+constexpr int kBK = 32;      // reduction depth of one pipeline stage
+constexpr int kStages = 3;
 
 // 16-byte asynchronous copy of two doubles; only the first `bytes` (0, 8 or 16) are read, the rest is zero-filled
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
