@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <set>
+#include <thread>
 
 namespace aoadmm {
 
@@ -186,6 +187,61 @@ __global__ void gen_sum_kernel(double* __restrict__ sums, int ctas, int dst0, in
     sums[dst0] = a;
     if (two) sums[dst0 + 1] = b;
   }
+}
+
+// Host -> device copy of a large contiguous buffer.  Page-locked sources go down in one DMA (about 55 GB/s on this
+// pool); pageable sources (MATLAB arrays, plain malloc) would be staged by the driver at about 11 GB/s, so they are
+// staged here instead: a few worker threads copy interleaved 8 MB chunks into their own pinned buffers and issue the
+// DMA of each chunk on their own stream while the next chunk is being copied (profiles/r01_h2d_probe.log).
+void h2d_copy_large(void* dst, const void* src, size_t bytes, int device) {
+  constexpr size_t kChunk = 8u << 20;
+  cudaPointerAttributes attr{};
+  const bool pinned = (cudaPointerGetAttributes(&attr, src) == cudaSuccess) &&
+                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+  cudaGetLastError();  // an unregistered host pointer may leave cudaErrorInvalidValue behind on old drivers
+  if (pinned || bytes < 8 * kChunk) {
+    AO_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return;
+  }
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int T = (int)std::min<size_t>(std::min<unsigned>(8u, std::max(2u, hw / 2)), bytes / kChunk);
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  std::vector<cudaError_t> status(T, cudaSuccess);
+  char* staging = nullptr;  // one page-locked block: two chunks per worker
+  AO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&staging), (size_t)T * 2 * kChunk, cudaHostAllocDefault));
+  auto worker = [&](int t) {
+    cudaError_t e = cudaSetDevice(device);
+    void* buf[2] = {staging + ((size_t)t * 2) * kChunk, staging + ((size_t)t * 2 + 1) * kChunk};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    int use = 0;
+    for (size_t c = t; c < nchunks && e == cudaSuccess; c += T, use ^= 1) {
+      const size_t off = c * kChunk, n = std::min(kChunk, bytes - off);
+      e = cudaEventSynchronize(ev[use]);  // the DMA that last read this staging buffer has finished
+      if (e != cudaSuccess) break;
+      std::memcpy(buf[use], static_cast<const char*>(src) + off, n);
+      e = cudaMemcpyAsync(static_cast<char*>(dst) + off, buf[use], n, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[use], st);
+    }
+    if (st != nullptr) {
+      const cudaError_t e2 = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = e2;
+    }
+    for (int b = 0; b < 2; ++b)
+      if (ev[b]) cudaEventDestroy(ev[b]);
+    if (st) cudaStreamDestroy(st);
+    status[t] = e;
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) th.emplace_back(worker, t);
+  for (auto& x : th) x.join();
+  cudaFreeHost(staging);
+  for (int t = 0; t < T; ++t)
+    if (status[t] != cudaSuccess)
+      throw CudaError(status[t] == cudaErrorMemoryAllocation ? 7 : 5,
+                      std::string("host->device copy of the tensor: ") + cudaGetErrorString(status[t]));
 }
 
 double now_s() {
@@ -356,7 +412,7 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
     if (src.data != nullptr && slab > 0) {
       // no padding: one linear copy (a pitched copy of narrow rows runs at ~2/3 of the PCIe rate, profiles/r01_h2d_probe.log)
       if (o.ld0 == o.dims[0])
-        AO_CUDA(cudaMemcpy(o.data, src.data, (size_t)o.dims[0] * slab * 8, cudaMemcpyHostToDevice));
+        h2d_copy_large(o.data, src.data, (size_t)o.dims[0] * slab * 8, device_);
       else
         AO_CUDA(cudaMemcpy2D(o.data, (size_t)o.ld0 * 8, src.data, (size_t)o.dims[0] * 8, (size_t)o.dims[0] * 8, slab,
                              cudaMemcpyHostToDevice));
