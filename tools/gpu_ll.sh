@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "mttkrp or config2 or dimension_tree or golden or script6" 2>&1 | tail -5
-timeout 300 python tools/perf_probe.py 4096 4096 256 8192 64 5 2>&1 | grep -E "mttkrp|run"
-timeout 300 python tools/perf_probe.py 1000 1000 1000 5000 32 10 2>&1 | grep -E "mttkrp|run"
-timeout 300 python tools/perf_probe.py 2048 2048 512 1024 8 5 2>&1 | grep -E "mttkrp|run"
+set -e
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3k1024_s3.json 2> gpurun_out/bench_c3k1024_s3.err
+echo "plain rc=$?"
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench_c3k1024.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+echo "ncu rc=$?"; wc -l gpurun_out/launches_bench_c3k1024.csv
