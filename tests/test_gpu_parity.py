@@ -713,3 +713,35 @@ def test_nvecs_medium_size_uses_large_tiles(ab):
     with ab.Solver(ab._with_rank(Z, G), pg.znorm_const(Z)) as s:
         for n in (1, 2, 3, 4, 5):
             _nvecs_close(s.nvecs(n, 6), pg.cmtf_nvecs(Z, n, 6), Z, n)
+
+
+def test_handles_release_all_device_memory(ab):
+    """create -> run -> destroy many times over every kind of problem (CP + matrix, PARAFAC2, linear coupling, missing
+    data, nvecs, TF32 mode, graph replay): the free device memory afterwards is what it was before."""
+    import ctypes
+    cudart = ctypes.CDLL('libcudart.so')
+
+    def free_bytes():
+        f, t = ctypes.c_size_t(), ctypes.c_size_t()
+        assert cudart.cudaMemGetInfo(ctypes.byref(f), ctypes.byref(t)) == 0
+        return f.value
+
+    cases = [pg.config_cp_matrix(40, 36, 30, 64, 5, seed=8)[:2], pg.config_cp_par2(seed=4, noise=0.1)[:2],
+             pg.config_linear_coupling(1, seed=1, second='tensor')[:2], pg.config_linear_coupling(4, seed=4, second='par2')[:2],
+             pg.config_script14()[:2]]
+    Zc, Gc = cases[0]
+    cases.append((pg.add_missing(Zc, 0.25, seed=3), Gc))
+
+    def one_round():
+        for Z, G in cases:
+            for extra in (dict(), dict(mttkrp_precision=1, graph=1)):
+                ab.cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, None, None, None, None,
+                                   pg.default_options(MaxOuterIters=8, **dict(ZERO_TOL, **extra)))
+        ab.cmtf_nvecs(cases[0][0], 1, 3)
+
+    one_round()                      # module loading, library workspaces, caches
+    before = free_bytes()
+    for _ in range(3):
+        one_round()
+    after = free_bytes()
+    assert before - after < (8 << 20), (before, after)
