@@ -235,8 +235,9 @@ int aoadmm_get_object_data(aoadmm_handle *h, int32_t object, double *out, int64_
  * the slices side by side, a B_k mode needs `slice` (1-based; Y = X_k' X_k), mode C is ones in the reference and is
  * refused.  slice = 0 otherwise.  Columns come in descending eigenvalue order, each signed so that its entry of
  * largest magnitude is positive (eigs leaves the sign open).  info (may be NULL): [0] subspace iterations,
- * [1] max ||Y u - theta u|| / theta_1 over the returned pairs.  With more than one GPU the sharded (last) mode of a
- * tensor returns AOADMM_ERR_UNSUPPORTED. */
+ * [1] max ||Y u - theta u|| / theta_1 over the returned pairs.  With more than one GPU every rank must make the call
+ * (collective): partial Gram matrices of the slabs are all-reduced; for the sharded (last) mode the slabs are exchanged
+ * chunk by chunk with NCCL point-to-point transfers. */
 int aoadmm_nvecs(aoadmm_handle *h, int32_t mode, int32_t slice, int32_t r, double *out, int64_t rows, double *info);
 /* MTTKRP of the resident CP object `object` in mode position `pos` (1-based) with the factors currently in the handle
  * (cmtf_fun_AOADMM.m:97), at `precision` (0 FP64, 1 TF32 opt-in: see aoadmm_options.mttkrp_precision), summed over

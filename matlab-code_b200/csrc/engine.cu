@@ -33,6 +33,11 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  // point-to-point exchange of tensor slabs (nvecs of the sharded mode)
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
 };
 
 NcclApi* load_nccl() {
@@ -49,6 +54,10 @@ NcclApi* load_nccl() {
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+  api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(api.lib, "ncclSend"));
+  api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(api.lib, "ncclRecv"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
   if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
     throw CudaError(6, "libnccl.so.2 lacks required symbols");
   return &api;
@@ -1977,8 +1986,10 @@ void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t r
   bool reduce_over_ranks = false;
   if (o.model == AOADMM_MODEL_CP) {
     if (slice != 0) throw CudaError(1, "nvecs: slice given for a CP mode");
-    if (o.sharded && pos == o.order - 1)
-      throw CudaError(2, "nvecs of the sharded (last) mode of a tensor is not supported with more than one GPU");
+    if (o.sharded && pos == o.order - 1) {
+      nvecs_sharded_mode(o, r, out, rows, info);
+      return;
+    }
     const View3& v = o.views[pos];
     const Tensor3& t = v.t;
     s.X = t.X;
@@ -2053,6 +2064,113 @@ void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t r
     cudaFree(U);
     throw;
   }
+  cudaFree(Y);
+  cudaFree(work);
+  cudaFree(U);
+}
+
+// nvecs of the mode the tensor is sharded along (the last one): Y(k,k') = <X(:,:,k), X(:,:,k')> needs pairs of slices
+// that live on different GPUs.  The middle extent J is cut into chunks; chunk c is gathered on rank c mod P with NCCL
+// point-to-point transfers over NVLink (every rank sends its k-range of the chunk, packed, straight into the owner's
+// buffer at its place in the global k order), the owner adds the chunk's K x K Gram matrix with the same DMMA kernel, and
+// one all-reduce at the end sums the owners' partial matrices.  Each slab crosses NVLink once.
+void Engine::nvecs_sharded_mode(ObjectState& o, int r, double* out, int64_t rows, double* info) {
+  if (!nccl_->Send || !nccl_->Recv || !nccl_->GroupStart || !nccl_->GroupEnd)
+    throw CudaError(6, "libnccl.so.2 lacks ncclSend/ncclRecv (needed for nvecs of the sharded mode)");
+  const Tensor3& t = o.views[o.order - 1].t;   // I x J x Kloc, leading dimension ldI
+  const long long Kt = o.last_full, Kloc = t.K, J = t.J, ld = t.ldI;
+  if (rows != Kt) throw CudaError(1, "nvecs: output rows do not match the mode size");
+  if (r < 1 || r > Kt) throw CudaError(1, "nvecs: the number of vectors must be between 1 and the mode size");
+  // slab ranges of all ranks (the caller chooses them): one all-reduce of a zero-padded table
+  std::vector<double> tab(2 * (size_t)world_, 0.0);
+  tab[2 * rank_] = (double)o.shard_offset;
+  tab[2 * rank_ + 1] = (double)Kloc;
+  double* tab_dev = nullptr;
+  AO_CUDA(cudaMalloc(&tab_dev, tab.size() * sizeof(double)));
+  AO_CUDA(cudaMemcpyAsync(tab_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+  allreduce(tab_dev, tab.size());
+  AO_CUDA(cudaMemcpyAsync(tab.data(), tab_dev, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  AO_CUDA(cudaStreamSynchronize(st_));
+  cudaFree(tab_dev);
+  long long Kmax = 0;
+  for (int q = 0; q < world_; ++q) Kmax = std::max<long long>(Kmax, (long long)tab[2 * q + 1]);
+  // chunk width: gathered chunk <= 256 MB, at least one chunk per rank when J allows
+  long long cj = std::max<long long>(1, (256LL << 20) / std::max<long long>(ld * Kt * 8, 1));
+  cj = std::min(cj, std::max<long long>(1, ceil_div(J, world_)));
+  const long long nchunks = ceil_div(J, cj), ngroups = ceil_div(nchunks, world_);
+  const size_t nn = (size_t)Kt * (size_t)Kt;
+  UnfoldSpec s;
+  s.layout = 1;
+  s.n = Kt;
+  s.I = t.I;
+  s.bs = ld;
+  double *gathered = nullptr, *send = nullptr, *Y = nullptr, *work = nullptr, *U = nullptr;
+  try {
+    AO_CUDA(cudaMalloc(&gathered, std::max<size_t>((size_t)ld * cj * Kt * 8, 256)));
+    AO_CUDA(cudaMalloc(&send, std::max<size_t>((size_t)ld * cj * std::max<long long>(Kloc, 1) * 8 * world_, 256)));
+    AO_CUDA(cudaMalloc(&Y, std::max<size_t>(nn * 8, 256)));
+    AO_CUDA(cudaMalloc(&U, std::max<size_t>((size_t)Kt * r * 8, 256)));
+    AO_CUDA(cudaMemsetAsync(Y, 0, nn * 8, st_));
+    s.X = gathered;
+    s.cs = ld * cj;   // upper bound for the workspace query
+    s.nb = cj;
+    AO_CUDA(cudaMalloc(&work, std::max<size_t>(unfold_gram_workspace(s) * 8, 256)));
+    const size_t part = (size_t)ld * cj * std::max<long long>(Kloc, 1);
+    for (long long g = 0; g < ngroups; ++g) {
+      // pack this rank's k-range of the P chunks of the group (chunk g*P + p goes to rank p)
+      for (int p = 0; p < world_; ++p) {
+        const long long j0 = (g * world_ + p) * cj, w = std::min(cj, J - j0);
+        if (w <= 0 || Kloc <= 0) continue;
+        AO_CUDA(cudaMemcpy2DAsync(send + part * p, (size_t)w * ld * 8, t.X + j0 * ld, (size_t)J * ld * 8, (size_t)w * ld * 8,
+                                  (size_t)Kloc, cudaMemcpyDeviceToDevice, st_));
+      }
+      const long long myj0 = (g * world_ + rank_) * cj, myw = std::min(cj, J - myj0);
+      AO_NCCL(nccl_->GroupStart());
+      for (int p = 0; p < world_; ++p) {
+        const long long j0 = (g * world_ + p) * cj, w = std::min(cj, J - j0);
+        if (w <= 0) continue;
+        if (p != rank_) {
+          if (Kloc > 0)
+            AO_NCCL(nccl_->Send(send + part * p, (size_t)(w * ld * Kloc), ncclDouble, p, static_cast<ncclComm_t>(comm_), st_));
+        } else {
+          for (int q = 0; q < world_; ++q) {
+            const long long off = (long long)tab[2 * q], kq = (long long)tab[2 * q + 1];
+            if (q == rank_ || kq <= 0) continue;
+            AO_NCCL(nccl_->Recv(gathered + (size_t)off * w * ld, (size_t)(w * ld * kq), ncclDouble, q,
+                                static_cast<ncclComm_t>(comm_), st_));
+          }
+        }
+      }
+      AO_NCCL(nccl_->GroupEnd());
+      if (myw > 0) {
+        if (Kloc > 0)
+          AO_CUDA(cudaMemcpyAsync(gathered + (size_t)o.shard_offset * myw * ld, send + part * rank_,
+                                  (size_t)myw * ld * Kloc * 8, cudaMemcpyDeviceToDevice, st_));
+        s.cs = ld * myw;   // element (i, jj, k) of the gathered chunk at i + ld*(jj + myw*k)
+        s.nb = myw;
+        launches_ += unfold_gram(s, Y, work, st_, true);
+      }
+    }
+    allreduce(Y, nn);
+    std::vector<double> theta(r);
+    const EigInfo ei = top_eigvecs(Y, Kt, r, U, theta.data(), st_);
+    launches_ += ei.launches;
+    if (info != nullptr) {
+      info[0] = ei.iterations;
+      info[1] = ei.residual;
+    }
+    AO_CUDA(cudaMemcpyAsync(out, U, (size_t)Kt * r * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    AO_CUDA(cudaStreamSynchronize(st_));
+  } catch (...) {
+    cudaFree(gathered);
+    cudaFree(send);
+    cudaFree(Y);
+    cudaFree(work);
+    cudaFree(U);
+    throw;
+  }
+  cudaFree(gathered);
+  cudaFree(send);
   cudaFree(Y);
   cudaFree(work);
   cudaFree(U);

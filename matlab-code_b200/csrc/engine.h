@@ -156,6 +156,7 @@ class Engine {
   // cmtf_nvecs.m / init_coupled_AOADMM_CMTF.m:50-69: r leading eigenvectors of X_(n) X_(n)' for global mode id `mode`
   // (slice: 1-based slice of a PARAFAC2 B_k mode, else 0); out: rows x r host buffer; info: [iterations, residual]
   void nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t rows, double* info);
+  void nvecs_sharded_mode(ObjectState& o, int r, double* out, int64_t rows, double* info);
   void mttkrp_to_host(int object, int pos, double* out, int precision = -1);  // unweighted MTTKRP of the resident factors (-1: precision of the last run)
   int64_t launches() const { return launches_; }
   void phase_ms(double ms[3]);

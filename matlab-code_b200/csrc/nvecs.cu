@@ -146,13 +146,15 @@ __global__ void __launch_bounds__(256) unfold_gram_kernel(GramArgs g) {
 }
 
 // Y(a,b) = Y(b,a) = sum over splits (fixed order) of the upper-triangle partials
-__global__ void gram_reduce_mirror_kernel(const double* __restrict__ P, int splits, long long n, double* __restrict__ Y) {
+__global__ void gram_reduce_mirror_kernel(const double* __restrict__ P, int splits, long long n, double* __restrict__ Y,
+                                          int accumulate) {
   const long long nn = n * n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nn; idx += (long long)gridDim.x * blockDim.x) {
     const long long a = idx % n, b = idx / n;
     if (a > b) continue;
     double s = 0.0;
     for (int z = 0; z < splits; ++z) s += P[(long long)z * nn + idx];
+    if (accumulate) s += Y[idx];   // Y stays exactly symmetric: both triangles receive the same sum
     Y[idx] = s;
     Y[b + n * a] = s;
   }
@@ -290,7 +292,7 @@ size_t unfold_gram_workspace(const UnfoldSpec& s) {
   return (size_t)p.splits * (size_t)s.n * (size_t)s.n;
 }
 
-int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st) {
+int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st, bool accumulate) {
   if (s.n <= 0) return 0;
   // the operand tiles are fetched in 16-byte pieces: base and all strides must keep pairs of doubles aligned
   if ((reinterpret_cast<uintptr_t>(s.X) & 15) != 0 || (s.layout == 0 ? (s.ld & 1) : ((s.cs | s.bs) & 1)) != 0)
@@ -312,7 +314,7 @@ int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st) {
     else if (p.bmt == 64) launch_gram<1, 64>(g, p, st);
     else launch_gram<1, 32>(g, p, st);
   }
-  gram_reduce_mirror_kernel<<<blocks_for(s.n * s.n), 256, 0, st>>>(work, p.splits, s.n, Y);
+  gram_reduce_mirror_kernel<<<blocks_for(s.n * s.n), 256, 0, st>>>(work, p.splits, s.n, Y, accumulate ? 1 : 0);
   AO_CHECK_LAUNCH();
   return 2;
 }

@@ -29,8 +29,8 @@ struct UnfoldSpec {
 
 // doubles of workspace needed by unfold_gram for this spec
 size_t unfold_gram_workspace(const UnfoldSpec& s);
-// Y (n x n, ld = n) = A A'.  Returns the number of launches.
-int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st);
+// Y (n x n, ld = n) = A A'  (accumulate: Y += A A').  Returns the number of launches.
+int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st, bool accumulate = false);
 
 struct EigInfo {
   int iterations = 0;
