@@ -322,7 +322,8 @@ int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st, b
 EigInfo top_eigvecs(const double* Y, long long n, int r, double* U, double* theta, cudaStream_t st) {
   EigInfo info;
   if (r < 1 || r > n) throw CudaError(1, "nvecs: the number of vectors must be between 1 and the mode size");
-  const int Rb = (int)std::min<long long>(n, (long long)r + std::max(8, r / 4));
+  // short modes: the block is the whole space, one Rayleigh-Ritz step (a Jacobi eigen-decomposition of Y) is exact
+  const int Rb = (n <= 128) ? (int)n : (int)std::min<long long>(n, (long long)r + std::max(8, r / 4));
   const size_t nb = (size_t)n * Rb, bb = (size_t)Rb * Rb;
   double* buf = nullptr;
   int* order_dev = nullptr;

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -q -k "release_all_device" 2>&1 | tail -8
+timeout 900 python -m pytest tests -m gpu -q -k "nvecs or init_front" 2>&1 | tail -5
