@@ -25,7 +25,9 @@
 extern "C" {
 #endif
 
-#define AOADMM_ABI_VERSION 2
+/* 1: first release; 2: Z.miss masks, device Znorm_const, engine options (dimtree, fuse_inner, graph,
+ * mttkrp_precision), out.f_rel_missing; 3: aoadmm_nvecs, aoadmm_object_mttkrp (no struct changed since 2). */
+#define AOADMM_ABI_VERSION 3
 
 typedef struct aoadmm_handle aoadmm_handle;
 
