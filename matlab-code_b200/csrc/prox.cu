@@ -287,8 +287,6 @@ __device__ void prefix_isotonic(const double* y0, long long dir, long long len, 
   sumwy2[0] = 0.0;
   sumw[0] = 0;
   range[0] = 0;
-  double err_prev_store = 0.0;
-  (void)err_prev_store;
   if (err != nullptr) err[0] = 0.0;
   double cs = 0.0;  // cumsum of squares of the elements BEFORE the current one (cumsumwy2(i-1), :70)
   for (long long i = 1; i <= len; ++i) {

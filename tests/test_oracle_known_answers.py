@@ -273,3 +273,83 @@ def test_oracle_nvecs_known_answers():
     for Fk in G['fac'][pm[1] - 1]:
         assert np.allclose(Fk.T @ Fk, np.eye(3), atol=1e-12)
     assert np.allclose(G['fac'][pm[0] - 1].T @ G['fac'][pm[0] - 1], np.eye(3), atol=1e-12)
+
+
+def test_oracle_fixed_point_satisfies_kkt_of_the_coupled_problem():
+    """Independent of the algorithm: at the fixed point of the restated AO-ADMM on the example_script6 structure (3-way CP
+    + two matrices, two exact couplings, non-negativity on 6 of 7 modes) the factors are a KKT point of
+        min  sum_p w_p || X_p - [[factors]] ||^2   s.t.  coupled factors equal, constrained factors >= 0:
+    the gradients of the coupled objects are individually non-zero but cancel (or are complementary to the active
+    bounds), the unconstrained mode has zero gradient."""
+    from oracle.tensor_ops import mttkrp
+    Z, G, _ = pg.config_script6(seed=3, noise=0.1)
+    opts = pg.default_options(MaxOuterIters=2000, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=20,
+                              innerRelPrTol_coupl=1e-8, innerRelPrTol_constr=1e-8, innerRelDualTol_coupl=1e-8,
+                              innerRelDualTol_constr=1e-8)
+    Go, oo = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=opts)
+    assert oo['f_couplings'] < 1e-12 and oo['f_constraints'] < 1e-12
+    F = Go['fac']
+    g = {}
+    for p, ms in enumerate(Z['modes']):
+        X, w = Z['object'][p], Z['weights'][p]
+        for pos, m in enumerate(ms):
+            had = np.ones((F[m - 1].shape[1],) * 2)
+            for q in ms:
+                if q != m:
+                    had = had * (F[q - 1].T @ F[q - 1])
+            if X.ndim > 2:
+                M = mttkrp(X, [F[q - 1] for q in ms], pos)
+            else:
+                M = X @ F[ms[1] - 1] if pos == 0 else X.T @ F[ms[0] - 1]
+            g[m] = 2 * w * (F[m - 1] @ had - M)
+    lin = Z['coupling']['lin_coupled_modes']
+    groups = {}
+    for m in range(1, 8):
+        groups.setdefault(('c', lin[m - 1]) if lin[m - 1] else ('m', m), []).append(m)
+    for key, ms in groups.items():
+        total = sum(g[m] for m in ms)
+        Fm = F[ms[0] - 1]
+        for m in ms:
+            assert np.linalg.norm(F[m - 1] - Fm) < 1e-10                        # exact coupling holds
+        if any(Z['constrained_modes'][m - 1] for m in ms):
+            assert Fm.min() > -1e-12
+            viol = np.linalg.norm(np.minimum(Fm, total))                         # F >= 0, grad >= 0, F .* grad = 0
+        else:
+            viol = np.linalg.norm(total)
+        assert viol < 1e-9, (key, viol)
+        if len(ms) > 1:                                                          # the single gradients do NOT vanish
+            assert min(np.linalg.norm(g[m]) for m in ms) > 1e-5
+
+
+def test_oracle_fixed_point_satisfies_kkt_with_l1_and_l2_ball():
+    """example_script10 structure with the l1 variant: min ||X - [[A,B,C]]||^2 + eta*||A||_1 s.t. ||b_r||, ||c_r|| <= 1.
+    At the fixed point: 0 in grad_A + eta*sign(A) (|grad| <= eta on the zeros, about half of the entries at this eta),
+    and on the ball-constrained modes every column gradient is -lambda_r * column with lambda_r >= 0 and ||column|| = 1."""
+    from oracle.tensor_ops import mttkrp
+    eta = 6e-2
+    Z, G, _ = pg.config_cp_tv(I=30, J=20, K=25, R=3, seed=2, noise=0.3, eta=eta, mode1=('l1 regularization',))
+    opts = pg.default_options(MaxOuterIters=2500, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=20,
+                              innerRelPrTol_coupl=1e-8, innerRelPrTol_constr=1e-8, innerRelDualTol_coupl=1e-8,
+                              innerRelDualTol_constr=1e-8)
+    Go, oo = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=opts)
+    F, Zc = Go['fac'], Go['constraint_fac']
+    X = Z['object'][0]
+    g = []
+    for pos in range(3):
+        had = np.ones((3, 3))
+        for q in range(3):
+            if q != pos:
+                had = had * (F[q].T @ F[q])
+        g.append(2 * (F[pos] @ had - mttkrp(X, F, pos)))
+    A = Zc[0]
+    assert np.linalg.norm(F[0] - A) < 1e-10
+    nz = np.abs(A) > 1e-12
+    assert 0.2 < nz.mean() < 0.9                                   # genuinely sparse, genuinely non-trivial
+    assert np.abs(g[0][nz] + eta * np.sign(A[nz])).max() < 1e-9
+    assert np.maximum(np.abs(g[0][~nz]) - eta, 0).max() < 1e-9
+    for pos in (1, 2):
+        for r in range(3):
+            col, gc = F[pos][:, r], g[pos][:, r]
+            lam = -(gc @ col) / (col @ col)
+            assert abs(np.linalg.norm(col) - 1.0) < 1e-9 and lam > 0
+            assert np.linalg.norm(gc + lam * col) < 1e-9
