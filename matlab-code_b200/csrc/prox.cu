@@ -259,8 +259,10 @@ __device__ __forceinline__ void tv_condat_serial(const double* y, double* x, lon
 // L0-segmentation", 2013): one forward pass that keeps the knots of the piecewise-linear derivative of the message
 // function in a double-ended queue (amortised two queue steps per element, no rescans), one backward pass through the
 // clipping bounds tm/tp.  About three times faster than the direct algorithm on noisy columns, where that one restarts
-// often; needs 8n doubles of workspace: knot positions xk and their slope / intercept increments ak, bk (2n each),
-// tm, tp (n each).  The minimiser is unique, so both algorithms agree to rounding.
+// often; needs 9n+1 doubles of workspace: knot positions xk and their slope / intercept increments ak, bk (2n each),
+// tm, tp (n each) and the table rc[c] = 1/c: the slopes are integers (sums of +-1), so the two divisions per element
+// become multiplications (<= 1 ulp from the quotient; an FP64 division is a ~200-cycle routine on the critical path).
+// The minimiser is unique, so both algorithms agree to rounding.
 __device__ __forceinline__ void tv_dp_serial(const double* y, double* beta, long long n, double lam, double* work) {
   if (n <= 0) return;
   if (n == 1 || !(lam > 0.0)) {
@@ -272,6 +274,7 @@ __device__ __forceinline__ void tv_dp_serial(const double* y, double* beta, long
   double* bk = work + 4 * n;
   double* tm = work + 6 * n;
   double* tp = work + 7 * n;
+  const double* rc = work + 8 * n;   // rc[c] = 1/c, c = 0..n (filled by the whole warp before the serial part)
   tm[0] = y[0] - lam;
   tp[0] = y[0] + lam;
   long long l = n - 1, r = n;
@@ -290,7 +293,7 @@ __device__ __forceinline__ void tv_dp_serial(const double* y, double* beta, long
       alo += ak[lo];
       blo += bk[lo];
     }
-    const double tmk = (-lam - blo) / alo;
+    const double tmk = (-lam - blo) * rc[(int)alo];
     l = lo - 1;
     xk[l] = tmk;
     tm[k] = tmk;
@@ -301,7 +304,7 @@ __device__ __forceinline__ void tv_dp_serial(const double* y, double* beta, long
       ahi += ak[hi];
       bhi += bk[hi];
     }
-    const double tpk = (lam + bhi) / (-ahi);
+    const double tpk = (lam + bhi) * rc[(int)(-ahi)];
     r = hi + 1;
     xk[r] = tpk;
     tp[k] = tpk;
@@ -462,8 +465,10 @@ __global__ void prox_serial_col_kernel(int kind, double p0, const double* __rest
   double* res = base + n;    // n
   double* work = base + 2 * n;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
-  if (kind == PROX_TV && !tv_dp)
-    for (long long i = threadIdx.x; i <= n; i += blockDim.x) work[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+  if (kind == PROX_TV) {
+    double* rc = tv_dp ? work + 8 * n : work;
+    for (long long i = threadIdx.x; i <= n; i += blockDim.x) rc[i] = (i > 0) ? 1.0 / (double)i : 0.0;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (kind == PROX_TV && tv_dp) {
@@ -567,10 +572,11 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     return n;
   }
   if (is_serial_kind(kind)) {
-    // TV: the dynamic-programming algorithm when its 10n doubles (column, result, 8n of queue / bounds) fit in shared
-    // memory, else the direct algorithm (3n+1 doubles; shared memory up to ~8500 rows, global scratch beyond)
-    const int tv_dp = (kind == PROX_TV && (size_t)rows * 10 * sizeof(double) <= kSerialSmemLimit) ? 1 : 0;
-    const long long per = tv_dp ? 10 * rows : serial_doubles_per_col(kind, rows);
+    // TV: the dynamic-programming algorithm when its 11n+1 doubles (column, result, 8n of queue / bounds, reciprocal
+    // table) fit in shared memory, else the direct algorithm (3n+1 doubles; shared memory up to ~8500 rows, global
+    // scratch beyond)
+    const int tv_dp = (kind == PROX_TV && ((size_t)rows * 11 + 1) * sizeof(double) <= kSerialSmemLimit) ? 1 : 0;
+    const long long per = tv_dp ? 11 * rows + 1 : serial_doubles_per_col(kind, rows);
     const size_t bytes = (size_t)per * sizeof(double);
     const int use_smem = bytes <= kSerialSmemLimit;
     if (!use_smem && scratch == nullptr) throw CudaError(1, "prox_apply: scratch buffer required for this size");

@@ -106,10 +106,10 @@ def test_prox_matches_oracle(ab, con, rows, cols):
         assert rel(ab.prox(con, V, rho=rho), ops[0](V, rho)) < 1e-12, (con, rows, cols, rho)
 
 
-@pytest.mark.parametrize('rows', [2, 3, 17, 1000, 2560, 2561, 6000])
+@pytest.mark.parametrize('rows', [2, 3, 17, 1000, 2327, 2328, 6000])
 @pytest.mark.parametrize('eta', [1e-3, 0.3, 50.0])
 def test_prox_tv_both_algorithms(ab, rows, eta):
-    """TV prox: the dynamic-programming kernel (rows <= 2560, workspace in shared memory) and the direct kernel (longer
+    """TV prox: the dynamic-programming kernel (rows <= 2327, workspace in shared memory) and the direct kernel (longer
     columns) against the oracle's direct algorithm: noisy, piecewise-constant, constant and tied columns; tiny, moderate
     and huge eta (one flat segment)."""
     rng = np.random.RandomState(rows)
