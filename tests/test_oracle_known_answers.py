@@ -353,3 +353,35 @@ def test_oracle_fixed_point_satisfies_kkt_with_l1_and_l2_ball():
             lam = -(gc @ col) / (col @ col)
             assert abs(np.linalg.norm(col) - 1.0) < 1e-9 and lam > 0
             assert np.linalg.norm(gc + lam * col) < 1e-9
+
+
+def test_oracle_parafac2_fixed_point_satisfies_kkt():
+    """PARAFAC2 (irregular slices, non-negative A and C): at the fixed point of the restated ADMM_B_Parafac2 scheme the
+    factors are a stationary point of  min sum_k ||X_k - A D_k B_k'||^2  s.t.  B_k = P_k DeltaB, P_k'P_k = I, A, C >= 0:
+    the coupling holds, every P_k is the polar factor of X_k' A D_k DeltaB' (P_k'M_k symmetric positive definite), the
+    gradient w.r.t. DeltaB (through all slices) and w.r.t. C vanishes, A satisfies complementarity."""
+    Z, G, _ = pg.config_single_par2(I=14, Jk=(10, 8, 11, 9, 12), R=3, seed=3, noise=0.1)
+    opts = pg.default_options(MaxOuterIters=1200, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=10,
+                              innerRelPrTol_coupl=1e-9, innerRelPrTol_constr=1e-9, innerRelDualTol_coupl=1e-9,
+                              innerRelDualTol_constr=1e-9)
+    Go, oo = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=opts)
+    m1, m2, m3 = Z['modes'][0]
+    A, Bk, C = Go['fac'][m1 - 1], Go['fac'][m2 - 1], Go['fac'][m3 - 1]
+    P, dB = Go['P'][0], Go['DeltaB'][0]
+    X = Z['object'][0]
+    gA, gC, gdB = np.zeros_like(A), np.zeros_like(C), np.zeros_like(dB)
+    for k in range(len(X)):
+        Dk = np.diag(C[k])
+        E = X[k] - A @ Dk @ Bk[k].T
+        gA += -2 * E @ Bk[k] @ Dk
+        gC[k] = -2 * np.diag(A.T @ E @ Bk[k])
+        gdB += P[k].T @ (-2 * E.T @ A @ Dk)
+        assert np.linalg.norm(Bk[k] - P[k] @ dB) < 1e-5 * np.linalg.norm(Bk[k])
+        assert np.linalg.norm(P[k].T @ P[k] - np.eye(3)) < 1e-12
+        S = P[k].T @ (X[k].T @ A @ Dk @ dB.T)
+        assert np.linalg.norm(S - S.T) < 1e-5 * np.linalg.norm(S)
+        assert np.linalg.eigvalsh((S + S.T) / 2).min() > 0
+    assert A.min() > -1e-9
+    assert np.linalg.norm(np.minimum(A, gA)) < 1e-4                   # A >= 0, grad >= 0, A .* grad = 0
+    assert np.linalg.norm(gC) < 1e-6 and C.min() > 0
+    assert np.linalg.norm(gdB) < 1e-6
