@@ -385,3 +385,38 @@ def test_oracle_parafac2_fixed_point_satisfies_kkt():
     assert np.linalg.norm(np.minimum(A, gA)) < 1e-4                   # A >= 0, grad >= 0, A .* grad = 0
     assert np.linalg.norm(gC) < 1e-6 and C.min() > 0
     assert np.linalg.norm(gdB) < 1e-6
+
+
+def test_oracle_linear_coupling_fixed_point_satisfies_kkt():
+    """Linear couplings H F = Delta (type 1, Sylvester solves) and F = Delta H (type 4, Cholesky solves), unconstrained:
+    at the fixed point the coupling equations hold and the gradients of the two objects — each of order 1e-3 — cancel in
+    the combination the constraint prescribes (H4' g1 + g4 = 0, resp. g1 H1' + g4 H4' = 0); the uncoupled modes have zero
+    gradient."""
+    from oracle.tensor_ops import mttkrp
+    opts = pg.default_options(MaxOuterIters=1500, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=20,
+                              innerRelPrTol_coupl=1e-9, innerRelPrTol_constr=1e-9, innerRelDualTol_coupl=1e-9,
+                              innerRelDualTol_constr=1e-9)
+    for ct in (1, 4):
+        Z, G, _ = pg.config_linear_coupling(ct, seed=ct, constrained=False)
+        Go, _ = cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, options=opts)
+        F, D, H = Go['fac'], Go['coupling_fac'][0], Z['coupling']['coupl_trafo_matrices']
+        g = {}
+        for p, ms in enumerate(Z['modes']):
+            X, w = Z['object'][p], Z['weights'][p]
+            for pos, m in enumerate(ms):
+                R = F[m - 1].shape[1]
+                had = np.ones((R, R))
+                for q in ms:
+                    if q != m:
+                        had = had * (F[q - 1].T @ F[q - 1])
+                M = mttkrp(X, [F[q - 1] for q in ms], pos) if X.ndim > 2 else (X @ F[ms[1] - 1] if pos == 0 else X.T @ F[ms[0] - 1])
+                g[m] = 2 * w * (F[m - 1] @ had - M)
+        if ct == 1:
+            feas = [H[0] @ F[0] - D, H[3] @ F[3] - D]
+            stat = g[4] + H[3].T @ g[1]                    # H1 = I: F1 = H4 F4
+        else:
+            feas = [F[0] - D @ H[0], F[3] - D @ H[3]]
+            stat = g[1] @ H[0].T + g[4] @ H[3].T
+        assert max(np.linalg.norm(f) for f in feas) < 1e-8, ct
+        assert np.linalg.norm(stat) < 1e-8 and min(np.linalg.norm(g[1]), np.linalg.norm(g[4])) > 1e-4, ct
+        assert max(np.linalg.norm(g[m]) for m in (2, 3, 5)) < 1e-8, ct
