@@ -761,3 +761,41 @@ def test_handles_release_all_device_memory(ab):
         one_round()
     after = free_bytes()
     assert before - after < (8 << 20), (before, after)
+
+
+def test_engine_fixed_point_satisfies_kkt_without_the_oracle(ab):
+    """Oracle-independent: run the ENGINE to its fixed point on the example_script6 structure and check the KKT
+    conditions of the coupled, non-negativity constrained problem directly with NumPy (gradients of coupled objects
+    cancel or are complementary to the bounds, coupled factors are equal)."""
+    Z, G, _ = pg.config_script6(seed=3, noise=0.1)
+    opts = pg.default_options(MaxOuterIters=2000, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=20,
+                              innerRelPrTol_coupl=1e-8, innerRelPrTol_constr=1e-8, innerRelDualTol_coupl=1e-8,
+                              innerRelDualTol_constr=1e-8)
+    Gd, od = ab.cmtf_fun_AOADMM(Z, pg.znorm_const(Z), G, None, None, None, None, opts)
+    assert od['f_couplings'] < 1e-12 and od['f_constraints'] < 1e-12
+    F = Gd['fac']
+    g = {}
+    for p, ms in enumerate(Z['modes']):
+        X, w = Z['object'][p], Z['weights'][p]
+        for pos, m in enumerate(ms):
+            had = np.ones((F[m - 1].shape[1],) * 2)
+            for q in ms:
+                if q != m:
+                    had = had * (F[q - 1].T @ F[q - 1])
+            M = oracle_mttkrp(X, [F[q - 1] for q in ms], pos) if X.ndim > 2 else (X @ F[ms[1] - 1] if pos == 0 else X.T @ F[ms[0] - 1])
+            g[m] = 2 * w * (F[m - 1] @ had - M)
+    lin = Z['coupling']['lin_coupled_modes']
+    groups = {}
+    for m in range(1, 8):
+        groups.setdefault(('c', lin[m - 1]) if lin[m - 1] else ('m', m), []).append(m)
+    for key, ms in groups.items():
+        total = sum(g[m] for m in ms)
+        Fm = F[ms[0] - 1]
+        for m in ms:
+            assert np.linalg.norm(F[m - 1] - Fm) < 1e-10
+        if any(Z['constrained_modes'][m - 1] for m in ms):
+            assert Fm.min() > -1e-12 and np.linalg.norm(np.minimum(Fm, total)) < 1e-9, key
+        else:
+            assert np.linalg.norm(total) < 1e-9, key
+        if len(ms) > 1:
+            assert min(np.linalg.norm(g[m]) for m in ms) > 1e-5
