@@ -1121,7 +1121,7 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
 }
 
 // third PARAFAC2 mode (:220-243): per-row right-hand sides and systems
-void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out) {
+void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out, const double* HHt) {
   Par2State& s = par2_[m.par2];
   ObjectState& o = objects_[m.p];
   ModeState &ma = mode(s.m1), &mb = mode(s.m2);
@@ -1146,6 +1146,7 @@ void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, do
   sa.Binv = s.Binv3;
   sa.Bsys = Bsys_out;
   sa.no_factor = (Bsys_out != nullptr) ? 1 : 0;
+  sa.HHt = HHt;
   sa.ctl = m.ctl;
   launches_ += par2_sys_prep(s.lay, sa, st_);
   launches_ += par2_rho_max(s.rho3, s.K, m.rho, st_);
@@ -1694,9 +1695,17 @@ void Engine::sweep(int iter, std::vector<int>& inner_fixed) {
             par2_update_B(m, iter);                                // :192-218
           } else {
             const bool ls = (coupl_id == 0 && !m.constrained);
-            if (m.lin >= 0)   // coupling type 1: B{m}{k} stay w*C_k, the coupled system is assembled later (:283-297)
+            if (m.lin >= 0 && lin_modes_[m.lin].par2c) {
+              // coupling type 1: B{m}{k} stay w*C_k, the coupled system is assembled later (:283-297)
               par2_precompute_C(m, 0, false, lin_modes_[m.lin].Bsys3);
-            else
+            } else if (m.lin >= 0) {
+              // coupling types 2, 3, 4: per-slice systems like the exact coupling (:305-311, :327-333, :349-355);
+              // type 2 replaces the coupling shift rho_k/2*I by rho_k/2*H*H'
+              const LinMode& lm = lin_modes_[m.lin];
+              const int con = m.constrained ? 1 : 0;
+              if (lm.ctype == 2) par2_precompute_C(m, con, false, nullptr, lm.HHt.p);
+              else par2_precompute_C(m, 1 + con, false);
+            } else
               par2_precompute_C(m, nterms, ls);                    // :220-243
             if (ls) {
               inner_fixed[m.id - 1] = 1;

@@ -76,6 +76,10 @@ struct LinMode {
   double* rho_stats = nullptr;  // [0] mean(rho), [1] sum(rho)
   const double* rho_A = nullptr;  // scalar rho used in A_inner  (m.rho, or mean(rho) for par2c)
   const double* rho_D = nullptr;  // scalar weight in the Delta update (m.rho, or sum(rho) for par2c)
+  // types 2, 3, 4 with a PARAFAC2 third mode (:305-311, :327-333, :349-355): row-wise rho_k and systems B{m}{k}
+  bool par2row = false;
+  DevMat Hs;                    // type 3: diag(rho) * H
+  DevMat AAA;                   // type 4: H * H'
 };
 
 struct LinGroup {
@@ -83,6 +87,9 @@ struct LinGroup {
   std::vector<int> modes;       // global ids, ascending
   DevMat Dold, Ddiff, AA, AAL, AAB, AAC, BB, Dt;
   double* AAinvdiag = nullptr;
+  int par2row = -1;             // position (in `modes`) of a third PARAFAC2 mode with row-wise rho, or -1
+  double* wsum = nullptr;       // type 2 with par2row: per-row sum of the weights (:813)
+  double* Minv = nullptr;       // type 4 with par2row: inv(AA + rho_k*AAA) per row (:957-960)
   double* scal = nullptr;       // device scalars: [0] sum rho, [1] 1/sum rho, [2] scratch rho of prep_system
   RedJob* jobs_dev = nullptr;
   int njobs = 0;
@@ -201,7 +208,8 @@ class Engine {
   void par2_update_T(Par2State& s);
   void par2_precompute_A(ModeState& m, int n_rho_terms, bool do_chol = true);
   void par2_update_B(ModeState& m, int outer_iter);
-  void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out = nullptr);
+  void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out = nullptr,
+                         const double* HHt = nullptr);
   void par2_refresh_gram(Par2State& s);
   DevMat* par2_field(int field, int index, int slice, int64_t* row_off, int64_t* nrows);
 

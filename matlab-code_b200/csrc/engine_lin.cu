@@ -44,9 +44,10 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
     // the first PARAFAC2 mode goes through the generic branches of :278-389 like a CP mode; the second one cannot be
     // coupled (:191); the third one has its own (K*R)^2 system for type 1 and per-slice Delta updates for types 4/5
     if (m.par2_role == 2) throw CudaError(1, "the second PARAFAC2 mode cannot be coupled");
-    if (m.par2_role == 3 && !par2c)
-      throw CudaError(2, "the third PARAFAC2 mode inside a linearly coupled group is supported for coupling type 1 only "
-                         "(coupling types 2..5 are not supported on device)");
+    const bool par2row = (m.par2_role == 3 && (ctype == 2 || ctype == 3 || ctype == 4));
+    if (m.par2_role == 3 && !par2c && !par2row)
+      throw CudaError(2, "the third PARAFAC2 mode inside a linearly coupled group is supported for coupling types 1..4 "
+                         "(coupling type 5 is not supported on device)");
     const int i = m.id - 1;
     if (prob->trafo == nullptr || prob->trafo[i] == nullptr)
       throw CudaError(1, "coupl_trafo_matrices{" + std::to_string(m.id) + "} is required for coupling type " + std::to_string(ctype));
@@ -86,7 +87,19 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
       dev_alloc(lm.HHt, m.R, m.R);
       launches_ += dgemm_small(0, 1, m.R, m.R, hc, 1.0, nullptr, lm.H.p, hr, lm.H.p, hr, 0.0, lm.HHt.p, m.R, st_, nullptr);
     }
-    if (par2c) {
+    if (par2row) {
+      if (g.par2row >= 0) throw CudaError(2, "at most one third PARAFAC2 mode per linearly coupled group");
+      lm.par2row = true;
+      g.par2row = (int)g.modes.size() - 1;
+      if (ctype == 3) dev_alloc(lm.Hs, hr, hc);
+      if (ctype == 4) {
+        dev_alloc(lm.AAA, hr, hr);
+        launches_ += dgemm_small(0, 1, hr, hr, hc, 1.0, nullptr, lm.H.p, hr, lm.H.p, hr, 0.0, lm.AAA.p, hr, st_, nullptr);
+        if (hr > 64) throw CudaError(2, "coupling type 4 with a PARAFAC2 third mode: at most 64 columns in the coupling factor");
+        AO_CUDA(cudaMalloc(&g.Minv, sizeof(double) * (size_t)m.rows * hr * hr));
+      }
+      if (ctype == 2) AO_CUDA(cudaMalloc(&g.wsum, sizeof(double) * (size_t)m.rows));
+    } else if (par2c) {
       const int64_t n = m.rows * m.R;
       if (n * 8 > 40 * 1024) throw CudaError(2, "coupling type 1 with a PARAFAC2 third mode: K*R must be <= 5120");
       lm.par2c = true;
@@ -191,13 +204,14 @@ void Engine::free_linear_coupling() {
       dev_free(*d);
     if (lm.lam) cudaFree(lm.lam);
     if (lm.muB) cudaFree(lm.muB);
-    for (DevMat* d : {&lm.HtH, &lm.B2, &lm.B2L, &lm.B2B, &lm.B2C}) dev_free(*d);
+    for (DevMat* d : {&lm.HtH, &lm.B2, &lm.B2L, &lm.B2B, &lm.B2C, &lm.Hs, &lm.AAA}) dev_free(*d);
     for (void* q : {(void*)lm.B2invdiag, (void*)lm.Bsys3, (void*)lm.rho_stats})
       if (q) cudaFree(q);
   }
   for (auto& g : lin_groups_) {
     for (DevMat* d : {&g.Dold, &g.Ddiff, &g.AA, &g.AAL, &g.AAB, &g.AAC, &g.BB, &g.Dt}) dev_free(*d);
-    for (void* p : {(void*)g.AAinvdiag, (void*)g.scal, (void*)g.jobs_dev, (void*)g.red, (void*)g.red_partials})
+    for (void* p : {(void*)g.AAinvdiag, (void*)g.scal, (void*)g.jobs_dev, (void*)g.red, (void*)g.red_partials,
+                    (void*)g.wsum, (void*)g.Minv})
       if (p) cudaFree(p);
   }
 }
@@ -283,7 +297,7 @@ void Engine::lin_prepare_group(int c) {
     a.ctl = ctl;
     launches_ += prep_system(a, st_, nullptr);
   }
-  if (g.ctype == 1 || g.ctype == 2) {
+  if ((g.ctype == 1 || g.ctype == 2) && g.par2row < 0) {
     LinTerm t[5];
     for (int i = 0; i < n; ++i) t[i] = LinTerm{nullptr, 1.0, lin_modes_[mode(g.modes[i]).lin].rho_D};
     launches_ += sum_recip(g.scal, t, n, st_);
@@ -300,17 +314,31 @@ void Engine::lin_prepare_group(int c) {
   if (g.ctype >= 3) {
     // AA = sum_j rho_j H_j'H_j (3) | sum_j rho_j H_j H_j' (4) | sum_j rhoC H2_j H2_j' (5, rhoC = rho of the LAST mode, :1032)
     const double* rhoC = mode(g.modes[n - 1]).rho;
+    bool first = true;
     for (int i = 0; i < n; ++i) {
       ModeState& m = mode(g.modes[i]);
       LinMode& lm = lin_modes_[m.lin];
-      const double beta = (i == 0) ? 0.0 : 1.0;
       const long long q = g.AA.rows;
-      if (g.ctype == 3)
+      if (lm.par2row && g.ctype == 4) continue;   // its rho_k * H H' enters the per-row systems below (:944-951)
+      const double beta = first ? 0.0 : 1.0;
+      first = false;
+      if (g.ctype == 3 && lm.par2row) {            // H' diag(rho) H (:878 with a vector rho)
+        launches_ += par2_rows_scale(lm.Hs.p, lm.H.p, m.rho_rows, lm.H.rows, (int)lm.H.cols, st_, nullptr);
+        launches_ += dgemm_small(1, 0, q, q, lm.H.rows, 1.0, nullptr, lm.H.p, lm.H.rows, lm.Hs.p, lm.H.rows, beta, g.AA.p, q, st_, nullptr);
+      } else if (g.ctype == 3)
         launches_ += dgemm_small(1, 0, q, q, lm.H.rows, 1.0, m.rho, lm.H.p, lm.H.rows, lm.H.p, lm.H.rows, beta, g.AA.p, q, st_, nullptr);
       else if (g.ctype == 4)
         launches_ += dgemm_small(0, 1, q, q, lm.H.cols, 1.0, m.rho, lm.H.p, lm.H.rows, lm.H.p, lm.H.rows, beta, g.AA.p, q, st_, nullptr);
       else
         launches_ += dgemm_small(0, 1, q, q, lm.H2.cols, 1.0, rhoC, lm.H2.p, lm.H2.rows, lm.H2.p, lm.H2.rows, beta, g.AA.p, q, st_, nullptr);
+    }
+    if (g.ctype == 4 && g.par2row >= 0) {
+      // Delta(k,:) = BB(k,:) / (AA + rho_k * H H')  (:957-960): K small inverses per outer iteration
+      ModeState& mp = mode(g.modes[g.par2row]);
+      LinMode& lp = lin_modes_[mp.lin];
+      if (first) AO_CUDA(cudaMemsetAsync(g.AA.p, 0, g.AA.bytes(), st_));   // no other mode in the group
+      launches_ += par2_rowsys_inverse(g.AA.p, lp.AAA.p, mp.rho_rows, (int)mp.rows, (int)g.AA.rows, g.Minv, ctl, st_);
+      return;
     }
     PrepArgs a{};
     a.nhad = 1;
@@ -350,6 +378,13 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
         launches_ += lincomb(lm.S2.p, nS, t, 2, st_, skip);
       }
       lin_Gt(lm, m, lm.S2.p, lm.tmpF.p, skip);
+      if (lm.par2row) {
+        // row k: A_inner = A{m}{k}' + rho_k/2 * (coupling term [+ Z - mu_Z]);  F(k,:) = (A_inner/L_k')/L_k  (:786-790 ...)
+        launches_ += par2_rows_ainner(lm.tmpF2.p, m.A.p, lm.tmpF.p, m.constrained ? m.Z.p : nullptr, m.muZ.p, m.rho_rows,
+                                      m.rows, m.R, st_, skip);
+        launches_ += par2_rows_apply(m.fac.p, lm.tmpF2.p, m.Binv_rows, m.rows, m.R, st_, skip);
+        continue;
+      }
       {
         LinTerm t[4] = {{m.A.p, 1.0, nullptr}, {lm.tmpF.p, 0.5, lm.rho_A}, {m.Z.p, 0.5, lm.rho_A}, {m.muZ.p, -0.5, lm.rho_A}};
         launches_ += lincomb(lm.tmpF.p, nF, t, m.constrained ? 4 : 2, st_, skip);
@@ -377,7 +412,10 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
       LinMode& lm = lin_modes_[m.lin];
       const long long nS = lm.S1.rows * lm.S1.cols;
       lin_G(lm, m, m.fac.p, lm.S1.p, skip);
-      if (g.ctype == 1 || g.ctype == 2) {  // :738-749, :808-815 rho-weighted mean
+      if (g.ctype == 2 && g.par2row >= 0) {   // :808-815 with a vector rho: row-wise weighted mean
+        launches_ += par2_rows_weighted_accum(D.p, g.wsum, lm.S1.p, m.muD.p, m.rho, lm.par2row ? m.rho_rows : nullptr, D.rows,
+                                              (int)D.cols, i == 0 ? 1 : 0, st_, skip);
+      } else if (g.ctype == 1 || g.ctype == 2) {  // :738-749, :808-815 rho-weighted mean
         if (i == 0) {
           LinTerm t[2] = {{lm.S1.p, 1.0, lm.rho_D}, {m.muD.p, 1.0, lm.rho_D}};
           launches_ += lincomb(D.p, nD, t, 2, st_, skip);
@@ -389,15 +427,24 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
         LinTerm t[2] = {{lm.S1.p, 1.0, nullptr}, {m.muD.p, 1.0, nullptr}};
         launches_ += lincomb(lm.S3.p, nS, t, 2, st_, skip);   // G(F) + mu
         const double beta = (i == 0) ? 0.0 : 1.0;
+        const double* rs = m.rho;   // scalar weight; a third PARAFAC2 mode scales its rows by rho_k first
+        if (lm.par2row) {
+          launches_ += par2_rows_scale(lm.S3.p, lm.S3.p, m.rho_rows, m.rows, m.R, st_, skip);
+          rs = nullptr;
+        }
         if (g.ctype == 3)       // BB' (R x q) += rho (F+mu)' H            (:879)
-          launches_ += dgemm_small(1, 0, m.R, lm.H.cols, m.rows, 1.0, m.rho, lm.S3.p, m.rows, lm.H.p, lm.H.rows, beta, g.BB.p, g.BB.rows, st_, skip);
+          launches_ += dgemm_small(1, 0, m.R, lm.H.cols, m.rows, 1.0, rs, lm.S3.p, m.rows, lm.H.p, lm.H.rows, beta, g.BB.p, g.BB.rows, st_, skip);
         else if (g.ctype == 4)  // BB (I x q) += rho (F+mu) H'              (:955)
-          launches_ += dgemm_small(0, 1, m.rows, lm.H.rows, m.R, 1.0, m.rho, lm.S3.p, m.rows, lm.H.p, lm.H.rows, beta, g.BB.p, g.BB.rows, st_, skip);
+          launches_ += dgemm_small(0, 1, m.rows, lm.H.rows, m.R, 1.0, rs, lm.S3.p, m.rows, lm.H.p, lm.H.rows, beta, g.BB.p, g.BB.rows, st_, skip);
         else                    // BB (q1 x q2) += rhoC (H F + mu) H2'      (:1046)
           launches_ += dgemm_small(0, 1, lm.S3.rows, lm.H2.rows, m.R, 1.0, rhoC, lm.S3.p, lm.S3.rows, lm.H2.p, lm.H2.rows, beta, g.BB.p, g.BB.rows, st_, skip);
       }
     }
-    if (g.ctype == 1 || g.ctype == 2) {
+    if (g.ctype == 2 && g.par2row >= 0) {
+      launches_ += par2_rows_divide(D.p, g.wsum, D.rows, (int)D.cols, st_, skip);
+    } else if (g.ctype == 4 && g.par2row >= 0) {   // Delta(k,:) = BB(k,:) / (AA + rho_k H H')  (:957-960)
+      launches_ += par2_rows_apply(D.p, g.BB.p, g.Minv, D.rows, (int)D.cols, st_, skip);
+    } else if (g.ctype == 1 || g.ctype == 2) {
       LinTerm t{D.p, 1.0, g.scal + 1};
       launches_ += lincomb(D.p, nD, &t, 1, st_, skip);
     } else if (g.ctype == 3) {   // Delta = AA\BB  (:881)  <=>  Delta' = BB' inv(AA)

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
       if (a.ridge != 0.0) b += a.ridge;
       if (a.bsum_half != 0.0) b += a.bsum_half;
     }
+    if (a.HHt != nullptr) b += half * a.HHt[e];
     W[e] = b;
     if (a.Bsys != nullptr) a.Bsys[(size_t)k * RR + e] = b;
   }
@@ -193,6 +194,85 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
     return;
   }
   cta_inverse_from_chol(W, V, R, a.Binv + (size_t)k * RR);
+}
+
+// ---- row-wise helpers for the third PARAFAC2 mode inside linear couplings 2..4 ------------------------------------
+__global__ void par2_rows_ainner_kernel(double* __restrict__ out, const double* __restrict__ A, const double* __restrict__ X,
+                                        const double* __restrict__ Z, const double* __restrict__ muZ,
+                                        const double* __restrict__ rho_k, long long rows, int cols,
+                                        const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const double half = rho_k[e % rows] / 2.0;
+    double v = A[e] + half * X[e];
+    if (Z != nullptr) v += half * (Z[e] - muZ[e]);
+    out[e] = v;
+  }
+}
+
+__global__ void par2_rows_apply_kernel(double* __restrict__ out, const double* __restrict__ in,
+                                       const double* __restrict__ Minv, long long rows, int q,
+                                       const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * q;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long k = e % rows;
+    const int c = (int)(e / rows);
+    const double* M = Minv + (size_t)k * q * q + (size_t)c * q;   // column c of M_k
+    double acc = 0.0;
+    for (int j = 0; j < q; ++j) acc = fma(in[k + rows * j], M[j], acc);
+    out[e] = acc;
+  }
+}
+
+__global__ void par2_rows_scale_kernel(double* __restrict__ out, const double* __restrict__ in,
+                                       const double* __restrict__ rho_k, long long rows, int cols,
+                                       const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    out[e] = rho_k[e % rows] * in[e];
+}
+
+__global__ void par2_rows_weighted_accum_kernel(double* __restrict__ D, double* __restrict__ wsum,
+                                                const double* __restrict__ S, const double* __restrict__ mu,
+                                                const double* __restrict__ rho_scalar, const double* __restrict__ rho_k,
+                                                long long rows, int cols, int first, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long k = e % rows;
+    const double w = (rho_k != nullptr) ? rho_k[k] : *rho_scalar;
+    const double v = w * (S[e] + mu[e]);
+    D[e] = first ? v : D[e] + v;
+    if (e < rows) wsum[k] = first ? w : wsum[k] + w;
+  }
+}
+
+__global__ void par2_rows_divide_kernel(double* __restrict__ D, const double* __restrict__ wsum, long long rows, int cols,
+                                        const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long n = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    D[e] = (1.0 / wsum[e % rows]) * D[e];
+}
+
+__global__ void __launch_bounds__(128) par2_rowsys_inverse_kernel(const double* __restrict__ AA, const double* __restrict__ AAA,
+                                                                  const double* __restrict__ rho_k, int q,
+                                                                  double* __restrict__ Minv, InnerCtl* ctl) {
+  extern __shared__ double sm[];
+  const int k = blockIdx.x, qq = q * q;
+  double* W = sm;
+  double* V = sm + qq;
+  const double rk = rho_k[k];
+  for (int e = threadIdx.x; e < qq; e += blockDim.x) W[e] = AA[e] + rk * AAA[e];
+  __syncthreads();
+  if (!cta_cholesky(W, q)) {
+    if (threadIdx.x == 0 && ctl != nullptr) ctl->err = 3;
+    return;
+  }
+  cta_inverse_from_chol(W, V, q, Minv + (size_t)k * qq);
 }
 
 __global__ void par2_rho_stats_kernel(const double* __restrict__ rho_k, int K, double* __restrict__ out) {
@@ -799,6 +879,51 @@ int par2_chol_solve_vec(const double* L, int K, int R, const double* a, double* 
   const size_t smem = (size_t)K * R * sizeof(double);
   if (smem > 40 * 1024) throw CudaError(2, "coupling type 1 with a PARAFAC2 third mode: K*R too large");
   par2_chol_solve_vec_kernel<<<1, 256, smem, st>>>(L, K, R, a, x, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rows_ainner(double* out, const double* A, const double* X, const double* Z, const double* muZ,
+                     const double* rho_k, long long rows, int cols, cudaStream_t st, const int* skip) {
+  par2_rows_ainner_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(out, A, X, Z, muZ, rho_k, rows, cols, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rows_apply(double* out, const double* in, const double* Minv, long long rows, int q, cudaStream_t st,
+                    const int* skip) {
+  par2_rows_apply_kernel<<<flat_grid(rows * q), 256, 0, st>>>(out, in, Minv, rows, q, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rows_scale(double* out, const double* in, const double* rho_k, long long rows, int cols, cudaStream_t st,
+                    const int* skip) {
+  par2_rows_scale_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(out, in, rho_k, rows, cols, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rows_weighted_accum(double* D, double* wsum, const double* S, const double* mu, const double* rho_scalar,
+                             const double* rho_k, long long rows, int cols, int first, cudaStream_t st, const int* skip) {
+  par2_rows_weighted_accum_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(D, wsum, S, mu, rho_scalar, rho_k, rows, cols,
+                                                                         first, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rows_divide(double* D, const double* wsum, long long rows, int cols, cudaStream_t st, const int* skip) {
+  par2_rows_divide_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(D, wsum, rows, cols, skip);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_rowsys_inverse(const double* AA, const double* AAA, const double* rho_k, int K, int q, double* Minv, InnerCtl* ctl,
+                        cudaStream_t st) {
+  if (q > 64) throw CudaError(2, "coupling type 4 with a PARAFAC2 third mode: at most 64 columns in the coupling factor");
+  const size_t smem = (size_t)2 * q * q * sizeof(double);
+  opt_in_smem(par2_rowsys_inverse_kernel, smem);
+  par2_rowsys_inverse_kernel<<<K, 128, smem, st>>>(AA, AAA, rho_k, q, Minv, ctl);
   AO_CHECK_LAUNCH();
   return 1;
 }

@@ -54,6 +54,7 @@ struct Par2SysArgs {
   double* Binv;            // K x R x R
   double* Bsys;            // optional: the assembled system matrices themselves (K x R x R)
   int no_factor;           // only assemble (rho_k, Bsys, rhs): the caller factors a larger system (coupling type 1)
+  const double* HHt;       // optional (mode 3, coupling type 2): B_k += rho_k/2 * H*H' (:307)
   InnerCtl* ctl;           // err = 3 when a system is not positive definite
 };
 int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st);
@@ -68,6 +69,26 @@ int par2_chol_solve_vec(const double* L, int K, int R, const double* a, double* 
 
 // rho_max = max_k rho_k (update_constraint uses max(rho) when rho is a vector, :1423-1424)
 int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st);
+
+// ---- third PARAFAC2 mode inside the linear couplings 2, 3, 4: row-wise rho_k and row-wise systems (:783-790, :848-855,
+// :914-921, :940-960).  All matrices are rows x cols column-major with leading dimension rows.
+// out(k,:) = A(k,:) + rho_k/2 * ( X(k,:) [+ Z(k,:) - muZ(k,:)] )                      (A_inner of row k)
+int par2_rows_ainner(double* out, const double* A, const double* X, const double* Z, const double* muZ,
+                     const double* rho_k, long long rows, int cols, cudaStream_t st, const int* skip);
+// out(k,:) = in(k,:) * M_k   with M_k the q x q matrix at Minv + k*q*q (symmetric)   ((A_inner/L')/L, BB(k,:)/(AA+AA_k))
+int par2_rows_apply(double* out, const double* in, const double* Minv, long long rows, int q, cudaStream_t st,
+                    const int* skip);
+// out(k,:) = rho_k * in(k,:)
+int par2_rows_scale(double* out, const double* in, const double* rho_k, long long rows, int cols, cudaStream_t st,
+                    const int* skip);
+// D(k,:) (+)= w_k * (S(k,:) + mu(k,:)),  wsum[k] (+)= w_k,  w_k = rho_k[k] (rho_k != nullptr) or *rho_scalar  (:808-813)
+int par2_rows_weighted_accum(double* D, double* wsum, const double* S, const double* mu, const double* rho_scalar,
+                             const double* rho_k, long long rows, int cols, int first, cudaStream_t st, const int* skip);
+// D(k,:) /= wsum[k]                                                                    (:815)
+int par2_rows_divide(double* D, const double* wsum, long long rows, int cols, cudaStream_t st, const int* skip);
+// Minv_k = inv(AA + rho_k * AAA), k < K (q x q each, q <= 64); ctl->err = 3 when a matrix is not positive definite  (:957-960)
+int par2_rowsys_inverse(const double* AA, const double* AAA, const double* rho_k, int K, int q, double* Minv, InnerCtl* ctl,
+                        cudaStream_t st);
 
 struct Par2BArgs {
   const double* A;         // stacked right-hand sides A_k (Jtot x R)

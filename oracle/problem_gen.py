@@ -487,26 +487,35 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
     elif second == 'par2':       # the first (A) mode of a PARAFAC2 object takes the place of the second tensor's mode
         sz = [I1, 14, 12, I4, [11] * 7, 7]
         modes = [[1, 2, 3], [4, 5, 6]]
+    elif second == 'par2c':      # the third (C) mode of a PARAFAC2 object (K = I4 slices) is the coupled one
+        sz = [I1, 14, 12, 16, [11] * I4, I4]
+        modes = [[1, 2, 3], [4, 5, 6]]
     else:
         sz = [I1, 14, 12, I4, 11, 9]
         modes = [[1, 2, 3], [4, 5, 6]]
     nm = len(sz)
     trafo = [None] * nm
     trafo2 = [None] * nm
+    second_mode = 6 if second == 'par2c' else 4
     for m, h in H.items():
-        trafo[m - 1] = h
+        trafo[(m if m == 1 else second_mode) - 1] = h
     for m, h in H2.items():
-        trafo2[m - 1] = h
+        trafo2[(m if m == 1 else second_mode) - 1] = h
     lin = [0] * nm
-    lin[0] = lin[3] = 1
+    lin[0] = lin[second_mode - 1] = 1
     coupling = {'lin_coupled_modes': lin, 'coupling_type': [ctype], 'coupl_trafo_matrices': trafo}
     if ctype == 5:
         coupling['coupl_trafo_matrices2'] = trafo2
     lambdas = [[1.0] * R1, [1.0] * R2]
     distr = [d_rand] * nm
-    model = ['CP', 'PAR2' if second == 'par2' else 'CP']
+    model = ['CP', 'PAR2' if second in ('par2', 'par2c') else 'CP']
     Delta_shapes = None
-    if ctype == 5 and second == 'par2':
+    if second == 'par2c':
+        free = {'lin_coupled_modes': [0] * nm, 'coupling_type': [], 'coupl_trafo_matrices': [None] * nm}
+        X, _, _ = create_coupled_data(model, sz, modes, lambdas, [noise] * 2, free, 0, distr, rng)
+        if ctype == 5:
+            Delta_shapes = [rng.rand(20, 4)]
+    elif ctype == 5 and second == 'par2':
         Delta_shapes = [rng.rand(20, 4)]
         free = {'lin_coupled_modes': [0] * nm, 'coupling_type': [], 'coupl_trafo_matrices': [None] * nm}
         X, _, _ = create_coupled_data(model, sz, modes, lambdas, [noise] * 2, free, 0, distr, rng)
@@ -531,7 +540,7 @@ def config_linear_coupling(ctype, seed=0, noise=0.05, constrained=True, second='
     cm = [0] * nm
     cons = [None] * nm
     if constrained:
-        for m in ((1, 4, 6) if second == 'par2' else (1, 4, 5)):
+        for m in ((1, 4, 6) if second in ('par2', 'par2c') else (1, 4, 5)):
             cm[m - 1] = 1
             cons[m - 1] = nn
     Z = {'loss_function': ['Frobenius'] * 2, 'model': model, 'modes': modes, 'size': sz, 'coupling': coupling,

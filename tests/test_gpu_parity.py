@@ -407,6 +407,18 @@ def test_linear_couplings_with_first_parafac2_mode(ab, ctype, constrained):
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
+@pytest.mark.parametrize('ctype', [1, 2, 3, 4])
+@pytest.mark.parametrize('constrained', [True, False])
+def test_linear_couplings_with_third_parafac2_mode(ab, ctype, constrained):
+    """A CP mode linearly coupled with the third (C) mode of a PARAFAC2 object: row-wise rho_k and per-slice systems
+    B{m}{k} (types 2-4: :305-311, :327-333, :349-355, :783-790, :848-855, :914-921; per-row Delta systems of type 4
+    :940-960; type 1 is the (K*R)^2 system of example_script14)."""
+    Z, G, _ = pg.config_linear_coupling(ctype, seed=30 + ctype, constrained=constrained, second='par2c')
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=12))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def _assert_missing_close(od, oo):
     n = oo['OuterIterations'] + 1
     a, b = od['func_rel_missing'][1:n], oo['func_rel_missing'][1:n]
