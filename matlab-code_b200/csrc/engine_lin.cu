@@ -40,14 +40,13 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
   dev_alloc(g.Ddiff, dr, dc);
   for (auto& m : modes_) {
     if (m.coupling != c) continue;
-    const bool par2c = (m.par2_role == 3 && ctype == 1);  // example_script14: H C = Delta with C of a PARAFAC2 model
+    // example_script14: H C = Delta with C of a PARAFAC2 model; type 5 (H C = Delta H2) shares the (K*R)^2 system
+    const bool par2c = (m.par2_role == 3 && (ctype == 1 || ctype == 5));
     // the first PARAFAC2 mode goes through the generic branches of :278-389 like a CP mode; the second one cannot be
     // coupled (:191); the third one has its own (K*R)^2 system for type 1 and per-slice Delta updates for types 4/5
     if (m.par2_role == 2) throw CudaError(1, "the second PARAFAC2 mode cannot be coupled");
     const bool par2row = (m.par2_role == 3 && (ctype == 2 || ctype == 3 || ctype == 4));
-    if (m.par2_role == 3 && !par2c && !par2row)
-      throw CudaError(2, "the third PARAFAC2 mode inside a linearly coupled group is supported for coupling types 1..4 "
-                         "(coupling type 5 is not supported on device)");
+    if (m.par2_role == 3 && !par2c && !par2row) throw CudaError(1, "coupling_type must be in 0..5");
     const int i = m.id - 1;
     if (prob->trafo == nullptr || prob->trafo[i] == nullptr)
       throw CudaError(1, "coupl_trafo_matrices{" + std::to_string(m.id) + "} is required for coupling type " + std::to_string(ctype));
@@ -111,6 +110,16 @@ void Engine::setup_linear_coupling(const aoadmm_problem* prob, int c) {
       AO_CUDA(cudaMalloc(&lm.rho_stats, sizeof(double) * 2));
       lm.rho_A = lm.rho_stats;       // mean(rho{mm})  (:712)
       lm.rho_D = lm.rho_stats + 1;   // sum(rho{jj})   (:742)
+      if (ctype == 5) {              // per-row Delta systems AA + rho_k * H2 H2' for the first size(Delta,1) slices (:1033-1051)
+        if (g.par2row >= 0) throw CudaError(2, "at most one third PARAFAC2 mode per linearly coupled group");
+        g.par2row = (int)g.modes.size() - 1;
+        const int64_t q2 = lm.H2.rows;
+        if (q2 > 64) throw CudaError(2, "coupling type 5 with a PARAFAC2 third mode: at most 64 columns in the coupling factor");
+        if (dr > m.rows) throw CudaError(1, "coupling type 5 with a PARAFAC2 third mode: coupling_fac has more rows than slices");
+        dev_alloc(lm.AAA, q2, q2);
+        launches_ += dgemm_small(0, 1, q2, q2, lm.H2.cols, 1.0, nullptr, lm.H2.p, q2, lm.H2.p, q2, 0.0, lm.AAA.p, q2, st_, nullptr);
+        AO_CUDA(cudaMalloc(&g.Minv, sizeof(double) * (size_t)dr * q2 * q2));
+      }
     } else if (ctype == 1 || ctype == 5) {
       // eigen-decomposition H'H = U diag(lam) U' once: one-sided Jacobi on H (q x I)
       if (m.rows > 4096) throw CudaError(2, "coupling types 1/5 support at most 4096 rows in the coupled factor");
@@ -313,13 +322,16 @@ void Engine::lin_prepare_group(int c) {
   }
   if (g.ctype >= 3) {
     // AA = sum_j rho_j H_j'H_j (3) | sum_j rho_j H_j H_j' (4) | sum_j rhoC H2_j H2_j' (5, rhoC = rho of the LAST mode, :1032)
-    const double* rhoC = mode(g.modes[n - 1]).rho;
+    // rhoC = mean(rho) of the LAST mode of the group (:1032; a scalar rho is its own mean)
+    const double* rhoC = lin_modes_[mode(g.modes[n - 1]).lin].par2c ? lin_modes_[mode(g.modes[n - 1]).lin].rho_stats
+                                                                      : mode(g.modes[n - 1]).rho;
     bool first = true;
     for (int i = 0; i < n; ++i) {
       ModeState& m = mode(g.modes[i]);
       LinMode& lm = lin_modes_[m.lin];
       const long long q = g.AA.rows;
       if (lm.par2row && g.ctype == 4) continue;   // its rho_k * H H' enters the per-row systems below (:944-951)
+      if (lm.par2c && g.ctype == 5) continue;     // likewise rho_k * H2 H2' (:1033-1040)
       const double beta = first ? 0.0 : 1.0;
       first = false;
       if (g.ctype == 3 && lm.par2row) {            // H' diag(rho) H (:878 with a vector rho)
@@ -338,6 +350,13 @@ void Engine::lin_prepare_group(int c) {
       LinMode& lp = lin_modes_[mp.lin];
       if (first) AO_CUDA(cudaMemsetAsync(g.AA.p, 0, g.AA.bytes(), st_));   // no other mode in the group
       launches_ += par2_rowsys_inverse(g.AA.p, lp.AAA.p, mp.rho_rows, (int)mp.rows, (int)g.AA.rows, g.Minv, ctl, st_);
+      return;
+    }
+    if (g.ctype == 5 && g.par2row >= 0) {
+      ModeState& mp = mode(g.modes[g.par2row]);
+      LinMode& lp = lin_modes_[mp.lin];
+      if (first) AO_CUDA(cudaMemsetAsync(g.AA.p, 0, g.AA.bytes(), st_));
+      launches_ += par2_rowsys_inverse(g.AA.p, lp.AAA.p, mp.rho_rows, (int)delta_[c - 1].rows, (int)g.AA.rows, g.Minv, ctl, st_);
       return;
     }
     PrepArgs a{};
@@ -406,7 +425,7 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
     }
     // ---- Delta update
     AO_CUDA(cudaMemcpyAsync(g.Dold.p, D.p, D.bytes(), cudaMemcpyDeviceToDevice, st_));
-    const double* rhoC = group[n - 1]->rho;
+    const double* rhoC = lin_modes_[group[n - 1]->lin].par2c ? lin_modes_[group[n - 1]->lin].rho_stats : group[n - 1]->rho;
     for (int i = 0; i < n; ++i) {
       ModeState& m = *group[i];
       LinMode& lm = lin_modes_[m.lin];
@@ -442,7 +461,7 @@ void Engine::run_admm_linear(int c, std::vector<ModeState*>& group, const aoadmm
     }
     if (g.ctype == 2 && g.par2row >= 0) {
       launches_ += par2_rows_divide(D.p, g.wsum, D.rows, (int)D.cols, st_, skip);
-    } else if (g.ctype == 4 && g.par2row >= 0) {   // Delta(k,:) = BB(k,:) / (AA + rho_k H H')  (:957-960)
+    } else if ((g.ctype == 4 || g.ctype == 5) && g.par2row >= 0) {   // Delta(k,:) = BB(k,:) / (AA + rho_k H H')  (:957-960, :1048-1051)
       launches_ += par2_rows_apply(D.p, g.BB.p, g.Minv, D.rows, (int)D.cols, st_, skip);
     } else if (g.ctype == 1 || g.ctype == 2) {
       LinTerm t{D.p, 1.0, g.scal + 1};

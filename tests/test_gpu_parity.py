@@ -407,7 +407,7 @@ def test_linear_couplings_with_first_parafac2_mode(ab, ctype, constrained):
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
-@pytest.mark.parametrize('ctype', [1, 2, 3, 4])
+@pytest.mark.parametrize('ctype', [1, 2, 3, 4, 5])
 @pytest.mark.parametrize('constrained', [True, False])
 def test_linear_couplings_with_third_parafac2_mode(ab, ctype, constrained):
     """A CP mode linearly coupled with the third (C) mode of a PARAFAC2 object: row-wise rho_k and per-slice systems
