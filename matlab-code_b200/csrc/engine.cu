@@ -217,7 +217,11 @@ void h2d_copy_large(void* dst, const void* src, size_t bytes, int device) {
   const size_t nchunks = (bytes + kChunk - 1) / kChunk;
   std::vector<cudaError_t> status(T, cudaSuccess);
   char* staging = nullptr;  // one page-locked block: two chunks per worker
-  AO_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&staging), (size_t)T * 2 * kChunk, cudaHostAllocDefault));
+  if (cudaHostAlloc(reinterpret_cast<void**>(&staging), (size_t)T * 2 * kChunk, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();   // no page-locked memory to spare: let the driver stage the copy
+    AO_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return;
+  }
   auto worker = [&](int t) {
     cudaError_t e = cudaSetDevice(device);
     void* buf[2] = {staging + ((size_t)t * 2) * kChunk, staging + ((size_t)t * 2 + 1) * kChunk};
