@@ -590,3 +590,52 @@ def config_script14(I=20, J=14, K=12, I2=16, Jk=10, Kp=40, R=3, seed=0, noise=0.
     cm = [1, 0, 0, 1, 0, 1 if constrained_c else 0]
     cons = [nn, None, None, nn, None, nn if constrained_c else None]
     return _finish(['CP', 'PAR2'], sz, modes, lambdas, [noise] * 2, coupling, distr, cm, cons, [0.5, 0.5], rng)
+
+
+def config_script2(I=20, J=30, I2=20, Jk=12, Kp=8, R=3, seed=0, noise=0.1):
+    """example_script2_matrix_PAR2_nonneg.m:20-64: a matrix exactly coupled (mode 1) with the first mode of a regular
+    PARAFAC2 object, every mode non-negative, weights [1/2 1/2]."""
+    rng = np.random.RandomState(seed)
+    sz = [I, J, I2, [Jk] * Kp, Kp]
+    modes = [[1, 2], [3, 4, 5]]
+    coupling = {'lin_coupled_modes': [1, 0, 1, 0, 0], 'coupling_type': [0], 'coupl_trafo_matrices': [None] * 5}
+    nn = ('non-negativity',)
+    return _finish(['CP', 'PAR2'], sz, modes, [[1.0] * R] * 2, [noise] * 2, coupling, [d_rand] * 5, [1] * 5, [nn] * 5,
+                   [0.5, 0.5], rng)
+
+
+def config_script15(I=28, dims1=(13, 11), dims2=(9, 12), M=17, seed=0, noise=0.1):
+    """example_script15_realdata.m:35-77 with synthetic data of the same structure: two 3-way CP tensors (3 and 5
+    components) and a matrix (5 components) that share the sample mode through ONE type-4 coupling C_m = Delta*H_m with
+    three members (Delta: I x 6; H_1 = [I_3; 0], H_4 = [I_5; 0], H_7 = T, :47-51), all modes non-negative, weights 1/3."""
+    rng = np.random.RandomState(seed)
+    sz = [I, dims1[0], dims1[1], I, dims2[0], dims2[1], I, M]
+    modes = [[1, 2, 3], [4, 5, 6], [7, 8]]
+    lambdas = [[1.0] * 3, [1.0] * 5, [1.0] * 5]
+    T = np.vstack([np.hstack([np.eye(4), np.zeros((4, 1))]), np.zeros((1, 5)), np.array([[0, 0, 0, 0, 1.0]])])
+    trafo = [None] * 8
+    trafo[0] = np.vstack([np.eye(3), np.zeros((3, 3))])
+    trafo[3] = np.vstack([np.eye(5), np.zeros((1, 5))])
+    trafo[6] = T
+    coupling = {'lin_coupled_modes': [1, 0, 0, 1, 0, 0, 1, 0], 'coupling_type': [4], 'coupl_trafo_matrices': trafo}
+    # ground truth with the coupling structure: C_m = Delta * H_m
+    Delta = rng.rand(I, 6)
+    A = [None] * 8
+    for p in range(3):
+        for n in modes[p]:
+            A[n - 1] = rng.rand(sz[n - 1], len(lambdas[p]))
+    for m in (1, 4, 7):
+        A[m - 1] = Delta @ trafo[m - 1]
+    X = []
+    for p in range(3):
+        Xp = full_ktensor([A[m - 1] for m in modes[p]], lambdas[p])
+        N = rng.randn(*Xp.shape)
+        X.append(np.asfortranarray(Xp + noise * np.linalg.norm(Xp) / np.linalg.norm(N) * N))
+    model = ['CP'] * 3
+    obj, _ = normalize_objects(X, model)
+    nn = ('non-negativity',)
+    Z = {'loss_function': ['Frobenius'] * 3, 'model': model, 'modes': modes, 'size': sz, 'coupling': coupling,
+         'constrained_modes': [1] * 8, 'constraints': [nn] * 8, 'weights': [1 / 3] * 3, 'object': obj}
+    init_options = {'lambdas_init': lambdas, 'nvecs': 0, 'distr': [d_rand] * 8, 'normalize': 0}
+    G = init_coupled_AOADMM_CMTF(Z, init_options, rng)
+    return Z, G, {'Delta': Delta}

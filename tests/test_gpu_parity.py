@@ -811,3 +811,24 @@ def test_engine_fixed_point_satisfies_kkt_without_the_oracle(ab):
             assert np.linalg.norm(total) < 1e-9, key
         if len(ms) > 1:
             assert min(np.linalg.norm(g[m]) for m in ms) > 1e-5
+
+
+def test_example_script2_matrix_coupled_with_first_parafac2_mode(ab):
+    """example_script2_matrix_PAR2_nonneg.m: a matrix exactly coupled with mode A of a regular PARAFAC2 object."""
+    Z, G, _ = pg.config_script2(seed=2)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=25))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
+def test_example_script15_structure_three_member_type4_coupling(ab):
+    """example_script15_realdata.m structure: two CP tensors (3 and 5 components) and a matrix (5 components) share
+    their sample mode through one type-4 coupling C_m = Delta*H_m with three members and a 6-column Delta."""
+    Z, G, _ = pg.config_script15(seed=3)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=40))
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=10, **ZERO_TOL))
+    assert np.all(oo['innerIters'][[0, 3, 6], :] == 5)
+    _assert_out_close(od, oo)
+    assert_state_close(Gd, Go)
