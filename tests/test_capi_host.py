@@ -138,3 +138,23 @@ def test_mex_gateway_compiles_against_stub_mex_header():
     assert nv.startswith('function U = cmtf_nvecs(Z,n,r)')
     shim = open(os.path.join(ROOT, 'matlab-code_b200', 'matlab', 'cmtf_fun_AOADMM.m')).read()
     assert shim.startswith('function [G,out] = cmtf_fun_AOADMM(Z,Znorm_const,G,fh,gh,lscalar,uscalar,options)')
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the engine) needs no GPU: one JSON line with the
+    contract keys, the CPU baseline description and an end-to-end block without device copies."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'ao_admm_outer_iters_per_s' and line['unit'] == 'outer_iters/s'
+    assert line['higher_is_better'] is True and line['n_gpus'] == 1 and line['steps'] == 1 and line['dtype'] == 'f64'
+    assert line['value'] > 0 and line['ms_per_step'] > 0 and line['vs_baseline'] is None and line['data'] == 'synthetic'
+    assert 'workload' in line['config'] and 'model' not in line['config']
+    cb = line['cpu_baseline']
+    assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['sample'] and cb['value'] == line['value']
+    e2e = line['e2e']
+    assert e2e['value'] == line['value'] and e2e['h2d_bytes_per_step'] == 0 and e2e['d2h_bytes_per_step'] == 0
