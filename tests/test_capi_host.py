@@ -158,3 +158,32 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['sample'] and cb['value'] == line['value']
     e2e = line['e2e']
     assert e2e['value'] == line['value'] and e2e['h2d_bytes_per_step'] == 0 and e2e['d2h_bytes_per_step'] == 0
+
+
+def test_init_front_end_host_logic_matches_oracle_without_device(ab):
+    """ab.init_coupled_AOADMM_CMTF (init_coupled_AOADMM_CMTF.m:37-169) with random factors and no constrained mode is
+    pure host logic: same shapes and, with the same random stream, the same numbers as the oracle's restatement, for
+    every coupling type and for PARAFAC2 objects."""
+    from oracle import problem_gen as pg
+    cases = [pg.config_linear_coupling(ct, seed=ct, constrained=False)[0] for ct in (1, 2, 3, 4)]
+    cases.append(pg.config_single_par2(seed=1, constrained=(0, 0, 0))[0])
+    Zs, _, _ = pg.config_script6(seed=1, sz=(6, 7, 5, 6, 8, 7, 9))
+    cases.append(dict(Zs, constrained_modes=[0] * 7))
+    for Z in cases:
+        P = len(Z['modes'])
+        R = 3
+        lambdas = []
+        for p in range(P):
+            lambdas.append([1.0] * (4 if (Z['coupling'].get('coupling_type') in ([2], [4]) and p == 0) else R))
+        r1, r2 = np.random.RandomState(5), np.random.RandomState(5)
+        io = {'lambdas_init': lambdas, 'nvecs': 0, 'normalize': 1}
+        Go = pg.init_coupled_AOADMM_CMTF(Z, dict(io, distr=[pg.d_rand] * len(Z['size'])), r2)
+        Gd = ab.init_coupled_AOADMM_CMTF(Z, dict(io, distr=[lambda a, b: r1.rand(a, b)] * len(Z['size'])), rng=r1)
+        for key in ('fac', 'coupling_fac', 'coupling_dual_fac', 'P', 'DeltaB', 'mu_DeltaB'):
+            for a, b in zip(Gd[key], Go[key]):
+                if b is None:
+                    assert a is None
+                elif isinstance(b, list):
+                    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), key
+                else:
+                    assert np.array_equal(a, b), key
