@@ -454,9 +454,17 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
         if (s.joff[k + 1] - s.joff[k] != s.Jmax) throw CudaError(1, "tPARAFAC2 needs slices of equal size");
     }
     if (m.con.kind == AOADMM_CON_QUADRATIC) {
-      if (m.par2_role == 2) throw CudaError(2, "quadratic regularization on the second PARAFAC2 mode is not supported on device");
-      if (m.con.matrix_n != m.rows) throw CudaError(1, "quadratic regularization: L must be rows x rows");
-      quad_prox_setup(m.quad, m.con.matrix, m.rows, m.con.p0, m.R, st_);
+      int64_t nq = m.rows;
+      if (m.par2_role == 2) {
+        // one L for every slice (constraints_to_prox.m:60-66 applied to G.fac{m}{k}, :567-568): regular slices only
+        const Par2State& s = par2_[m.par2];
+        nq = s.joff[1] - s.joff[0];
+        for (int k = 0; k < s.K; ++k)
+          if (s.joff[k + 1] - s.joff[k] != nq)
+            throw CudaError(1, "quadratic regularization on the second PARAFAC2 mode needs slices of equal size");
+      }
+      if (m.con.matrix_n != nq) throw CudaError(1, "quadratic regularization: L must be rows x rows");
+      quad_prox_setup(m.quad, m.con.matrix, nq, m.con.p0, m.R, st_);
       m.con.matrix = nullptr;  // the host buffer belongs to the caller
     }
   }
@@ -1245,7 +1253,11 @@ void Engine::build_objective_jobs() {
   for (int i = 0; i < nb_modes_; ++i) {
     ModeState& m = modes_[i];
     auto& t = terms_->mode[i];
-    if (m.par2_role == 2) continue;  // per-slice terms come from par2_seg_norms
+    if (m.par2_role == 2) {          // per-slice terms come from par2_seg_norms ...
+      if (m.constrained && m.con.kind == AOADMM_CON_QUADRATIC)   // ... except sum_k eta*trace(B_k' L B_k): L*B_k in m.V
+        t.idx_reg = add(RED_DOT, m.fac.p, m.V.p, m.rows, m.R);
+      continue;
+    }
     t.idx_norm2 = add(RED_NORM2, m.fac.p, nullptr, m.rows, m.R);
     if (m.constrained) t.idx_diffZ = add(RED_DIFF2, m.fac.p, m.Z.p, m.rows, m.R);
     if (m.coupling != 0 && m.lin < 0) t.idx_diffD = add(RED_DIFF2, m.fac.p, delta_[m.coupling - 1].p, m.rows, m.R);
@@ -1393,8 +1405,17 @@ void Engine::enqueue_objective(bool first) {
     }
   }
   for (auto& m : modes_)
-    if (m.constrained && m.con.kind == AOADMM_CON_QUADRATIC)
-      launches_ += dgemm_small(0, 0, m.rows, m.R, m.rows, 1.0, nullptr, m.quad.L, m.rows, m.fac.p, m.rows, 0.0, m.V.p, m.rows, st_, nullptr);
+    if (m.constrained && m.con.kind == AOADMM_CON_QUADRATIC) {
+      if (m.par2_role == 2) {   // the same L on every (regular) slice of the stacked B
+        const Par2State& s = par2_[m.par2];
+        const long long J = m.quad.n;
+        for (int k = 0; k < s.K; ++k)
+          launches_ += dgemm_small(0, 0, J, m.R, J, 1.0, nullptr, m.quad.L, J, m.fac.p + s.joff[k], m.rows, 0.0,
+                                   m.V.p + s.joff[k], m.rows, st_, nullptr);
+      } else {
+        launches_ += dgemm_small(0, 0, m.rows, m.R, m.rows, 1.0, nullptr, m.quad.L, m.rows, m.fac.p, m.rows, 0.0, m.V.p, m.rows, st_, nullptr);
+      }
+    }
   for (auto& m : modes_)
     if (m.lin >= 0) {
       LinMode& lm = lin_modes_[m.lin];
@@ -1471,6 +1492,7 @@ void Engine::finish_objective(bool first, double f[4]) {
     const ModeState& m = modes_[i];
     if (m.par2_role == 2) {
       if (m.constrained && reg_red_kind(m.con.kind) >= 0) f_tensors += m.con.p0 * st2[m.par2].reg;
+      if (terms_->mode[i].idx_reg >= 0) f_tensors += m.con.p0 * r[terms_->mode[i].idx_reg];   // quadratic regularization
       continue;
     }
     const int ir = terms_->mode[i].idx_reg;

@@ -832,3 +832,17 @@ def test_example_script15_structure_three_member_type4_coupling(ab):
     assert np.all(oo['innerIters'][[0, 3, 6], :] == 5)
     _assert_out_close(od, oo)
     assert_state_close(Gd, Go)
+
+
+def test_quadratic_regularization_on_parafac2_bk(ab):
+    """'quadratic regularization' (eta*trace(B_k' L B_k), constraints_to_prox.m:60-67) on the B_k mode of a regular
+    PARAFAC2 object: one L (second-difference Laplacian) for every slice, per-slice rho_k in the prox."""
+    J = 9
+    L = 2.0 * np.eye(J) - np.eye(J, k=1) - np.eye(J, k=-1)
+    L[0, 0] = L[-1, -1] = 1.0
+    nn = ('non-negativity',)
+    Z, G, _ = pg.config_single_par2(I=14, Jk=(J,) * 5, R=3, seed=6, noise=0.05, constrained=(1, 1, 1),
+                                    constraints=[nn, ('quadratic regularization', 0.05, L), nn])
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=10))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
