@@ -420,3 +420,27 @@ def test_oracle_linear_coupling_fixed_point_satisfies_kkt():
         assert max(np.linalg.norm(f) for f in feas) < 1e-8, ct
         assert np.linalg.norm(stat) < 1e-8 and min(np.linalg.norm(g[1]), np.linalg.norm(g[4])) > 1e-4, ct
         assert max(np.linalg.norm(g[m]) for m in (2, 3, 5)) < 1e-8, ct
+
+
+def test_oracle_em_fixed_point_is_a_kkt_point_of_the_masked_problem():
+    """Missing data (Z.miss, EM imputation :408-441): at the fixed point the imputed entries equal the model, so the
+    factors must be a KKT point of the MASKED problem  min sum_observed (x - [[A,B,C]])^2, A,B,C >= 0  — checked with the
+    explicitly masked residual, which the algorithm never forms."""
+    from oracle.tensor_ops import full_ktensor, mttkrp
+    nn = ('non-negativity',)
+    Z, G, _ = pg.config_single_cp(sz=(14, 12, 10), R=3, seed=4, noise=0.1, constraints=[nn, nn, nn])
+    Zm = pg.add_missing(Z, 0.3, seed=2)
+    X0, M = Zm['object'][0].copy(), Zm['miss'][0]
+    opts = pg.default_options(MaxOuterIters=2000, AbsFuncTol=0.0, OuterRelTol=1e-15, MaxInnerIters=20,
+                              innerRelPrTol_coupl=1e-9, innerRelPrTol_constr=1e-9, innerRelDualTol_coupl=1e-9,
+                              innerRelDualTol_constr=1e-9)
+    Go, oo = cmtf_fun_AOADMM(Zm, pg.znorm_const(Zm), G, options=opts)
+    assert oo['f_rel_missing'] < 1e-10
+    F = Go['fac']
+    E = np.where(M, X0 - full_ktensor(F), 0.0)
+    active = 0
+    for pos in range(3):
+        g = -2 * mttkrp(E, F, pos)
+        assert F[pos].min() > -1e-12 and np.linalg.norm(np.minimum(F[pos], g)) < 1e-9, pos
+        active += np.linalg.norm(g) > 1e-4
+    assert active >= 1            # at least one mode sits on its bounds with a non-zero gradient
