@@ -187,3 +187,14 @@ def test_init_front_end_host_logic_matches_oracle_without_device(ab):
                     assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), key
                 else:
                     assert np.array_equal(a, b), key
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+    """INTEGRATION.md maps every C-ABI entry point to the reference interface it replaces."""
+    import re
+    header = open(os.path.join(ROOT, 'include', 'aoadmm.h')).read()
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    funcs = set(re.findall(r'\b(aoadmm_[a-z_0-9]+)\s*\(', header))
+    funcs -= {'aoadmm_status', 'aoadmm_abi_version', 'aoadmm_device_count'}   # the status enum; two trivial queries
+    missing = sorted(f for f in funcs if f not in doc)
+    assert not missing, missing
