@@ -166,6 +166,10 @@ class Solver:
                 if miss[p] is not None:
                     if not isinstance(miss[p], (list, tuple)) or len(miss[p]) != len(sl):
                         raise AoadmmError(1, 'Z.miss{%d} must be a cell array of length %d for PAR2.' % (p + 1, len(sl)))
+                    for k, m in enumerate(miss[p]):          # cmtf_AOADMM.m:107-114
+                        ma = np.asarray(m)
+                        if ma.dtype != np.bool_ and not (np.issubdtype(ma.dtype, np.number) and np.all((ma == 0) | (ma == 1))):
+                            raise AoadmmError(1, 'Z.miss{%d}{%d} must be a logical or binary (0/1) array.' % (p + 1, k + 1))
                     mk = [np.asfortranarray(np.asarray(m) != 0, dtype=np.uint8) for m in miss[p]]
                     for k, (m, x) in enumerate(zip(mk, sl)):
                         if m.shape != x.shape:
