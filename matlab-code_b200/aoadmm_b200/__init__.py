@@ -512,6 +512,11 @@ def cmtf_AOADMM(Z, init, alg_options, init_options=None, **dist):
     The front end only computes Znorm_const (:124-156) and packs Zhat (:197-206); constraints stay named specs
     because the device cannot call MATLAB/Python function handles ('custom' -> AoadmmError UNSUPPORTED)."""
     P = len(Z['object'])
+    for m, con in enumerate(Z['constraints']):                             # :33-39
+        if Z['constrained_modes'][m] and con and con[0] == 'tPARAFAC2':
+            p = [q for q in range(P) if (m + 1) in Z['modes'][q]][0]
+            if Z['model'][p] != 'PAR2' or list(Z['modes'][p]).index(m + 1) != 1:
+                raise ValueError('The tPARAFAC2 constraint can only be imposed on the second mode of a PARAFAC2 model')
     if isinstance(init, str):                                              # :44-53
         if init.lower() != 'random':
             raise ValueError('Initialization type not supported')

@@ -110,6 +110,9 @@ def test_unsupported_inputs_raise_before_touching_the_device(ab):
     Zm = dict(Z, miss=[np.ones((3, 3, 3)), None, None])       # cmtf:missingData:maskSizeMismatch (cmtf_AOADMM.m:85-88)
     with pytest.raises(ab.AoadmmError):
         ab.cmtf_fun_AOADMM(Zm, pg.znorm_const(Z), G, None, None, None, None, pg.default_options())
+    Zt = dict(Z, constraints=[('tPARAFAC2', 0.1)] + list(Z['constraints'][1:]))              # cmtf_AOADMM.m:33-39
+    with pytest.raises(ValueError):
+        ab.cmtf_AOADMM(Zt, G, pg.default_options())
     Zp, Gp, _ = pg.config_single_par2(I=6, Jk=(5, 4), R=2, seed=0)
     for bad, msg in (([np.ones((6, 5))], 'cell array of length'),                              # :101-104
                      ([np.full((6, 5), 0.5), np.ones((6, 4))], 'logical or binary'),            # :107-114
