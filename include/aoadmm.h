@@ -13,8 +13,10 @@
  *  - mode ids, coupling ids are 1-based exactly as in Z.modes / Z.coupling.lin_coupled_modes;
  *  - the caller owns every host buffer; the library owns all device memory;
  *  - every entry point returns an aoadmm_status (0 = ok); no C++ exception crosses the ABI;
- *  - a handle is not thread-safe; one host thread drives one handle (one GPU per process;
- *    multi-GPU = one process per GPU, see aoadmm_dist).
+ *  - a handle is not thread-safe; one host thread drives one handle.  Multi-GPU comes in two forms:
+ *      aoadmm_create_multi : ONE caller process / thread (a MATLAB session) hands over the whole problem and the
+ *                            library drives n_gpus devices itself (the form the MEX gateway uses);
+ *      aoadmm_create + aoadmm_dist : one process per GPU (torchrun / MPI launchers), each passing its own slab.
  */
 #ifndef AOADMM_H_
 #define AOADMM_H_
@@ -26,8 +28,10 @@ extern "C" {
 #endif
 
 /* 1: first release; 2: Z.miss masks, device Znorm_const, engine options (dimtree, fuse_inner, graph,
- * mttkrp_precision), out.f_rel_missing; 3: aoadmm_nvecs, aoadmm_object_mttkrp (no struct changed since 2). */
-#define AOADMM_ABI_VERSION 3
+ * mttkrp_precision), out.f_rel_missing; 3: aoadmm_nvecs, aoadmm_object_mttkrp (no struct changed since 2);
+ * 4: aoadmm_create_multi / aoadmm_gpu_count / aoadmm_comm_release, communicators cached per process,
+ *    aoadmm_out.non_finite_mode appended (a non-finite inner residual no longer aborts the run). */
+#define AOADMM_ABI_VERSION 4
 
 typedef struct aoadmm_handle aoadmm_handle;
 
@@ -38,7 +42,7 @@ typedef enum {
   AOADMM_ERR_INVALID_ARG = 1,
   AOADMM_ERR_UNSUPPORTED = 2,          /* 'custom' constraint, non-Frobenius loss, ... */
   AOADMM_ERR_NOT_POSITIVE_DEFINITE = 3, /* chol() would have thrown (cmtf_fun_AOADMM.m:142 ...) */
-  AOADMM_ERR_NON_FINITE = 4,
+  AOADMM_ERR_NON_FINITE = 4,            /* kept for ABI stability; no entry point returns it since version 4 */
   AOADMM_ERR_CUDA = 5,
   AOADMM_ERR_NCCL = 6,
   AOADMM_ERR_OOM = 7,
@@ -171,6 +175,9 @@ typedef struct {
   int32_t error_mode;         /* mode id that raised NOT_POSITIVE_DEFINITE / NON_FINITE (0 if none) */
   double f_rel_missing;       /* out.f_rel_missing (NaN without Z.miss), cmtf_fun_AOADMM.m:436-440 */
   double *func_rel_missing;   /* out.func_rel_missing, MaxOuterIters+1 entries, or NULL */
+  int32_t non_finite_mode;    /* 0, or the id of the first mode whose inner ADMM loop saw a NaN/Inf residual ratio
+                                 (||fac|| = 0 or ||mu_DeltaB|| = 0, cmtf_fun_AOADMM.m:584, :1086-1112).  Like the
+                                 reference the run goes on (NaN > tol is false, Inf > tol is true); this is a warning. */
 } aoadmm_out;
 
 /* State fields of G (init_coupled_AOADMM_CMTF.m:41-45, :62-80, :133-169) */
@@ -190,8 +197,23 @@ int aoadmm_abi_version(void);
 int aoadmm_device_count(int *count);
 /* rank 0 fills the 128-byte id; replaces nothing in the reference (no distributed layer exists) */
 int aoadmm_nccl_unique_id(uint8_t id[128]);
-/* copies / partitions the data to HBM once.  dist may be NULL (single GPU, device 0). */
+/* copies / partitions the data to HBM once.  dist may be NULL (single GPU, device 0).  With dist->world_size > 1 the
+ * NCCL communicator of (nccl_unique_id, rank, world_size) is created on first use and cached for the life of the
+ * process: passing the same id again (every rank alike) reuses it, so repeated solves pay the bootstrap once. */
 int aoadmm_create(const aoadmm_problem *problem, const aoadmm_dist *dist, aoadmm_handle **out);
+/* Multi-GPU from ONE caller (functions/cmtf_AOADMM.m:193 is one MATLAB process): `problem` describes the WHOLE
+ * objects (shard_offset = 0, shard_extent = size of the last mode, `data` / `miss` = the full arrays).  The library
+ * cuts every tensor of order >= 3 into n_gpus contiguous slabs of its last mode (slab r = indices
+ * [extent*r/n, extent*(r+1)/n)), uploads slab r to devices[r] (NULL = devices 0..n_gpus-1) from its own worker
+ * thread, creates the communicators with ncclCommInitAll (cached per device list) and returns ONE handle.  Every
+ * entry point below then acts on all devices: set_state replicates, run drives one worker thread per GPU,
+ * get_state / out come from device 0 (all replicas are bit-identical), aoadmm_get_object_data gathers the slabs.
+ * n_gpus = 1 is the same as aoadmm_create(problem, {0,1,devices[0]}). */
+int aoadmm_create_multi(const aoadmm_problem *problem, int32_t n_gpus, const int32_t *devices, aoadmm_handle **out);
+/* number of GPUs driven by this handle (1 for aoadmm_create) */
+int aoadmm_gpu_count(const aoadmm_handle *h, int32_t *n_gpus);
+/* destroys every cached NCCL communicator of this process (no handle may be alive) */
+int aoadmm_comm_release(void);
 int aoadmm_destroy(aoadmm_handle *h);
 const char *aoadmm_last_error(const aoadmm_handle *h); /* h may be NULL: last creation error */
 
@@ -248,7 +270,7 @@ int aoadmm_object_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t 
 /* one timed MTTKRP of object `object` in mode position `pos` (1-based position inside the object)
  * using the factors currently resident in the handle; returns device milliseconds (CUDA events). */
 int aoadmm_time_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t reps, float *ms_out);
-/* number of kernels launched by this handle so far (bench.py "gpu_launches"). */
+/* number of kernels launched by this handle so far, summed over its GPUs (bench.py "gpu_launches"). */
 int aoadmm_launch_count(const aoadmm_handle *h, int64_t *count);
 /* per-phase device time accumulated by aoadmm_run since creation, milliseconds:
  * [0] MTTKRP (tensor), [1] matrix-block products, [2] everything else */

@@ -82,7 +82,14 @@ def constraint_spec(c):
 class Solver:
     """Handle lifecycle around the C ABI: create (tensors to HBM once) -> set_state -> run -> get_state."""
 
-    def __init__(self, Z, Znorm_const, rank=0, world_size=1, device=0, unique_id=None, shard=None):
+    def __init__(self, Z, Znorm_const, rank=0, world_size=1, device=0, unique_id=None, shard=None, n_gpus=1,
+                 devices=None):
+        """One GPU: defaults.  Several GPUs from THIS process (one caller, like a MATLAB session): n_gpus=N [, devices=[..]]
+        with the whole objects in Z (aoadmm_create_multi cuts the slabs).  One process per GPU (torchrun): rank,
+        world_size, device, unique_id [, shard] with this rank's slab or the whole object in Z."""
+        if n_gpus > 1 and world_size > 1:
+            raise ValueError('n_gpus > 1 (one process drives all GPUs) and world_size > 1 (one process per GPU) exclude each other')
+        self.n_gpus = int(n_gpus)
         self._keep = []
         self._h = _capi.HandleP()
         self.Z = Z
@@ -243,7 +250,20 @@ class Solver:
         self.rank, self.world_size = rank, world_size
         self.rows = rows
         self.nsl = nsl
-        _capi.check(lib.aoadmm_create(C.byref(pb), C.byref(dist), C.byref(self._h)))
+        if self.n_gpus > 1:
+            devs = None
+            if devices is not None:
+                devs = np.asarray(list(devices), dtype=np.int32)
+                if devs.size != self.n_gpus:
+                    raise ValueError('devices must list n_gpus ordinals')
+                self._keep.append(devs)
+            _capi.check(lib.aoadmm_create_multi(C.byref(pb), self.n_gpus,
+                                                devs.ctypes.data_as(_capi.c_int32_p) if devs is not None else None,
+                                                C.byref(self._h)))
+        else:
+            if devices is not None:
+                dist.device = int(list(devices)[0])
+            _capi.check(lib.aoadmm_create(C.byref(pb), C.byref(dist), C.byref(self._h)))
         self._keep_problem = pb
 
     # ------------------------------------------------------------------------------------------
@@ -416,7 +436,7 @@ class Solver:
                 'OuterIterations': it, 'func_val_conv': hist[0][:it + 1].copy(),
                 'func_coupl_conv': hist[1][:it + 1].copy(), 'func_constr_conv': hist[2][:it + 1].copy(),
                 'func_PAR2_coupl': hist[3][:it + 1].copy(), 'time_at_it': hist[4][:it + 1].copy(),
-                'innerIters': inner[:, :it].astype(np.float64)}
+                'innerIters': inner[:, :it].astype(np.float64), 'non_finite_mode': int(out.non_finite_mode)}
 
     # ---- benchmark helpers --------------------------------------------------------------------
     def generate_cp_data(self, obj, factors, noise, seed):
@@ -425,7 +445,8 @@ class Solver:
         _capi.check(lib.aoadmm_generate_cp_data(self._h, obj, arr, float(noise), int(seed)), self._h)
 
     def get_object_data(self, obj, out):
-        """This rank's slab of CP object `obj` (1-based) into the F-contiguous float64 array `out`."""
+        """This rank's slab of CP object `obj` (1-based) - the whole object for an n_gpus handle - into the F-contiguous
+        float64 array `out`."""
         assert out.dtype == np.float64 and out.flags['F_CONTIGUOUS']
         _capi.check(lib.aoadmm_get_object_data(self._h, obj, _dp(out), out.size), self._h)
         return out

@@ -80,7 +80,8 @@ class Out(C.Structure):
                 ('f_PAR2_couplings', C.c_double), ('OuterIterations', C.c_int32), ('exit_flag', C.c_int32),
                 ('func_val_conv', c_double_p), ('func_coupl_conv', c_double_p), ('func_constr_conv', c_double_p),
                 ('func_PAR2_coupl', c_double_p), ('time_at_it', c_double_p), ('inner_iters', c_int32_p),
-                ('error_mode', C.c_int32), ('f_rel_missing', C.c_double), ('func_rel_missing', c_double_p)]
+                ('error_mode', C.c_int32), ('f_rel_missing', C.c_double), ('func_rel_missing', c_double_p),
+                ('non_finite_mode', C.c_int32)]
 
 
 HandleP = C.c_void_p
@@ -89,12 +90,16 @@ HandleP = C.c_void_p
 EXPORTS = ['aoadmm_abi_version', 'aoadmm_device_count', 'aoadmm_nccl_unique_id', 'aoadmm_create', 'aoadmm_destroy',
            'aoadmm_last_error', 'aoadmm_set_state', 'aoadmm_get_state', 'aoadmm_run', 'aoadmm_mttkrp', 'aoadmm_prox',
            'aoadmm_chol_solve', 'aoadmm_gram', 'aoadmm_generate_cp_data', 'aoadmm_time_mttkrp', 'aoadmm_launch_count',
-           'aoadmm_phase_ms', 'aoadmm_last_run_ms', 'aoadmm_get_object_data', 'aoadmm_last_loop_ms', 'aoadmm_object_mttkrp', 'aoadmm_nvecs']
+           'aoadmm_phase_ms', 'aoadmm_last_run_ms', 'aoadmm_get_object_data', 'aoadmm_last_loop_ms', 'aoadmm_object_mttkrp', 'aoadmm_nvecs',
+           'aoadmm_create_multi', 'aoadmm_gpu_count', 'aoadmm_comm_release']
 
 lib.aoadmm_abi_version.restype = C.c_int
 lib.aoadmm_device_count.argtypes = [C.POINTER(C.c_int)]
 lib.aoadmm_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
 lib.aoadmm_create.argtypes = [C.POINTER(Problem), C.POINTER(Dist), C.POINTER(HandleP)]
+lib.aoadmm_create_multi.argtypes = [C.POINTER(Problem), C.c_int32, c_int32_p, C.POINTER(HandleP)]
+lib.aoadmm_gpu_count.argtypes = [HandleP, c_int32_p]
+lib.aoadmm_comm_release.argtypes = []
 lib.aoadmm_destroy.argtypes = [HandleP]
 lib.aoadmm_last_error.argtypes = [HandleP]
 lib.aoadmm_last_error.restype = C.c_char_p

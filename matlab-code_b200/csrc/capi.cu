@@ -1,14 +1,21 @@
 // capi.cu - extern "C" boundary (include/aoadmm.h).  No C++ exception crosses the ABI: every entry point
 // converts failures into an aoadmm_status and records a message retrievable with aoadmm_last_error().
+#include <algorithm>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "engine.h"
 
 struct aoadmm_handle {
-  aoadmm::Engine* eng = nullptr;
+  std::vector<aoadmm::Engine*> eng;   // one per GPU driven by this handle (rank order)
   std::string err;
+  ~aoadmm_handle() {
+    for (auto* e : eng) delete e;
+  }
 };
 
 namespace aoadmm {
@@ -35,6 +42,31 @@ int guard(aoadmm_handle* h, F&& fn) {
     if (h) h->err = e.what(); else { std::lock_guard<std::mutex> l(g_mu); g_create_error = e.what(); }
     return AOADMM_ERR_INVALID_ARG;
   }
+}
+
+// fn(rank) for rank = 0..n-1: inline for one GPU, else one worker thread per GPU (the engine methods are host-blocking:
+// they synchronise their stream once per outer iteration).  Every worker runs to completion; the first failure (in
+// rank order) is rethrown on the caller's thread.  Replicated state makes data-dependent failures identical on all ranks.
+template <typename F>
+void for_each_rank(int n, F&& fn) {
+  if (n == 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::exception_ptr> errs(n);
+  std::vector<std::thread> th;
+  th.reserve(n);
+  for (int r = 0; r < n; ++r)
+    th.emplace_back([&, r] {
+      try {
+        fn(r);
+      } catch (...) {
+        errs[r] = std::current_exception();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n; ++r)
+    if (errs[r]) std::rethrow_exception(errs[r]);
 }
 
 struct DevBuf {
@@ -73,28 +105,102 @@ int aoadmm_nccl_unique_id(uint8_t id[128]) {
   return guard(nullptr, [&] { aoadmm::nccl_unique_id(id); });
 }
 
+int aoadmm_comm_release(void) {
+  return guard(nullptr, [&] { aoadmm::comm_release_all(); });
+}
+
 int aoadmm_create(const aoadmm_problem* problem, const aoadmm_dist* dist, aoadmm_handle** out) {
   if (!out) return AOADMM_ERR_INVALID_ARG;
   *out = nullptr;
   aoadmm_handle* h = nullptr;
   int rc = guard(nullptr, [&] {
     h = new aoadmm_handle();
-    h->eng = new aoadmm::Engine(problem, dist);
+    h->eng.push_back(nullptr);
+    h->eng[0] = new aoadmm::Engine(problem, dist);   // a throwing constructor has released everything it acquired
   });
   if (rc != AOADMM_OK) {
-    if (h) {
-      delete h->eng;
-      delete h;
-    }
+    delete h;
     return rc;
   }
   *out = h;
   return AOADMM_OK;
 }
 
+int aoadmm_create_multi(const aoadmm_problem* problem, int32_t n_gpus, const int32_t* devices, aoadmm_handle** out) {
+  if (!out) return AOADMM_ERR_INVALID_ARG;
+  *out = nullptr;
+  aoadmm_handle* h = nullptr;
+  int rc = guard(nullptr, [&] {
+    if (problem == nullptr) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "problem is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw aoadmm::CudaError(AOADMM_ERR_NO_DEVICE, "no CUDA device available");
+    if (n_gpus < 1 || n_gpus > ndev)
+      throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "n_gpus must be between 1 and the number of visible devices (" + std::to_string(ndev) + ")");
+    std::vector<int> devs(n_gpus);
+    for (int r = 0; r < n_gpus; ++r) {
+      devs[r] = devices ? devices[r] : r;
+      if (devs[r] < 0 || devs[r] >= ndev) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "device ordinal out of range");
+      for (int q = 0; q < r; ++q)
+        if (devs[q] == devs[r]) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "a device is listed twice");
+    }
+    if (problem->nb_modes <= 0 || problem->n_objects <= 0 || problem->objects == nullptr || problem->mode_rows == nullptr)
+      throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "empty problem");
+    // slabs of the last mode of every >= 3-way CP object (column-major: a slab is one contiguous range)
+    std::vector<std::vector<aoadmm_object>> objs(n_gpus, std::vector<aoadmm_object>(problem->objects, problem->objects + problem->n_objects));
+    for (int p = 0; p < problem->n_objects; ++p) {
+      const aoadmm_object& src = problem->objects[p];
+      if (src.model != AOADMM_MODEL_CP || src.order < 3 || n_gpus == 1) continue;
+      if (src.modes == nullptr) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "object without modes");
+      int64_t lead = 1;
+      for (int d = 0; d < src.order; ++d) {
+        if (src.modes[d] < 1 || src.modes[d] > problem->nb_modes) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "mode id out of range");
+        if (d + 1 < src.order) lead *= problem->mode_rows[src.modes[d] - 1];
+      }
+      const int64_t ext = problem->mode_rows[src.modes[src.order - 1] - 1];
+      if (src.shard_offset != 0 || (src.shard_extent != ext && src.shard_extent != 0))
+        throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "aoadmm_create_multi takes whole objects (shard_offset = 0, shard_extent = size of the last mode)");
+      if (ext < n_gpus)
+        throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "object " + std::to_string(p + 1) + ": the last mode has fewer indices (" +
+                                                           std::to_string(ext) + ") than there are GPUs");
+      for (int r = 0; r < n_gpus; ++r) {
+        const int64_t lo = ext * r / n_gpus, hi = ext * (r + 1) / n_gpus;
+        aoadmm_object& o = objs[r][p];
+        o.shard_offset = lo;
+        o.shard_extent = hi - lo;
+        if (src.data != nullptr) o.data = src.data + lead * lo;
+        if (src.miss != nullptr) o.miss = src.miss + lead * lo;
+      }
+    }
+    std::vector<void*> comms(n_gpus, nullptr);
+    if (n_gpus > 1) comms = aoadmm::comms_for_devices(devs);
+    h = new aoadmm_handle();
+    h->eng.assign(n_gpus, nullptr);
+    for_each_rank(n_gpus, [&](int r) {
+      aoadmm_problem pr = *problem;
+      pr.objects = objs[r].data();
+      aoadmm_dist d{};
+      d.rank = r;
+      d.world_size = n_gpus;
+      d.device = devs[r];
+      h->eng[r] = new aoadmm::Engine(&pr, &d, comms[r]);
+    });
+  });
+  if (rc != AOADMM_OK) {
+    delete h;   // engines that were built on the other devices go with it
+    return rc;
+  }
+  *out = h;
+  return AOADMM_OK;
+}
+
+int aoadmm_gpu_count(const aoadmm_handle* h, int32_t* n_gpus) {
+  if (!h || !n_gpus) return AOADMM_ERR_INVALID_ARG;
+  *n_gpus = (int32_t)h->eng.size();
+  return AOADMM_OK;
+}
+
 int aoadmm_destroy(aoadmm_handle* h) {
   if (!h) return AOADMM_OK;
-  delete h->eng;
   delete h;
   return AOADMM_OK;
 }
@@ -110,66 +216,118 @@ const char* aoadmm_last_error(const aoadmm_handle* h) {
 int aoadmm_set_state(aoadmm_handle* h, int32_t field, int32_t index, int32_t slice, const double* data, int64_t rows,
                      int64_t cols) {
   if (!h) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->set_state(field, index, slice, data, rows, cols); });
+  return guard(h, [&] {
+    for_each_rank((int)h->eng.size(), [&](int r) { h->eng[r]->set_state(field, index, slice, data, rows, cols); });
+  });
 }
 
 int aoadmm_get_state(aoadmm_handle* h, int32_t field, int32_t index, int32_t slice, double* data, int64_t rows,
                      int64_t cols) {
   if (!h) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->get_state(field, index, slice, data, rows, cols); });
+  return guard(h, [&] { h->eng[0]->get_state(field, index, slice, data, rows, cols); });  // replicas are identical
 }
 
 int aoadmm_run(aoadmm_handle* h, const aoadmm_options* options, aoadmm_out* out) {
   if (!h) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->run(options, out); });
+  return guard(h, [&] {
+    if (out == nullptr) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "run: NULL options/out");
+    const int n = (int)h->eng.size();
+    std::vector<aoadmm_out> others(n);   // ranks > 0: scalars only, no history arrays
+    for (auto& o : others) std::memset(&o, 0, sizeof(o));
+    for_each_rank(n, [&](int r) { h->eng[r]->run(options, r == 0 ? out : &others[r]); });
+  });
 }
 
 int aoadmm_generate_cp_data(aoadmm_handle* h, int32_t object, const double* const* factors, double noise, uint64_t seed) {
   if (!h || !factors) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->generate_cp_data(object, factors, noise, seed); });
+  return guard(h, [&] {
+    for_each_rank((int)h->eng.size(), [&](int r) { h->eng[r]->generate_cp_data(object, factors, noise, seed); });
+  });
 }
 
 int aoadmm_get_object_data(aoadmm_handle* h, int32_t object, double* out, int64_t n_elements) {
   if (!h || !out) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->object_to_host(object, out, n_elements); });
+  return guard(h, [&] {
+    const int n = (int)h->eng.size();
+    if (n == 1) {
+      h->eng[0]->object_to_host(object, out, n_elements);
+      return;
+    }
+    int64_t total = 0;
+    std::vector<int64_t> off(n), cnt(n);
+    for (int r = 0; r < n; ++r) {
+      h->eng[r]->object_slab(object, &off[r], &cnt[r]);
+      total += cnt[r];
+    }
+    if (total != n_elements) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "get_object_data: size mismatch");
+    for_each_rank(n, [&](int r) { h->eng[r]->object_to_host(object, out + off[r], cnt[r]); });
+  });
 }
 
 int aoadmm_nvecs(aoadmm_handle* h, int32_t mode, int32_t slice, int32_t r, double* out, int64_t rows, double* info) {
   if (!h || !out || r < 1 || rows < 1) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->nvecs_to_host(mode, slice, r, out, rows, info); });
+  return guard(h, [&] {
+    const int n = (int)h->eng.size();
+    std::vector<std::vector<double>> tmp(n);
+    for (int q = 1; q < n; ++q) tmp[q].resize((size_t)rows * r);
+    for_each_rank(n, [&](int q) { h->eng[q]->nvecs_to_host(mode, slice, r, q == 0 ? out : tmp[q].data(), rows, q == 0 ? info : nullptr); });
+  });
 }
 
 int aoadmm_object_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t precision, double* out) {
   if (!h || !out || precision < 0 || precision > 1) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng->mttkrp_to_host(object, pos, out, precision); });
+  return guard(h, [&] {
+    const int n = (int)h->eng.size();
+    std::vector<std::vector<double>> tmp(n);
+    if (n > 1) {
+      const int m = h->eng[0]->object_mode(object, pos);
+      if (m < 0) throw aoadmm::CudaError(AOADMM_ERR_INVALID_ARG, "mttkrp: object / position out of range");
+      for (int q = 1; q < n; ++q) tmp[q].resize((size_t)h->eng[0]->mode_rows(m) * h->eng[0]->mode_rank(m));
+    }
+    for_each_rank(n, [&](int q) { h->eng[q]->mttkrp_to_host(object, pos, q == 0 ? out : tmp[q].data(), precision); });
+  });
 }
 
 int aoadmm_time_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t reps, float* ms_out) {
   if (!h || !ms_out) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { *ms_out = h->eng->time_mttkrp(object, pos, reps); });
+  return guard(h, [&] {
+    const int n = (int)h->eng.size();
+    std::vector<float> ms(n, 0.f);
+    for_each_rank(n, [&](int q) { ms[q] = h->eng[q]->time_mttkrp(object, pos, reps); });
+    *ms_out = *std::max_element(ms.begin(), ms.end());
+  });
 }
 
 int aoadmm_launch_count(const aoadmm_handle* h, int64_t* count) {
   if (!h || !count) return AOADMM_ERR_INVALID_ARG;
-  *count = h->eng->launches();
+  int64_t total = 0;
+  for (auto* e : h->eng) total += e->launches();
+  *count = total;
   return AOADMM_OK;
 }
 
 int aoadmm_phase_ms(const aoadmm_handle* h, double ms[3]) {
   if (!h || !ms) return AOADMM_ERR_INVALID_ARG;
-  h->eng->phase_ms(ms);
+  ms[0] = ms[1] = ms[2] = 0.0;
+  for (auto* e : h->eng) {   // slowest GPU per phase
+    double v[3];
+    e->phase_ms(v);
+    for (int q = 0; q < 3; ++q) ms[q] = std::max(ms[q], v[q]);
+  }
   return AOADMM_OK;
 }
 
 int aoadmm_last_run_ms(const aoadmm_handle* h, double* ms) {
   if (!h || !ms) return AOADMM_ERR_INVALID_ARG;
-  *ms = h->eng->last_run_ms();
+  *ms = 0.0;
+  for (auto* e : h->eng) *ms = std::max(*ms, e->last_run_ms());
   return AOADMM_OK;
 }
 
 int aoadmm_last_loop_ms(const aoadmm_handle* h, double* ms) {
   if (!h || !ms) return AOADMM_ERR_INVALID_ARG;
-  *ms = h->eng->last_loop_ms();
+  *ms = 0.0;
+  for (auto* e : h->eng) *ms = std::max(*ms, e->last_loop_ms());
   return AOADMM_OK;
 }
 

@@ -4,8 +4,11 @@
 #include <cuda.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
 #include <stdexcept>
+#include <utility>
 
 namespace aoadmm {
 
@@ -25,6 +28,23 @@ struct CudaError : public std::runtime_error {
   } while (0)
 
 #define AO_CHECK_LAUNCH() AO_CUDA(cudaGetLastError())
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) acts on the CURRENT device only, and one process may drive several
+// GPUs from several host threads (aoadmm_create_multi): remember the largest size configured per (device, kernel).
+// No attribute call happens once a size is configured, so the steady state stays legal inside CUDA-graph capture.
+inline void ensure_dynamic_smem(const void* kern, size_t bytes, size_t threshold = 48 * 1024) {
+  if (bytes <= threshold) return;
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> configured;
+  int dev = 0;
+  AO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = configured[std::make_pair(dev, kern)];
+  if (bytes > cur) {
+    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+}
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

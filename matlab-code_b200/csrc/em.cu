@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) em_kernel(EmArgs a, int kper) {
         const bool in = (i < a.I) && (j < a.J);
         const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
         xv[p][q] = in ? a.X[idx] : 0.0;
-        mk[p][q] = in ? a.mask[idx] : (uint8_t)2;   // 2 = outside the object
+        mk[p][q] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed (as in norm2_masked_kernel); 2 = outside the object
       }
     }
 #pragma unroll

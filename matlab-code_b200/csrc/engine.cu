@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <set>
 #include <thread>
 
@@ -31,6 +33,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   // point-to-point exchange of tensor slabs (nvecs of the sharded mode)
@@ -42,6 +45,8 @@ struct NcclApi {
 
 NcclApi* load_nccl() {
   static NcclApi api;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   if (api.lib != nullptr) return &api;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
@@ -52,6 +57,7 @@ NcclApi* load_nccl() {
   api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+  api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(api.lib, "ncclCommInitAll"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
   api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(api.lib, "ncclSend"));
@@ -69,6 +75,124 @@ void nccl_unique_id(uint8_t id[128]) {
   ncclResult_t r = api->GetUniqueId(&uid);
   if (r != ncclSuccess) throw CudaError(6, "ncclGetUniqueId failed");
   std::memcpy(id, uid.internal, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Process-wide communicator cache.  Creating a communicator costs seconds at 8 ranks (bootstrap + the connection set-up
+// of the first collective), far more than a solve of a resident problem, so communicators outlive the handles:
+//   * one process per GPU (aoadmm_dist): the 128-byte unique id is the key - a handle created with an id that was
+//     used before in this process gets the same communicator (every rank must then reuse it, which holds when all
+//     ranks pass the same id again);
+//   * one process driving several GPUs (aoadmm_create_multi): the device list is the key (ncclCommInitAll).
+// A fresh communicator runs one small all-reduce so that the first timed collective does not pay the lazy set-up.
+// Released by aoadmm_comm_release() or at process exit.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct CommCache {
+  std::mutex mu;
+  std::map<std::string, ncclComm_t> by_uid;                       // key: 128-byte id + rank + world
+  std::map<std::vector<int>, std::vector<ncclComm_t>> by_devices;
+};
+CommCache& comm_cache() {
+  static CommCache c;
+  return c;
+}
+void warm_up_comm(NcclApi* api, ncclComm_t comm, cudaStream_t st) {
+  double* buf = nullptr;
+  AO_CUDA(cudaMalloc(&buf, 256 * sizeof(double)));
+  AO_CUDA(cudaMemsetAsync(buf, 0, 256 * sizeof(double), st));
+  const ncclResult_t r = api->AllReduce(buf, buf, 256, ncclDouble, ncclSum, comm, st);
+  const cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (r != ncclSuccess) throw CudaError(6, std::string("NCCL warm-up all-reduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  AO_CUDA(e);
+}
+}  // namespace
+
+// communicator of (unique id, rank, world) - created on first use, cached afterwards
+void* comm_for_unique_id(const uint8_t id[128], int rank, int world, cudaStream_t st) {
+  NcclApi* api = load_nccl();
+  std::string key(reinterpret_cast<const char*>(id), 128);
+  key += "/" + std::to_string(rank) + "/" + std::to_string(world);
+  CommCache& c = comm_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.by_uid.find(key);
+    if (it != c.by_uid.end()) return it->second;
+  }
+  ncclUniqueId uid;
+  std::memcpy(uid.internal, id, 128);
+  ncclComm_t comm = nullptr;
+  const ncclResult_t r = api->CommInitRank(&comm, world, uid, rank);
+  if (r != ncclSuccess) throw CudaError(6, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  warm_up_comm(api, comm, st);
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.by_uid[key] = comm;
+  return comm;
+}
+
+// communicators of a single-process device group (one per device, in the order of `devices`)
+std::vector<void*> comms_for_devices(const std::vector<int>& devices) {
+  NcclApi* api = load_nccl();
+  if (!api->CommInitAll) throw CudaError(6, "libnccl.so.2 lacks ncclCommInitAll");
+  CommCache& c = comm_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.by_devices.find(devices);
+  if (it == c.by_devices.end()) {
+    std::vector<ncclComm_t> comms(devices.size(), nullptr);
+    const ncclResult_t r = api->CommInitAll(comms.data(), (int)devices.size(), devices.data());
+    if (r != ncclSuccess) throw CudaError(6, std::string("ncclCommInitAll: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+    // warm-up: every rank must enter the collective, so issue them as one group from this thread
+    std::vector<double*> bufs(devices.size(), nullptr);
+    std::vector<cudaStream_t> sts(devices.size(), nullptr);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    bool ok = true;
+    for (size_t i = 0; i < devices.size() && ok; ++i) {
+      ok = cudaSetDevice(devices[i]) == cudaSuccess && cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaMalloc(&bufs[i], 256 * sizeof(double)) == cudaSuccess &&
+           cudaMemsetAsync(bufs[i], 0, 256 * sizeof(double), sts[i]) == cudaSuccess;
+    }
+    if (ok && api->GroupStart && api->GroupEnd) {
+      api->GroupStart();
+      for (size_t i = 0; i < devices.size(); ++i)
+        ok = ok && api->AllReduce(bufs[i], bufs[i], 256, ncclDouble, ncclSum, comms[i], sts[i]) == ncclSuccess;
+      ok = (api->GroupEnd() == ncclSuccess) && ok;
+    }
+    for (size_t i = 0; i < devices.size(); ++i) {
+      cudaSetDevice(devices[i]);
+      if (sts[i]) {
+        ok = (cudaStreamSynchronize(sts[i]) == cudaSuccess) && ok;
+        cudaStreamDestroy(sts[i]);
+      }
+      if (bufs[i]) cudaFree(bufs[i]);
+    }
+    cudaSetDevice(prev);
+    if (!ok) {
+      for (auto cm : comms)
+        if (cm) api->CommDestroy(cm);
+      cudaGetLastError();
+      throw CudaError(6, "NCCL warm-up all-reduce over the device group failed");
+    }
+    it = c.by_devices.emplace(devices, comms).first;
+  }
+  return std::vector<void*>(it->second.begin(), it->second.end());
+}
+
+void comm_release_all() {
+  CommCache& c = comm_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  NcclApi* api = nullptr;
+  try {
+    api = load_nccl();
+  } catch (...) {
+    return;
+  }
+  for (auto& kv : c.by_uid) api->CommDestroy(kv.second);
+  for (auto& kv : c.by_devices)
+    for (auto cm : kv.second) api->CommDestroy(cm);
+  c.by_uid.clear();
+  c.by_devices.clear();
 }
 
 #define AO_NCCL(expr)                                                                                 \
@@ -334,7 +458,18 @@ struct Engine::ObjTerms {
 // ---------------------------------------------------------------------------------------------------
 // construction
 // ---------------------------------------------------------------------------------------------------
-Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
+Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist, void* shared_comm) {
+  // A constructor that throws never runs the destructor: everything acquired so far (up to the whole tensor in HBM,
+  // streams, events, pinned buffers) is released here before the error leaves.
+  try {
+    construct(prob, dist, shared_comm);
+  } catch (...) {
+    release();
+    throw;
+  }
+}
+
+void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void* shared_comm) {
   if (prob == nullptr) throw CudaError(1, "problem is NULL");
   if (dist != nullptr) {
     rank_ = dist->rank;
@@ -350,6 +485,12 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   AO_CUDA(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
   AO_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   AO_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  if (world_ > 1) {
+    // the communicator first: a problem that is rejected below is rejected on every rank alike (the problem struct is
+    // the same everywhere), so no rank is left waiting inside ncclCommInitRank for a peer that already gave up
+    nccl_ = load_nccl();
+    comm_ = shared_comm != nullptr ? shared_comm : comm_for_unique_id(dist->nccl_unique_id, rank_, world_, st_);
+  }
 
   nb_modes_ = prob->nb_modes;
   n_objects_ = prob->n_objects;
@@ -632,12 +773,6 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   }
 
   if (world_ > 1) {
-    nccl_ = load_nccl();
-    ncclUniqueId uid;
-    std::memcpy(uid.internal, dist->nccl_unique_id, 128);
-    ncclComm_t comm;
-    AO_NCCL(nccl_->CommInitRank(&comm, world_, uid, rank_));
-    comm_ = comm;
     for (auto& o : objects_)
       if (o.znorm_pending_allreduce) {  // partial norms of the slabs -> norm of the whole tensor
         AO_CUDA(cudaMemcpyAsync(cp0_tmp_, &o.znorm, sizeof(double), cudaMemcpyHostToDevice, st_));
@@ -649,28 +784,46 @@ Engine::Engine(const aoadmm_problem* prob, const aoadmm_dist* dist) {
   AO_CUDA(cudaDeviceSynchronize());
 }
 
-Engine::~Engine() {
+Engine::~Engine() { release(); }
+
+// frees every device / pinned resource; safe on a partially constructed engine and idempotent
+void Engine::release() {
   cudaSetDevice(device_);
   if (st_) cudaStreamSynchronize(st_);
-  if (comm_ && nccl_) nccl_->CommDestroy(static_cast<ncclComm_t>(comm_));
+  if (st2_) cudaStreamSynchronize(st2_);
+  cudaGetLastError();
+  comm_ = nullptr;   // communicators belong to the process-wide cache (comm_for_unique_id / comms_for_devices)
+  auto dfree = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  auto hfree = [](auto*& p) {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+  };
   for (auto& m : modes_) {
     for (DevMat* d : {&m.fac, &m.Z, &m.muZ, &m.muD, &m.A, &m.Alast, &m.C, &m.B, &m.L, &m.Binv, &m.Btmp, &m.GtG, &m.Znew, &m.V}) dev_free(*d);
-    if (m.invdiag) cudaFree(m.invdiag);
-    if (m.rho) cudaFree(m.rho);
+    dfree(m.invdiag);
+    dfree(m.rho);
     quad_prox_free(m.quad);
   }
+  modes_.clear();
   for (auto& o : objects_) {
-    if (o.data) cudaFree(o.data);
-    if (o.Tbuf) cudaFree(o.Tbuf);
-    if (o.mask) cudaFree(o.mask);
-    if (o.em_kr) cudaFree(o.em_kr);
+    dfree(o.data);
+    dfree(o.Tbuf);
+    dfree(o.mask);
+    dfree(o.em_kr);
     for (auto& v : o.views) {
       if (v.f0_own) packed_factor_free(v.f0);
       if (v.f1_own) packed_factor_free(v.f1);
     }
   }
+  objects_.clear();
   for (auto& d : delta_) dev_free(d);
+  delta_.clear();
   free_linear_coupling();
+  lin_modes_.clear();
+  lin_groups_.clear();
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
     for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.mask, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
@@ -682,26 +835,41 @@ Engine::~Engine() {
     packed_factor_free(s.fA);
     packed_factor_free(s.ones);
   }
-  for (void* p : {(void*)mws_.ws, (void*)gram_ws_, (void*)admm_partials_, (void*)admm_sums_, (void*)admm_counter_,
-                  prox_scratch_, (void*)krtmp_[0], (void*)krtmp_[1], (void*)ctl_dev_, (void*)jobs_dev_,
-                  (void*)red_dev_, (void*)red_partials_, (void*)cp0_tmp_})
-    if (p) cudaFree(p);
-  if (em_sums_) cudaFree(em_sums_);
-  if (em_partials_) cudaFree(em_partials_);
-  if (em_sums_host_) cudaFreeHost(em_sums_host_);
-  if (ctl_host_) cudaFreeHost(ctl_host_);
-  if (red_host_) cudaFreeHost(red_host_);
-  if (run_ev_[0]) cudaEventDestroy(run_ev_[0]);
-  if (run_ev_[1]) cudaEventDestroy(run_ev_[1]);
-  if (run_ev_[2]) cudaEventDestroy(run_ev_[2]);
+  par2_.clear();
+  dfree(mws_.ws);
+  dfree(gram_ws_);
+  dfree(admm_partials_);
+  dfree(admm_sums_);
+  dfree(admm_counter_);
+  dfree(prox_scratch_);
+  dfree(krtmp_[0]);
+  dfree(krtmp_[1]);
+  dfree(ctl_dev_);
+  dfree(jobs_dev_);
+  dfree(red_dev_);
+  dfree(red_partials_);
+  dfree(cp0_tmp_);
+  dfree(em_sums_);
+  dfree(em_partials_);
+  hfree(em_sums_host_);
+  hfree(ctl_host_);
+  hfree(red_host_);
+  for (auto& e : run_ev_) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  }
   for (auto& e : ev_pool_) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
+  ev_pool_.clear();
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
+  ev_fork_ = ev_join_ = nullptr;
   if (st2_) cudaStreamDestroy(st2_);
   if (st_) cudaStreamDestroy(st_);
+  st_ = st2_ = nullptr;
+  cudaGetLastError();
 }
 
 void Engine::build_views(ObjectState& o) {
@@ -1664,9 +1832,8 @@ void Engine::check_errors(aoadmm_out* out) {
     if (ctl_host_[i].err != 0) {
       if (out) out->error_mode = i + 1;
       const int code = ctl_host_[i].err;
-      throw CudaError(code, code == 3 ? "system matrix of mode " + std::to_string(i + 1) +
-                                            " is not positive definite (chol would fail, cmtf_fun_AOADMM.m:142)"
-                                      : "non-finite residual in the ADMM loop of mode " + std::to_string(i + 1));
+      throw CudaError(code, "system matrix of mode " + std::to_string(i + 1) +
+                                " is not positive definite (chol would fail, cmtf_fun_AOADMM.m:142)");
     }
   }
 }
@@ -1782,6 +1949,7 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
   opt_ = *opt;
   if (opt_.MaxInnerIters < 1) throw CudaError(1, "MaxInnerIters must be >= 1");
   out->error_mode = 0;
+  out->non_finite_mode = 0;
   if (run_ev_[0] == nullptr) {
     AO_CUDA(cudaEventCreate(&run_ev_[0]));
     AO_CUDA(cudaEventCreate(&run_ev_[1]));
@@ -1926,6 +2094,8 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
   out->f_PAR2_couplings = f[3];
   out->f_rel_missing = has_missing_ ? f_rel_missing_ : std::nan("");
   out->OuterIterations = iter - 1;
+  for (int i = n_ctl_ - 1; i >= 0; --i)
+    if (ctl_host_[i].warn != 0) out->non_finite_mode = i + 1;
   if (iter > opt_.MaxOuterIters) {                                   // make_exit_flag.m:4-5
     out->exit_flag = 0;
   } else {
@@ -1988,6 +2158,17 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   o.T_version = 0;  // cached partial contractions refer to the old data
   for (auto p : tmp) cudaFree(p);
   cudaFree(sums);
+}
+
+// position of this rank's slab of CP object `object` inside the whole object (elements, column-major)
+void Engine::object_slab(int object, int64_t* offset_elems, int64_t* n_elems) const {
+  if (object < 1 || object > n_objects_) throw CudaError(1, "object out of range");
+  const ObjectState& o = objects_[object - 1];
+  if (o.model != AOADMM_MODEL_CP) throw CudaError(1, "not a CP object");
+  int64_t lead = 1;
+  for (int d = 0; d + 1 < o.order; ++d) lead *= o.dims[d];
+  *offset_elems = lead * o.shard_offset;
+  *n_elems = lead * o.dims[o.order - 1];
 }
 
 void Engine::object_to_host(int object, double* out, int64_t n_elements) {

@@ -26,6 +26,10 @@ void dev_alloc(DevMat& m, int64_t rows, int64_t cols);  // zero-initialised devi
 void dev_free(DevMat& m);
 
 struct NcclApi;  // dlopen'ed NCCL entry points (multi-GPU only)
+// process-wide communicator cache (engine.cu)
+void* comm_for_unique_id(const uint8_t id[128], int rank, int world, cudaStream_t st);
+std::vector<void*> comms_for_devices(const std::vector<int>& devices);
+void comm_release_all();
 
 struct ModeState {
   int id = 0;                 // 1-based global mode id
@@ -152,14 +156,27 @@ struct ObjectState {
 
 class Engine {
  public:
-  Engine(const aoadmm_problem* prob, const aoadmm_dist* dist);
+  // shared_comm: communicator of this rank created by the caller (single-process device group), else nullptr and the
+  // communicator of dist->nccl_unique_id is taken from the process-wide cache
+  Engine(const aoadmm_problem* prob, const aoadmm_dist* dist, void* shared_comm = nullptr);
   ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
   void set_state(int field, int index, int slice, const double* data, int64_t rows, int64_t cols);
   void get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols);
   void run(const aoadmm_options* opt, aoadmm_out* out);
   void generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed);
   float time_mttkrp(int object, int pos, int reps);
   void object_to_host(int object, double* out, int64_t n_elements);
+  void object_slab(int object, int64_t* offset_elems, int64_t* n_elems) const;
+  int device() const { return device_; }
+  int64_t mode_rows(int mode_id) const { return (mode_id >= 1 && mode_id <= nb_modes_) ? modes_[mode_id - 1].rows : -1; }
+  int mode_rank(int mode_id) const { return (mode_id >= 1 && mode_id <= nb_modes_) ? modes_[mode_id - 1].R : -1; }
+  int object_mode(int object, int pos) const {   // global mode id at 1-based position `pos` of 1-based object, or -1
+    if (object < 1 || object > n_objects_) return -1;
+    const ObjectState& o = objects_[object - 1];
+    return (pos >= 1 && pos <= o.order) ? o.modes[pos - 1] : -1;
+  }
   // cmtf_nvecs.m / init_coupled_AOADMM_CMTF.m:50-69: r leading eigenvectors of X_(n) X_(n)' for global mode id `mode`
   // (slice: 1-based slice of a PARAFAC2 B_k mode, else 0); out: rows x r host buffer; info: [iterations, residual]
   void nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t rows, double* info);
@@ -173,6 +190,8 @@ class Engine {
 
  private:
   // setup
+  void construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void* shared_comm);
+  void release();
   void build_views(ObjectState& o);
   void build_objective_jobs();
   // sweep pieces

@@ -254,7 +254,9 @@ __global__ void lin_finalize_kernel(LinFin fin, const double* __restrict__ red, 
   ctl->iters += 1;
   const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
   if (!cont) ctl->done = 1;
-  if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+  // a NaN ratio (0/0 of a factor driven to zero) makes its comparison false and an Inf keeps the loop going, exactly
+  // as in the reference's while-test (:600, :633, :519); the run goes on and the event is only recorded
+  if (!isfinite(rpk + rdk + rpc + rdc)) ctl->warn = 4;
 }
 
 unsigned flat_grid(long long n) { return (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8); }

@@ -679,11 +679,7 @@ int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk
   const long long ldo = round_up(t.I, 2);
   if ((size_t)nsplit * Rp_total * ldo * 8 > w.ws_bytes) throw CudaError(1, "mttkrp workspace too small (lead)");
   auto kern = mttkrp_lead_kernel<NT, WARPS_N, PREC>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_done = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM);
   dim3 grid(mtiles, nsplit, nchunk);
   kern<<<grid, kThreads, C::SMEM, st>>>(t.map_lead, fj.data, fk.data, w.ws, (int)t.I, (int)t.J, (int)t.K,
                                         (long long)fj.rows_pad, (long long)fk.rows_pad, njt, nsplit, ldo, Rp_total, skip);
@@ -706,11 +702,7 @@ int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& f
   const int nparts = (EPI == 0) ? nsplit : jtiles;
   if ((size_t)nparts * Rp_total * ldo * 8 > w.ws_bytes) throw CudaError(1, "mttkrp workspace too small (inner)");
   auto kern = mttkrp_inner_kernel<NT, WARPS_N, EPI, EMIT, PREC>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_done = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM);
   dim3 grid(jtiles, nsplit, nchunk);
   kern<<<grid, kThreads, C::SMEM, st>>>(t.map_inner, fi.data, fe.data, w.ws, (int)t.I, (int)t.J, (int)t.K,
                                         (long long)fi.rows_pad, (long long)fe.rows_pad, nit, nsplit, ldo, Rp_total, Tbuf,

@@ -190,12 +190,8 @@ GramPlan plan_gram(const UnfoldSpec& s) {
 
 template <int L, int BMT>
 void launch_gram(const GramArgs& g, const GramPlan& p, cudaStream_t st) {
-  static bool attr_set = false;
   const size_t smem = (size_t)kStages * 2 * TileGeom<L, BMT>::doubles * sizeof(double);
-  if (!attr_set) {
-    AO_CUDA(cudaFuncSetAttribute(unfold_gram_kernel<L, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(unfold_gram_kernel<L, BMT>), smem, 0);
   dim3 grid((unsigned)p.T, (unsigned)p.T, (unsigned)p.splits);
   unfold_gram_kernel<L, BMT><<<grid, 256, smem, st>>>(g);
   AO_CHECK_LAUNCH();

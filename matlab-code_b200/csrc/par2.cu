@@ -646,7 +646,9 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L,
     ctl->iters += 1;
     const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
     if (!cont) ctl->done = 1;
-    if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+    // a NaN ratio (0/0 of a factor driven to zero) makes its comparison false and an Inf keeps the loop going, exactly
+  // as in the reference's while-test (:600, :633, :519); the run goes on and the event is only recorded
+  if (!isfinite(rpk + rdk + rpc + rdc)) ctl->warn = 4;
     *counter = 0u;
   }
 }
@@ -814,12 +816,7 @@ __global__ void __launch_bounds__(256) par2_residual_kernel(Par2Layout L, const 
 
 template <typename Kern>
 void opt_in_smem(Kern kern, size_t smem) {
-  static std::map<const void*, size_t> configured;  // once per kernel and size (no attribute calls under graph capture)
-  size_t& cur = configured[reinterpret_cast<const void*>(kern)];
-  if (smem > 48 * 1024 && smem > cur) {
-    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cur = smem;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);  // once per device, kernel and size
 }
 
 unsigned flat_grid(long long n) { return (unsigned)std::min<long long>(ceil_div(std::max<long long>(n, 1), 256), 148 * 8); }

@@ -580,14 +580,8 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     const size_t bytes = (size_t)per * sizeof(double);
     const int use_smem = bytes <= kSerialSmemLimit;
     if (!use_smem && scratch == nullptr) throw CudaError(1, "prox_apply: scratch buffer required for this size");
-    if (use_smem && bytes > 48 * 1024) {
-      static size_t configured = 0;
-      if (bytes > configured) {
-        AO_CUDA(cudaFuncSetAttribute(prox_serial_col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kSerialSmemLimit));
-        configured = kSerialSmemLimit;
-      }
-    }
+    if (use_smem && bytes > 48 * 1024)
+      ensure_dynamic_smem(reinterpret_cast<const void*>(prox_serial_col_kernel<true>), kSerialSmemLimit);
     if (use_smem)
       prox_serial_col_kernel<true><<<cols, 32, bytes, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
                                                             static_cast<double*>(scratch), per, skip, tv_dp);

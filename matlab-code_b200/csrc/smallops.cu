@@ -231,7 +231,9 @@ __device__ void finalize_ctl(const double* sums, const FinInfo& fin, const Inner
   ctl->iters += 1;
   const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
   if (!cont) ctl->done = 1;
-  if (!isfinite(rpk + rdk + rpc + rdc) && ctl->err == 0) ctl->err = 4;
+  // a NaN ratio (0/0 of a factor driven to zero) makes its comparison false and an Inf keeps the loop going, exactly
+  // as in the reference's while-test (:600, :633, :519); the run goes on and the event is only recorded
+  if (!isfinite(rpk + rdk + rpc + rdc)) ctl->warn = 4;
 }
 
 // Solves x * (L L') = a in place for one row held in shared memory (element e at row_s[e*BT]).
@@ -675,13 +677,7 @@ int gram(const double* F, int64_t rows, int64_t ld, int R, double* G, double* ws
 
 int prep_system(const PrepArgs& a, cudaStream_t st, const int* skip) {
   const size_t smem = (a.R <= 64) ? (size_t)2 * a.R * a.R * sizeof(double) : 0;
-  if (smem > 40 * 1024) {
-    static bool done = false;
-    if (!done) {
-      AO_CUDA(cudaFuncSetAttribute(prep_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
-      done = true;
-    }
-  }
+  if (smem > 40 * 1024) ensure_dynamic_smem(reinterpret_cast<const void*>(prep_system_kernel), 2 * 64 * 64 * 8, 40 * 1024);
   if (a.Binv != nullptr && a.R > 64 && a.Btmp == nullptr) throw CudaError(1, "prep_system: Btmp scratch required for R > 64");
   prep_system_kernel<<<1, 256, smem, st>>>(a, skip);
   AO_CHECK_LAUNCH();
@@ -710,13 +706,8 @@ FinInfo make_fin(const AdmmGroup& g) {
 }
 template <typename K>
 void set_smem(K kern, size_t smem) {
-  // once per kernel and size: no attribute calls on the steady-state path (they are not allowed inside graph capture)
-  static std::map<const void*, size_t> configured;
-  size_t& cur = configured[reinterpret_cast<const void*>(kern)];
-  if (smem > 40 * 1024 && smem > cur) {
-    AO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cur = smem;
-  }
+  // once per device, kernel and size: no attribute calls on the steady-state path (not allowed inside graph capture)
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, 40 * 1024);
 }
 }  // namespace
 

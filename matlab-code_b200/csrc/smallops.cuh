@@ -46,8 +46,8 @@ __device__ __forceinline__ double prox_elem(int kind, double v, double p0, doubl
 struct InnerCtl {
   int done;        // 1: the data-dependent exit test of the ADMM while-loop has fired
   int iters;       // inner iterations executed so far (the reference's inner_iter-1)
-  int err;         // 0 ok, 3 not positive definite, 4 non-finite
-  int pad;
+  int err;         // 0 ok, 3 not positive definite
+  int warn;        // 4: a residual ratio of this loop was NaN/Inf at least once during the run (not an error)
   double res[4];   // rel_primal_coupling, rel_dual_coupling, rel_primal_constr, rel_dual_constr
 };
 

@@ -8,6 +8,13 @@
 // cannot call MATLAB function handles, the named specs in Z.constraints are used instead), Znorm_const from
 // cmtf_AOADMM.m:124-156, G from init_coupled_AOADMM_CMTF.m or the caller, options from the script (:120-132).
 //
+// Engine knobs read from options (all optional): b200_gpus (number of B200s this MATLAB session drives through
+// aoadmm_create_multi, default 1), b200_dimtree, b200_mttkrp_precision, b200_fuse_inner, b200_graph.
+//
+// Error handling: mexErrMsgIdAndTxt leaves mexFunction with a longjmp that runs no C++ destructor, so nothing in
+// here calls it directly - failures travel as a C++ exception (MexError) to the bottom of mexFunction, where every
+// local (mask byte vectors, the engine handle, property copies) has already been destroyed.
+//
 // Build (on a machine with MATLAB; not possible in the offline build container):
 //   mex -R2018a -I<repo>/include aoadmm_mex.cpp -L<repo>/matlab-code_b200/aoadmm_b200 -laoadmm_b200
 // tests/test_capi_host.py compiles this file against a stub mex.h so that it at least stays syntactically valid.
@@ -21,7 +28,28 @@
 
 namespace {
 
-[[noreturn]] void fail(const char* id, const std::string& msg) { mexErrMsgIdAndTxt(id, "%s", msg.c_str()); }
+struct MexError {
+  std::string id, msg;
+};
+[[noreturn]] void fail(const char* id, const std::string& msg) { throw MexError{id, msg}; }
+
+// mxGetProperty returns a deep COPY that the caller owns (a second host copy of a whole tensor): the copies made during
+// one call are collected here and destroyed when the call ends.  cmtf_fun_AOADMM.m passes Z.object{p}.data (shared
+// data, no copy), so this path only serves callers that hand a Tensor Toolbox object to aoadmm_mex directly.
+struct PropertyCopies {
+  std::vector<mxArray*> owned;
+  ~PropertyCopies() {
+    for (mxArray* a : owned) mxDestroyArray(a);
+  }
+};
+
+// engine handle owned for the duration of the call
+struct HandleGuard {
+  aoadmm_handle* h = nullptr;
+  ~HandleGuard() {
+    if (h != nullptr) aoadmm_destroy(h);
+  }
+};
 
 const mxArray* field(const mxArray* s, const char* name, bool required = true) {
   const mxArray* f = mxIsStruct(s) ? mxGetField(s, 0, name) : nullptr;
@@ -48,10 +76,11 @@ std::string string_of(const mxArray* a) {
 }
 
 // numeric data of a Tensor Toolbox `tensor` object (property .data) or of a plain double array
-const mxArray* dense_data(const mxArray* obj) {
+const mxArray* dense_data(const mxArray* obj, PropertyCopies& pc) {
   if (std::strcmp(mxGetClassName(obj), "tensor") == 0) {
-    const mxArray* d = mxGetProperty(obj, 0, "data");
+    mxArray* d = mxGetProperty(obj, 0, "data");
     if (d == nullptr) fail("aoadmm:invalidArg", "tensor object without .data");
+    pc.owned.push_back(d);
     return d;
   }
   if (!mxIsDouble(obj) || mxIsComplex(obj) || mxIsSparse(obj))
@@ -61,15 +90,20 @@ const mxArray* dense_data(const mxArray* obj) {
 
 // Z.miss{p} (cmtf_AOADMM.m:68-121): logical / numeric array, Tensor Toolbox tensor, or sptensor (converted with
 // full()) -> one byte per element, 1 = observed
-std::vector<uint8_t> mask_bytes(const mxArray* m, size_t expected, int p) {
-  mxArray* conv = nullptr;
+std::vector<uint8_t> mask_bytes(const mxArray* m, size_t expected, int p, PropertyCopies& pc) {
   if (std::strcmp(mxGetClassName(m), "sptensor") == 0) {
     mxArray* in = const_cast<mxArray*>(m);
+    mxArray* conv = nullptr;
     if (mexCallMATLAB(1, &conv, 1, &in, "full") != 0 || conv == nullptr)
       fail("cmtf:missingData:maskTypeError", "Z.miss{" + std::to_string(p + 1) + "} cannot be converted with full()");
+    pc.owned.push_back(conv);
     m = conv;
   }
-  if (std::strcmp(mxGetClassName(m), "tensor") == 0) m = mxGetProperty(m, 0, "data");
+  if (std::strcmp(mxGetClassName(m), "tensor") == 0) {
+    mxArray* d = mxGetProperty(m, 0, "data");
+    if (d != nullptr) pc.owned.push_back(d);
+    m = d;
+  }
   if (m == nullptr || mxGetNumberOfElements(m) != expected)
     fail("cmtf:missingData:maskSizeMismatch", "Z.miss{" + std::to_string(p + 1) + "} size does not match Z.object{" + std::to_string(p + 1) + "}.");
   std::vector<uint8_t> out(expected);
@@ -82,7 +116,6 @@ std::vector<uint8_t> mask_bytes(const mxArray* m, size_t expected, int p) {
   } else {
     fail("cmtf:missingData:maskTypeError", "Z.miss{" + std::to_string(p + 1) + "} must be logical, double, tensor or sptensor");
   }
-  if (conv != nullptr) mxDestroyArray(conv);
   return out;
 }
 
@@ -104,8 +137,7 @@ int constraint_kind(const std::string& n) {  // constraints_to_prox.m:13-91
 
 void check(int status, aoadmm_handle* h) {
   if (status == AOADMM_OK) return;
-  const std::string msg = aoadmm_last_error(h);
-  if (h != nullptr) aoadmm_destroy(h);
+  const std::string msg = aoadmm_last_error(h);   // copied before the HandleGuard of the caller destroys its owner
   switch (status) {
     case AOADMM_ERR_UNSUPPORTED: fail("aoadmm:unsupported", msg);
     case AOADMM_ERR_NOT_POSITIVE_DEFINITE: fail("aoadmm:notPositiveDefinite", msg);  // chol() would have thrown
@@ -129,7 +161,9 @@ const StateField kModeFields[] = {{"fac", AOADMM_FIELD_FAC},
 
 }  // namespace
 
-void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+namespace {
+void solve(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  PropertyCopies pc;
   if (nrhs != 4) fail("aoadmm:invalidArg", "usage: [G,out] = aoadmm_mex(Z, Znorm_const, G, options)");
   if (nlhs > 2) fail("aoadmm:invalidArg", "too many outputs");
   const mxArray *Z = prhs[0], *Zn = prhs[1], *G = prhs[2], *opt = prhs[3];
@@ -197,11 +231,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (par2) {
       const int K = (int)mxGetNumberOfElements(obj);
       obj_slices[p].resize(K);
-      for (int k = 0; k < K; ++k) obj_slices[p][k] = mxGetPr(dense_data(mxGetCell(obj, k)));
+      for (int k = 0; k < K; ++k) obj_slices[p][k] = mxGetPr(dense_data(mxGetCell(obj, k), pc));
       o.slices = obj_slices[p].data();
       o.n_slices = K;
     } else {
-      o.data = mxGetPr(dense_data(obj));
+      const mxArray* dd = dense_data(obj, pc);
+      size_t expect = 1;
+      for (int d = 0; d < order; ++d) expect *= (size_t)mode_rows[obj_modes[p][d] - 1];
+      if (mxGetNumberOfElements(dd) != expect) fail("aoadmm:invalidArg", "Z.object{" + std::to_string(p + 1) + "} does not have the size Z.size prescribes");
+      o.data = mxGetPr(dd);
       o.shard_offset = 0;
       o.shard_extent = mode_rows[obj_modes[p][order - 1] - 1];
     }
@@ -214,12 +252,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         miss_par2[p].resize(K);
         miss_par2_ptr[p].resize(K);
         for (int k = 0; k < K; ++k) {
-          miss_par2[p][k] = mask_bytes(mxGetCell(mp, k), mxGetNumberOfElements(dense_data(mxGetCell(obj, k))), p);
+          miss_par2[p][k] = mask_bytes(mxGetCell(mp, k), (size_t)mode_rows[obj_modes[p][0] - 1] * (size_t)slice_rows[obj_modes[p][1] - 1][k], p, pc);
           miss_par2_ptr[p][k] = miss_par2[p][k].data();
         }
         o.miss_slices = miss_par2_ptr[p].data();
       } else {
-        miss_cp[p] = mask_bytes(mp, mxGetNumberOfElements(dense_data(obj)), p);
+        size_t expect = 1;
+        for (int d = 0; d < order; ++d) expect *= (size_t)mode_rows[obj_modes[p][d] - 1];
+        miss_cp[p] = mask_bytes(mp, expect, p, pc);
         o.miss = miss_cp[p].data();
       }
     }
@@ -317,8 +357,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   pb.constraints = cons.data();
   pb.ridge = (ridge != nullptr && !mxIsEmpty(ridge)) ? mxGetPr(ridge) : nullptr;
 
-  aoadmm_handle* h = nullptr;
-  check(aoadmm_create(&pb, nullptr, &h), nullptr);
+  // one MATLAB session drives options.b200_gpus devices (default 1): the library cuts the mode-3 slabs itself
+  const int n_gpus = (int)opt_scalar(opt, "b200_gpus", 1.0);
+  if (n_gpus < 1) fail("aoadmm:invalidArg", "options.b200_gpus must be >= 1");
+  HandleGuard guard;
+  check(n_gpus > 1 ? aoadmm_create_multi(&pb, n_gpus, nullptr, &guard.h) : aoadmm_create(&pb, nullptr, &guard.h), nullptr);
+  aoadmm_handle* h = guard.h;
 
   // ---- state in ------------------------------------------------------------------------------
   auto put = [&](int fld, int index, int slice, const mxArray* a) {
@@ -416,15 +460,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     }
     get(AOADMM_FIELD_PAR2_DELTAB, p + 1, 0, mxGetCell(mxGetField(Gout, 0, "DeltaB"), p));
   }
-  aoadmm_destroy(h);
   plhs[0] = Gout;
 
   // ---- out struct (cmtf_fun_AOADMM.m:480-494) --------------------------------------------------
   if (nlhs > 1) {
     const char* names[] = {"f_tensors", "f_couplings", "f_constraints", "f_PAR2_couplings", "f_rel_missing", "exit_flag",
                            "OuterIterations", "func_val_conv", "func_coupl_conv", "func_constr_conv", "func_PAR2_coupl",
-                           "time_at_it", "innerIters", "func_rel_missing"};
-    mxArray* out = mxCreateStructMatrix(1, 1, 14, names);
+                           "time_at_it", "innerIters", "func_rel_missing", "non_finite_mode"};
+    mxArray* out = mxCreateStructMatrix(1, 1, 15, names);
+    mxSetField(out, 0, "non_finite_mode", mxCreateDoubleScalar((double)ro.non_finite_mode));
     mxSetField(out, 0, "f_tensors", mxCreateDoubleScalar(ro.f_tensors));
     mxSetField(out, 0, "f_couplings", mxCreateDoubleScalar(ro.f_couplings));
     mxSetField(out, 0, "f_constraints", mxCreateDoubleScalar(ro.f_constraints));
@@ -454,4 +498,28 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   } else {
     for (auto& a : hist) mxDestroyArray(a);
   }
+}
+}  // namespace
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  std::string id, msg;
+  try {
+    solve(nlhs, plhs, nrhs, prhs);
+    return;
+  } catch (const MexError& e) {
+    id = e.id;
+    msg = e.msg;
+  } catch (const std::exception& e) {
+    id = "aoadmm:internal";
+    msg = e.what();
+  }
+  // MATLAB copies the formatted message before the longjmp; the two strings above are the only live C++ objects
+  static char idbuf[128], msgbuf[2048];
+  std::strncpy(idbuf, id.c_str(), sizeof(idbuf) - 1);
+  std::strncpy(msgbuf, msg.c_str(), sizeof(msgbuf) - 1);
+  id.clear();
+  id.shrink_to_fit();
+  msg.clear();
+  msg.shrink_to_fit();
+  mexErrMsgIdAndTxt(idbuf, "%s", msgbuf);
 }

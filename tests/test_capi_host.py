@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(ab):
     for n in names:
         assert hasattr(ab._capi.lib, n), n
     assert sorted(ab._capi.EXPORTS) == names
-    assert ab._capi.lib.aoadmm_abi_version() == 3
+    assert ab._capi.lib.aoadmm_abi_version() == 4
 
 
 def test_struct_layouts_match_header(ab, tmp_path):
