@@ -275,10 +275,12 @@ def main():
         lo, hi = ab.shard_range(K, rank, world)
         return ab.Solver(Zx, zn, rank=rank, world_size=world, device=local_rank, unique_id=uid, shard=[(lo, hi), None]), (lo, hi)
 
+    warm_out = [None]   # `out` of the most recent warm-up run (the trajectory from G)
+
     def timed_run(solver, G, opts_fn, steps, whole_ms=None):
         """W warm-up steps, then exactly `steps` outer iterations timed with CUDA events on the engine's stream(s)."""
         solver.set_state(G)
-        solver.run(opts_fn(max(args.warmup, 3)))
+        warm_out[0] = solver.run(opts_fn(max(args.warmup, 3)))
         barrier()
         l0 = solver.launch_count()
         ph0 = solver.phase_ms().copy()
@@ -307,6 +309,7 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms, wall_ms, launches, ph, out = timed_run(solver, G, zero_tol_options, args.steps, whole_ms)
+    traj = np.array(warm_out[0]['func_val_conv'])   # objective of the first W iterations from G (device-resident data)
     call_ms = whole_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     if world == 1 and (clocks is None or not clocks.get('samples')):
@@ -403,8 +406,11 @@ def main():
         e2e_run_dev_ms = s2.last_run_ms()
         s2.close()
         assert o2['OuterIterations'] == args.steps and np.isfinite(o2['f_tensors'])
-        # the end-to-end call starts from the same data and state as the device-resident leg: same answer
-        assert abs(o2['f_tensors'] - out['f_tensors']) <= 1e-10 * max(1.0, abs(out['f_tensors'])), (o2['f_tensors'], out['f_tensors'])
+        # the end-to-end call starts from the same data and state as the device-resident leg's warm-up run: the same
+        # objective trajectory over the iterations both have made
+        nt = min(len(traj), len(o2['func_val_conv']))
+        assert np.max(np.abs(o2['func_val_conv'][:nt] - traj[:nt]) / np.maximum(1.0, np.abs(traj[:nt]))) < 1e-10, \
+            (o2['func_val_conv'][:nt], traj[:nt])
         e2e_s = max_over_ranks(e2e_s)
         state_bytes = sum(a.nbytes for k in ('fac', 'constraint_fac', 'constraint_dual_fac', 'coupling_dual_fac', 'coupling_fac')
                           for a in G[k] if a is not None)

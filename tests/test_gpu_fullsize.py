@@ -113,7 +113,8 @@ def test_config3_slab_mttkrp_rows_and_dimension_tree(ab):
             runs[dt] = (s.get_state(), out)
     for m in range(5):
         assert rel(runs[1][0]['fac'][m], runs[0][0]['fac'][m]) < 1e-10, m
-    assert np.max(np.abs(runs[1][1]['func_val_conv'] - runs[0][1]['func_val_conv'])) < 1e-12
+    f3, ft = runs[0][1]['func_val_conv'], runs[1][1]['func_val_conv']     # (random, unnormalised start: f ~ 1e4)
+    assert np.max(np.abs(ft - f3) / np.maximum(1.0, np.abs(f3))) < 1e-12
     # first outer iteration against the oracle's scalar bookkeeping: objective at iteration 0 from the host copy
     # (cp_func.m:47-56): f = w * (||X||^2 - 2 <X, [[A,B,C]]> + ||[[A,B,C]]||^2) + the same for the matrix
     from oracle.tensor_ops import mttkrp as oracle_mttkrp

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <vector>
 
+// every launch is followed by CK(cudaGetLastError()): a launch that fails (e.g. too many resources for 32 warps x 16
+// accumulators) must not be timed - an unlaunched kernel "runs" in microseconds and prints an absurd rate
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); exit(1);} }while(0)
 
 template<int NACC>
@@ -66,9 +68,9 @@ int main() {
     auto run = [&](int nacc) {
       for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        if (nacc == 4) dmma_rate<4><<<sms, warps * 32>>>(out, iters, 1.0);
-        if (nacc == 8) dmma_rate<8><<<sms, warps * 32>>>(out, iters, 1.0);
-        if (nacc == 16) dmma_rate<16><<<sms, warps * 32>>>(out, iters, 1.0);
+        if (nacc == 4) dmma_rate<4><<<sms, warps * 32>>>(out, iters, 1.0); CK(cudaGetLastError());
+        if (nacc == 8) dmma_rate<8><<<sms, warps * 32>>>(out, iters, 1.0); CK(cudaGetLastError());
+        if (nacc == 16) dmma_rate<16><<<sms, warps * 32>>>(out, iters, 1.0); CK(cudaGetLastError());
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
       }
       float ms = time_ms(e0, e1);
@@ -81,7 +83,7 @@ int main() {
     int iters = 20000;
     for (int rep = 0; rep < 3; rep++) {
       cudaEventRecord(e0);
-      dfma_rate<16><<<sms, warps * 32>>>(out, iters, 1.0);
+      dfma_rate<16><<<sms, warps * 32>>>(out, iters, 1.0); CK(cudaGetLastError());
       cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     }
     float ms = time_ms(e0, e1);
@@ -92,7 +94,7 @@ int main() {
   {
     int iters = 2000000;
     cudaEventRecord(e0);
-    dmma_rate<16><<<sms, 16 * 32>>>(out, iters, 1.0);
+    dmma_rate<16><<<sms, 16 * 32>>>(out, iters, 1.0); CK(cudaGetLastError());
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     float ms = time_ms(e0, e1);
     double flops = 2.0 * 256 * 16 * (double)iters * 16 * sms;
@@ -105,7 +107,7 @@ int main() {
     for (int blocks : {sms * 4, sms * 8, sms * 16}) {
       for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        read_bw<<<blocks, 512>>>(x, bytes / 16, out);
+        read_bw<<<blocks, 512>>>(x, bytes / 16, out); CK(cudaGetLastError());
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
       }
       float ms = time_ms(e0, e1);
