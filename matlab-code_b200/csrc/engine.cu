@@ -640,6 +640,10 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
         dev_alloc(m.Znew, m.rows, m.R);
         dev_alloc(m.V, m.rows, m.R);
         prox_bytes = std::max(prox_bytes, prox_scratch_bytes(m.con.kind, m.rows, m.R));
+        if (m.par2_role == 2 && prox_supports_segments(m.con.kind)) {
+          const Par2State& s = par2_[m.par2];
+          prox_bytes = std::max(prox_bytes, prox_segments_scratch_bytes(m.con.kind, s.Jmax, m.R, s.K));
+        }
       }
     }
     if (m.coupling != 0 && m.lin < 0) dev_alloc(m.muD, m.rows, m.R);  // linear couplings: allocated with their own shape
@@ -1288,8 +1292,12 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
       launches_ += par2_B_form_prox_input(s.lay, b, m.V.p, m.ctl, st_);
       if (m.con.kind == AOADMM_CON_TPARAFAC2) {  // :553-554: all slices at once with the vector rho
         launches_ += par2_tsmooth_prox(s.lay, m.V.p, s.rho2, m.con.p0, s.tdiag, m.Znew.p, m.ctl, st_);
+      } else if (prox_supports_segments(m.con.kind)) {
+        // :567-568: prox of every slice with its own rho_k - all K slices and R columns in ONE launch
+        launches_ += prox_apply_segments(m.con.kind, m.con.p0, m.con.p1, m.V.p, s.Jtot, m.Znew.p, s.Jtot, s.joff_dev, s.K,
+                                         s.Jmax, s.Jtot, s.R, s.rho2, prox_scratch_, st_, &m.ctl->done);
       } else {
-        for (int k = 0; k < s.K; ++k)  // :567-568: prox of every slice with its own rho_k
+        for (int k = 0; k < s.K; ++k)  // whole-matrix operators ('orthonormal', 'quadratic regularization'): per slice
           launches_ += apply_prox(m, m.V.p + s.joff[k], s.Jtot, m.Znew.p + s.joff[k], s.Jtot, s.joff[k + 1] - s.joff[k], s.R,
                                   s.rho2 + k, &m.ctl->done);
       }

@@ -20,6 +20,22 @@ __device__ __forceinline__ double load_rho(const double* rho_dev, double rho_hos
   return rho_dev != nullptr ? *rho_dev : rho_host;
 }
 
+// Segmented application (PARAFAC2 B_k mode, cmtf_fun_AOADMM.m:567-568): the stacked Jtot x R matrix is K independent
+// row segments [seg_off[k], seg_off[k+1]) with their own rho_k; blockIdx.y picks the segment, so the prox of every
+// slice and every column is ONE launch instead of K.  seg_off == nullptr: the whole column, scalar rho.
+struct SegInfo {
+  const long long* seg_off;
+  long long max_rows;   // longest segment (sizes the per-column workspace)
+};
+__device__ __forceinline__ void seg_select(const SegInfo& sg, long long& rows, long long& row0, const double*& rho_dev) {
+  row0 = 0;
+  if (sg.seg_off != nullptr) {
+    row0 = sg.seg_off[blockIdx.y];
+    rows = sg.seg_off[blockIdx.y + 1] - row0;
+    if (rho_dev != nullptr) rho_dev += blockIdx.y;
+  }
+}
+
 __device__ __forceinline__ double prox_elem2(int kind, double v, double p0, double p1, double rho) {
   switch (kind) {
     case PROX_NONNEG: return fmax(v, 0.0);
@@ -54,14 +70,16 @@ __global__ void prox_elementwise_kernel(int kind, double p0, double p1, const do
 // ---- column-norm based operators: one CTA per column ----------------------------------------------
 __global__ void prox_colnorm_kernel(int kind, double p0, const double* __restrict__ X, long long ldx,
                                     double* __restrict__ out, long long ldo, long long rows,
-                                    const double* rho_dev, double rho_host, const int* __restrict__ skip) {
+                                    const double* rho_dev, double rho_host, const int* __restrict__ skip, SegInfo sg) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ double red[32];
   __shared__ double s_val;
   __shared__ long long s_arg;
+  long long row0;
+  seg_select(sg, rows, row0, rho_dev);
   const double rho = load_rho(rho_dev, rho_host);
-  const double* x = X + (long long)blockIdx.x * ldx;
-  double* o = out + (long long)blockIdx.x * ldo;
+  const double* x = X + (long long)blockIdx.x * ldx + row0;
+  double* o = out + (long long)blockIdx.x * ldo + row0;
   const bool nonneg = (kind == PROX_NONNEG_L2_BALL || kind == PROX_NONNEG_L2_SPHERE);
   double s = 0.0;
   for (long long i = threadIdx.x; i < rows; i += blockDim.x) {
@@ -109,13 +127,16 @@ __global__ void prox_colnorm_kernel(int kind, double p0, const double* __restric
 // ---- simplex / l1-ball: Michelot's finite algorithm, one CTA per column -----------------------------
 __global__ void prox_simplex_col_kernel(int kind, double eta, const double* __restrict__ X, long long ldx,
                                         double* __restrict__ out, long long ldo, long long rows,
-                                        const int* __restrict__ skip) {
+                                        const int* __restrict__ skip, SegInfo sg) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ double red[32];
   __shared__ double s_theta;
   __shared__ double s_cnt;
-  const double* x = X + (long long)blockIdx.x * ldx;
-  double* o = out + (long long)blockIdx.x * ldo;
+  long long row0;
+  const double* no_rho = nullptr;
+  seg_select(sg, rows, row0, no_rho);
+  const double* x = X + (long long)blockIdx.x * ldx + row0;
+  double* o = out + (long long)blockIdx.x * ldo + row0;
   const bool l1 = (kind == PROX_L1_BALL);
   if (l1) {
     double s = 0.0;
@@ -453,13 +474,15 @@ template <bool SMEM>
 __global__ void prox_serial_col_kernel(int kind, double p0, const double* __restrict__ X, long long ldx,
                                        double* __restrict__ out, long long ldo, long long rows,
                                        const double* rho_dev, double rho_host, double* gscratch,
-                                       long long scratch_per_col, const int* __restrict__ skip, int tv_dp) {
+                                       long long scratch_per_col, const int* __restrict__ skip, int tv_dp, SegInfo sg) {
   if (skip != nullptr && *skip != 0) return;
   extern __shared__ double sm[];
+  long long row0;
+  seg_select(sg, rows, row0, rho_dev);
   const double rho = load_rho(rho_dev, rho_host);
-  double* base = SMEM ? sm : (gscratch + (long long)blockIdx.x * scratch_per_col);
-  const double* x = X + (long long)blockIdx.x * ldx;
-  double* o = out + (long long)blockIdx.x * ldo;
+  double* base = SMEM ? sm : (gscratch + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * scratch_per_col);
+  const double* x = X + (long long)blockIdx.x * ldx + row0;
+  double* o = out + (long long)blockIdx.x * ldo + row0;
   const long long n = rows;
   double* y = base;          // n
   double* res = base + n;    // n
@@ -527,10 +550,46 @@ size_t prox_scratch_bytes(int kind, long long rows, int cols) {
   return (per > kSerialSmemLimit) ? per * (size_t)cols : 0;
 }
 
+size_t prox_segments_scratch_bytes(int kind, long long max_rows, int cols, int nseg) {
+  if (!is_serial_kind(kind)) return 0;
+  const size_t per = (size_t)serial_doubles_per_col(kind, max_rows) * sizeof(double);
+  return (per > kSerialSmemLimit) ? per * (size_t)cols * (size_t)nseg : 0;
+}
+
+bool prox_supports_segments(int kind) {
+  return kind == PROX_L2_BALL || kind == PROX_NONNEG_L2_BALL || kind == PROX_NONNEG_L2_SPHERE || kind == PROX_L2_REG ||
+         kind == PROX_SIMPLEX_COL || kind == PROX_L1_BALL || kind == PROX_SIMPLEX_ROW || is_serial_kind(kind);
+}
+
+namespace {
+int prox_apply_impl(int kind, double p0, double p1, const double* X, long long ldx, double* out, long long ldo,
+                    long long rows, int cols, const double* rho_dev, double rho_host, void* scratch, cudaStream_t st,
+                    const int* skip, SegInfo sg, int nseg, long long total_rows);
+}
+
 int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, double* out, long long ldo,
                long long rows, int cols, const double* rho_dev, double rho_host, void* scratch, cudaStream_t st,
                const int* skip) {
+  return prox_apply_impl(kind, p0, p1, X, ldx, out, ldo, rows, cols, rho_dev, rho_host, scratch, st, skip,
+                         SegInfo{nullptr, rows}, 1, rows);
+}
+
+int prox_apply_segments(int kind, double p0, double p1, const double* X, long long ldx, double* out, long long ldo,
+                        const long long* seg_off_dev, int nseg, long long max_rows, long long total_rows, int cols,
+                        const double* rho_dev_per_seg, void* scratch, cudaStream_t st, const int* skip) {
+  if (!prox_supports_segments(kind)) throw CudaError(2, "prox_apply_segments: kind " + std::to_string(kind) + " works on whole matrices");
+  if (nseg <= 0) return 0;
+  return prox_apply_impl(kind, p0, p1, X, ldx, out, ldo, max_rows, cols, rho_dev_per_seg, 0.0, scratch, st, skip,
+                         SegInfo{seg_off_dev, max_rows}, nseg, total_rows);
+}
+
+namespace {
+int prox_apply_impl(int kind, double p0, double p1, const double* X, long long ldx, double* out, long long ldo,
+                    long long rows, int cols, const double* rho_dev, double rho_host, void* scratch, cudaStream_t st,
+                    const int* skip, SegInfo sg, int nseg, long long total_rows) {
+
   if (rows <= 0 || cols <= 0) return 0;
+  const dim3 colgrid((unsigned)cols, (unsigned)nseg);
   if (prox_is_elementwise(kind) || kind == PROX_NONE) {
     const long long n = rows * cols;
     const unsigned ctas = (unsigned)std::min<long long>(ceil_div(n, 256), 148 * 8);
@@ -543,16 +602,17 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     case PROX_NONNEG_L2_BALL:
     case PROX_NONNEG_L2_SPHERE:
     case PROX_L2_REG:
-      prox_colnorm_kernel<<<cols, 256, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host, skip);
+      prox_colnorm_kernel<<<colgrid, 256, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host, skip, sg);
       AO_CHECK_LAUNCH();
       return 1;
     case PROX_SIMPLEX_COL:
     case PROX_L1_BALL:
-      prox_simplex_col_kernel<<<cols, 256, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, skip);
+      prox_simplex_col_kernel<<<colgrid, 256, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, skip, sg);
       AO_CHECK_LAUNCH();
       return 1;
     case PROX_SIMPLEX_ROW:
-      prox_simplex_row_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, st>>>(p0, X, ldx, out, ldo, rows, cols, skip);
+      // rows are independent and the projection does not involve rho: the stacked matrix is one problem
+      prox_simplex_row_kernel<<<(unsigned)ceil_div(total_rows, 128), 128, 0, st>>>(p0, X, ldx, out, ldo, total_rows, cols, skip);
       AO_CHECK_LAUNCH();
       return 1;
     default: break;
@@ -583,15 +643,16 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
     if (use_smem && bytes > 48 * 1024)
       ensure_dynamic_smem(reinterpret_cast<const void*>(prox_serial_col_kernel<true>), kSerialSmemLimit);
     if (use_smem)
-      prox_serial_col_kernel<true><<<cols, 32, bytes, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
-                                                            static_cast<double*>(scratch), per, skip, tv_dp);
+      prox_serial_col_kernel<true><<<colgrid, 32, bytes, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
+                                                               static_cast<double*>(scratch), per, skip, tv_dp, sg);
     else
-      prox_serial_col_kernel<false><<<cols, 32, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
-                                                         static_cast<double*>(scratch), per, skip, 0);
+      prox_serial_col_kernel<false><<<colgrid, 32, 0, st>>>(kind, p0, X, ldx, out, ldo, rows, rho_dev, rho_host,
+                                                            static_cast<double*>(scratch), per, skip, 0, sg);
     AO_CHECK_LAUNCH();
     return 1;
   }
   throw CudaError(2, "prox kind " + std::to_string(kind) + " is not implemented on device");
 }
+}  // namespace
 
 }  // namespace aoadmm

@@ -143,6 +143,15 @@ int prox_apply(int kind, double p0, double p1, const double* X, long long ldx, d
                long long rows, int cols, const double* rho_dev, double rho_host, void* scratch, cudaStream_t st,
                const int* skip);
 
+// The same operator applied to K row segments of a stacked matrix in ONE launch (PARAFAC2 B_k mode, :567-568: the prox of
+// every slice with its own rho_k): segment k = rows seg_off_dev[k] .. seg_off_dev[k+1]-1 of every column, rho of segment
+// k = rho_dev_per_seg[k].  Only kinds with prox_supports_segments(); scratch >= prox_segments_scratch_bytes().
+bool prox_supports_segments(int kind);
+size_t prox_segments_scratch_bytes(int kind, long long max_rows, int cols, int nseg);
+int prox_apply_segments(int kind, double p0, double p1, const double* X, long long ldx, double* out, long long ldo,
+                        const long long* seg_off_dev, int nseg, long long max_rows, long long total_rows, int cols,
+                        const double* rho_dev_per_seg, void* scratch, cudaStream_t st, const int* skip);
+
 // 'quadratic regularization' (constraints_to_prox.m:62-67): prox(x,rho) = (2*eta/rho*L + I) \ x for a SYMMETRIC L,
 // applied in the eigen-basis L = Q diag(lam) Q' (computed once): out = Q * ((Q'x) ./ (2*eta/rho*lam + 1)).
 struct QuadProx {
