@@ -7,8 +7,8 @@
 //   :1249-1252 objective of a PARAFAC2 object with a mask: w sum_k || M_k .* (X_k - A D_k B_k') ||^2
 // One pass over the object does all of it: the model value of every element is a rank-R product
 //     m(i,j,k) = sum_r Fi(i,r) Fj(j,r) Fk(k,r)
-// evaluated by 64 x 64 output tiles (4 x 4 outputs per thread, factor tiles staged in shared memory), compared with
-// the stored element and the mask, and five sums are reduced deterministically (per-CTA partials, fixed-order final
+// evaluated as a GEMM per slab k on the FP64 tensor cores (DMMA.8x8x4; 64 x 64 output tiles, factor tiles staged in
+// shared memory once per CTA), compared with the stored element and the mask, and five sums are reduced deterministically (per-CTA partials, fixed-order final
 // sum):  [0] sum_missing (m-x)^2   [1] sum_missing x^2   [2] sum_observed x*m   [3] sum_observed m^2
 //        [4] sum_observed (x-m)^2
 // A PARAFAC2 object is the K = 1 case on the stacked I x Jtot matrix with Fj(j,:) = B(j,:) .* C(seg(j),:).
@@ -21,92 +21,104 @@ namespace aoadmm {
 namespace {
 
 constexpr int kTile = 64;
-constexpr int kRC = 32;  // rank chunk staged per pass
+constexpr int kRC = 32;          // rank chunk staged per pass
+constexpr int kPitch = kTile + 4;  // smem row pitch: the 4 x 8 fragment footprint of a DMMA operand hits 32 distinct banks
 
-__global__ void __launch_bounds__(256) em_kernel(EmArgs a, int kper) {
-  __shared__ double As[kRC][kTile];
-  __shared__ double Bs[kRC][kTile];
+// The model of slab k is a rank-R GEMM, M_k = (Fi diag(Fk(k,:))) * Fj': it runs on the FP64 tensor cores like the
+// MTTKRP (mma.m8n8k4, SASS DMMA.8x8x4).  CTA tile 64 (i) x 64 (j), 8 warps as 4 (i) x 2 (j), warp tile 16 x 32 =
+// 2 x 4 accumulator tiles.  The unscaled factor tiles are staged in shared memory once per CTA (once per rank chunk
+// when R > 32) and reused for every k of the CTA's range; the k-dependent scale Fk(k,r) is applied to the A fragment
+// in registers (2 DMUL per 8 DMMA).  Epilogue per k: the 16 model values of a lane are compared with the stored
+// element and the mask byte, missing entries are overwritten, five sums are accumulated.
+__global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
+  __shared__ double As[kRC][kPitch];
+  __shared__ double Bs[kRC][kPitch];
+  __shared__ double cs[kRC];
   __shared__ double red[32];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wi = warp & 3, wj = warp >> 2;
+  const int q = lane & 3, p = lane >> 2;
   const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTile;
   const int k0 = blockIdx.z * kper, k1 = min(a.K, k0 + kper);
   const int nchunk = (a.R + kRC - 1) / kRC;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int k = k0; k < k1; ++k) {
-    double acc[4][4];
+    double acc[2][4][2];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     for (int c = 0; c < nchunk; ++c) {
       const int r0 = c * kRC;
-      __syncthreads();
-      for (int e = tid; e < kRC * kTile; e += 256) {
-        const int ii = e % kTile, rr = e / kTile;
-        const int r = r0 + rr;
-        double va = 0.0;
-        if (r < a.R && i0 + ii < a.I) {
-          va = a.Fi[i0 + ii + (long long)r * a.ldFi];
-          if (a.Fk != nullptr) va *= a.Fk[k + (long long)r * a.ldFk];
-        }
-        As[rr][ii] = va;
-      }
+      __syncthreads();   // every warp has finished reading cs / As / Bs of the previous (k, chunk)
       if (nchunk > 1 || k == k0) {
         for (int e = tid; e < kRC * kTile; e += 256) {
-          const int jj = e % kTile, rr = e / kTile;
+          const int ii = e % kTile, rr = e / kTile;
           const int r = r0 + rr;
-          Bs[rr][jj] = (r < a.R && j0 + jj < a.J) ? a.Fj[j0 + jj + (long long)r * a.ldFj] : 0.0;
+          As[rr][ii] = (r < a.R && i0 + ii < a.I) ? a.Fi[i0 + ii + (long long)r * a.ldFi] : 0.0;
+          Bs[rr][ii] = (r < a.R && j0 + ii < a.J) ? a.Fj[j0 + ii + (long long)r * a.ldFj] : 0.0;
         }
+      }
+      if (tid < kRC) {
+        const int r = r0 + tid;
+        cs[tid] = (r < a.R) ? ((a.Fk != nullptr) ? a.Fk[k + (long long)r * a.ldFk] : 1.0) : 0.0;
       }
       __syncthreads();
-#pragma unroll 8
-      for (int rr = 0; rr < kRC; ++rr) {
-        double av[4], bv[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) av[p] = As[rr][tx + 16 * p];
+      for (int ks = 0; ks < kRC / 4; ++ks) {
+        const int rr = 4 * ks + q;
+        const double ck = cs[rr];
+        double af[2], bf[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bv[q] = Bs[rr][ty + 16 * q];
+        for (int mt = 0; mt < 2; ++mt) af[mt] = As[rr][16 * wi + 8 * mt + p] * ck;
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = Bs[rr][32 * wj + 8 * nt + p];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[p][q] = fma(av[p], bv[q], acc[p][q]);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
     }
-    // epilogue: all loads of the tile first (independent, so their DRAM latencies overlap), then compare / impute
-    double xv[4][4];
-    uint8_t mk[4][4];
+    // epilogue: accumulator (mt, nt, e) of this lane is element i = i0 + 16 wi + 8 mt + p, j = j0 + 32 wj + 8 nt + 2 q + e.
+    // All loads of the tile first (independent, so their DRAM latencies overlap), then compare / impute.
+    double xv[2][4][2];
+    uint8_t mk[2][4][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long j = j0 + ty + 16 * q;
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const long long i = i0 + tx + 16 * p;
-        const bool in = (i < a.I) && (j < a.J);
-        const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
-        xv[p][q] = in ? a.X[idx] : 0.0;
-        mk[p][q] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed (as in norm2_masked_kernel); 2 = outside the object
-      }
-    }
+      for (int e = 0; e < 2; ++e) {
+        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long j = j0 + ty + 16 * q;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const long long i = i0 + tx + 16 * p;
-        const double x = xv[p][q], m = acc[p][q];
-        if (mk[p][q] == 1) {
-          s[2] = fma(x, m, s[2]);
-          s[3] = fma(m, m, s[3]);
-          const double d = x - m;
-          s[4] = fma(d, d, s[4]);
-        } else if (mk[p][q] == 0) {
-          const double d = m - x;
-          s[0] = fma(d, d, s[0]);
-          s[1] = fma(x, x, s[1]);
-          if (a.impute) a.X[i + a.ldI * (j + (long long)a.J * k)] = m;
+        for (int mt = 0; mt < 2; ++mt) {
+          const long long i = i0 + 16 * wi + 8 * mt + p;
+          const bool in = (i < a.I) && (j < a.J);
+          const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
+          xv[mt][nt][e] = in ? a.X[idx] : 0.0;
+          mk[mt][nt][e] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed; 2 = outside
         }
       }
-    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const long long i = i0 + 16 * wi + 8 * mt + p;
+          const double x = xv[mt][nt][e], m = acc[mt][nt][e];
+          if (mk[mt][nt][e] == 1) {
+            s[2] = fma(x, m, s[2]);
+            s[3] = fma(m, m, s[3]);
+            const double d = x - m;
+            s[4] = fma(d, d, s[4]);
+          } else if (mk[mt][nt][e] == 0) {
+            const double d = m - x;
+            s[0] = fma(d, d, s[0]);
+            s[1] = fma(x, x, s[1]);
+            if (a.impute) a.X[i + a.ldI * (j + (long long)a.J * k)] = m;
+          }
+        }
+      }
   }
   const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
 #pragma unroll
