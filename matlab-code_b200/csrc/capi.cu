@@ -224,7 +224,10 @@ int aoadmm_set_state(aoadmm_handle* h, int32_t field, int32_t index, int32_t sli
 int aoadmm_get_state(aoadmm_handle* h, int32_t field, int32_t index, int32_t slice, double* data, int64_t rows,
                      int64_t cols) {
   if (!h) return AOADMM_ERR_INVALID_ARG;
-  return guard(h, [&] { h->eng[0]->get_state(field, index, slice, data, rows, cols); });  // replicas are identical
+  return guard(h, [&] {
+    for_each_rank((int)h->eng.size(), [&](int r) { h->eng[r]->prepare_state_read(); });   // collective (no-op unless stale)
+    h->eng[0]->get_state(field, index, slice, data, rows, cols);                            // replicas are identical
+  });
 }
 
 int aoadmm_run(aoadmm_handle* h, const aoadmm_options* options, aoadmm_out* out) {

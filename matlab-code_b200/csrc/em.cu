@@ -48,6 +48,24 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    // The stored elements and mask bytes of this lane's 16 outputs are requested BEFORE the tensor-core loop, so their
+    // DRAM latency hides behind it: accumulator (mt, nt, e) is element i = i0 + 16 wi + 8 mt + p, j = j0 + 32 wj + 8 nt + 2 q + e.
+    double xv[2][4][2];
+    uint8_t mk[2][4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const long long i = i0 + 16 * wi + 8 * mt + p;
+          const bool in = (i < a.I) && (j < a.J);
+          const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
+          xv[mt][nt][e] = in ? a.X[idx] : 0.0;
+          mk[mt][nt][e] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed; 2 = outside
+        }
+      }
     for (int c = 0; c < nchunk; ++c) {
       const int r0 = c * kRC;
       __syncthreads();   // every warp has finished reading cs / As / Bs of the previous (k, chunk)
@@ -79,24 +97,7 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
           for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
     }
-    // epilogue: accumulator (mt, nt, e) of this lane is element i = i0 + 16 wi + 8 mt + p, j = j0 + 32 wj + 8 nt + 2 q + e.
-    // All loads of the tile first (independent, so their DRAM latencies overlap), then compare / impute.
-    double xv[2][4][2];
-    uint8_t mk[2][4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const long long i = i0 + 16 * wi + 8 * mt + p;
-          const bool in = (i < a.I) && (j < a.J);
-          const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
-          xv[mt][nt][e] = in ? a.X[idx] : 0.0;
-          mk[mt][nt][e] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed; 2 = outside
-        }
-      }
+    // epilogue: compare the model with the stored elements loaded above / impute
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll

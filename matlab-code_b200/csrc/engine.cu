@@ -719,7 +719,10 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
     double* res = cp0_tmp_ + 148 * 8;
     if (o.model == AOADMM_MODEL_PAR2) {
       Par2State& s = par2_[mode(o.modes[0]).par2];
-      launches_ += object_norm2(s.X, s.mask, s.I, s.ldX, s.Jtot, part, res, st_);
+      launches_ += object_norm2(s.X_alloc, s.mask_alloc, s.I, s.ldX, s.jhi - s.jlo, part, res, st_);
+      if (s.sharded) {   // sum of the ranks' slices (the communicator exists since the top of the constructor)
+        allreduce(res, 1);
+      }
     } else {
       size_t slab = 1;
       for (int d = 1; d < o.order; ++d) slab *= (size_t)o.dims[d];
@@ -830,7 +833,7 @@ void Engine::release() {
   lin_groups_.clear();
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
-    for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X, (void*)s.mask, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
+    for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X_alloc, (void*)s.mask_alloc, (void*)s.redbuf, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
                     (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.Vprev, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
                     (void*)s.res_partials})
       if (q) cudaFree(q);
@@ -1106,21 +1109,47 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   o.last_full = s.K;
   o.shard_extent = s.K;
   s.ldX = round_up(s.I, 2);
-  const size_t xbytes = std::max<size_t>((size_t)s.ldX * s.Jtot * sizeof(double), 256);
-  AO_CUDA(cudaMalloc(&s.X, xbytes));
-  if (s.ldX != s.I) AO_CUDA(cudaMemset(s.X, 0, xbytes));
+  // Slices sharded over the GPUs unless a path needs every slice on every rank: a linear coupling on one of
+  // the object's modes (the (K*R)^2 / row-wise systems of :283-355 are assembled from all slices), the tPARAFAC2 prox
+  // (a solve ACROSS the slices), quadratic regularisation on B_k, or fewer slices than ranks.
+  s.k0 = 0;
+  s.k1 = s.K;
+  if (world_ > 1 && s.K >= world_) {
+    bool ok = true;
+    for (int d = 0; d < 3; ++d) {
+      const ModeState& m = mode(o.modes[d]);
+      if (m.coupling != 0 && coupling_type_[m.coupling - 1] != 0) ok = false;
+    }
+    if (mb.constrained && (mb.con.kind == AOADMM_CON_TPARAFAC2 || mb.con.kind == AOADMM_CON_QUADRATIC ||
+                           mb.con.kind == AOADMM_CON_ORTHONORMAL))
+      ok = false;
+    if (ok) {
+      s.sharded = true;
+      s.k0 = (int)((int64_t)s.K * rank_ / world_);
+      s.k1 = (int)((int64_t)s.K * (rank_ + 1) / world_);
+    }
+  }
+  s.jlo = s.joff[s.k0];
+  s.jhi = s.joff[s.k1];
+  const int64_t Jloc = s.jhi - s.jlo;
+  const size_t xbytes = std::max<size_t>((size_t)s.ldX * Jloc * sizeof(double), 256);
+  AO_CUDA(cudaMalloc(&s.X_alloc, xbytes));
+  if (s.ldX != s.I) AO_CUDA(cudaMemset(s.X_alloc, 0, xbytes));
+  s.X = s.X_alloc - (size_t)s.jlo * s.ldX;      // global column indexing (only columns jlo..jhi-1 are ever touched)
   std::vector<int> seg((size_t)s.Jtot);
   for (int k = 0; k < s.K; ++k) {
+    for (int64_t j = s.joff[k]; j < s.joff[k + 1]; ++j) seg[(size_t)j] = k;
+    if (k < s.k0 || k >= s.k1) continue;          // another rank's slice (its pointer may be NULL)
     if (src.slices[k] == nullptr) throw CudaError(1, "PARAFAC2 object: NULL slice");
     AO_CUDA(cudaMemcpy2D(s.X + (size_t)s.joff[k] * s.ldX, (size_t)s.ldX * 8, src.slices[k], (size_t)s.I * 8,
                          (size_t)s.I * 8, (size_t)jk[k], cudaMemcpyHostToDevice));
-    for (int64_t j = s.joff[k]; j < s.joff[k + 1]; ++j) seg[(size_t)j] = k;
   }
   if (src.miss_slices != nullptr) {
-    const size_t mbytes = std::max<size_t>((size_t)s.ldX * s.Jtot, 256);
-    AO_CUDA(cudaMalloc(&s.mask, mbytes));
-    AO_CUDA(cudaMemset(s.mask, 0, mbytes));
-    for (int k = 0; k < s.K; ++k) {
+    const size_t mbytes = std::max<size_t>((size_t)s.ldX * Jloc, 256);
+    AO_CUDA(cudaMalloc(&s.mask_alloc, mbytes));
+    AO_CUDA(cudaMemset(s.mask_alloc, 0, mbytes));
+    s.mask = s.mask_alloc - (size_t)s.jlo * s.ldX;
+    for (int k = s.k0; k < s.k1; ++k) {
       if (src.miss_slices[k] == nullptr) throw CudaError(1, "Z.miss{p}{k} must be given for every PARAFAC2 slice");
       AO_CUDA(cudaMemcpy2D(s.mask + (size_t)s.joff[k] * s.ldX, (size_t)s.ldX, src.miss_slices[k], (size_t)s.I, (size_t)s.I,
                            (size_t)jk[k], cudaMemcpyHostToDevice));
@@ -1140,8 +1169,13 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   s.lay.Jmax = s.Jmax;
   s.lay.joff = s.joff_dev;
   s.lay.seg = s.seg_dev;
-  make_tensor3(s.view, s.X, s.I, s.Jtot, 1, s.ldX);
-  packed_factor_alloc(s.fW, s.Jtot, s.R);
+  s.lay.k0 = s.k0;
+  s.lay.k1 = s.k1;
+  s.lay.jlo = s.jlo;
+  s.lay.jhi = s.jhi;
+  make_tensor3(s.view, s.X_alloc, s.I, Jloc, 1, s.ldX);   // this rank's columns as an I x Jloc x 1 tensor
+  packed_factor_alloc(s.fW, Jloc, s.R);
+  AO_CUDA(cudaMalloc(&s.redbuf, sizeof(double) * ((size_t)s.R * s.R + 8)));
   packed_factor_alloc(s.fA, s.I, s.R);
   packed_factor_alloc(s.ones, 1, s.R);
   packed_factor_pack(s.ones, nullptr, 1, st_, nullptr);
@@ -1181,7 +1215,7 @@ void Engine::par2_update_T(Par2State& s) {
   phase_begin(1);
   packed_factor_pack(s.fA, a.fac.p, a.rows, st_, nullptr);
   ++launches_;
-  launches_ += mttkrp3(s.view, 1, s.fA, s.ones, s.R, 1.0, s.T.p, s.Jtot, mws_, st_, nullptr);
+  launches_ += mttkrp3(s.view, 1, s.fA, s.ones, s.R, 1.0, s.T.p + s.jlo, s.Jtot, mws_, st_, nullptr);   // local rows of T
   phase_end();
   s.T_version = a.version;
 }
@@ -1223,11 +1257,13 @@ void Engine::par2_precompute_A(ModeState& m, int n_rho_terms, bool do_chol) {
   ModeState &mb = mode(s.m2), &mc = mode(s.m3);
   phase_begin(1);
   launches_ += par2_scale_rows(s.lay, s.W.p, mb.fac.p, mc.fac.p, mc.rows, 1.0, nullptr, 0.0, st_);
-  packed_factor_pack(s.fW, s.W.p, s.Jtot, st_, nullptr);
+  packed_factor_pack(s.fW, s.W.p + s.jlo, s.Jtot, st_, nullptr);
   ++launches_;
   launches_ += mttkrp3(s.view, 0, s.fW, s.ones, s.R, o.weight, m.A.p, m.rows, mws_, st_, nullptr);
+  if (s.sharded) allreduce(m.A.p, (size_t)m.rows * m.R);    // sum over the ranks' slices (:159-163)
   phase_end();
   launches_ += par2_modeA_had(s.lay, s.G2, mc.fac.p, mc.rows, s.Csum, st_);
+  if (s.sharded) allreduce(s.Csum, (size_t)s.R * s.R);      // :164
   PrepArgs a{};
   a.nhad = 1;
   a.had[0] = s.Csum;
@@ -1286,7 +1322,13 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
                opt_.innerRelDualTol_constr};
   for (int it = 0; it < opt_.MaxInnerIters; ++it) {
     launches_ += par2_B_step1(s.lay, b, m.ctl, it > 0 ? 1 : 0, st_);  // cold start once per outer iteration
-    launches_ += par2_B_deltaB(s.lay, b, m.ctl, st_);
+    if (s.sharded) {   // DeltaB = sum_k rho_k P_k'(B_k + mu_k) / sum_k rho_k over ALL slices (:541-544)
+      launches_ += par2_B_deltaB(s.lay, b, m.ctl, st_, s.redbuf);
+      allreduce(s.redbuf, (size_t)s.R * s.R + 1);
+      launches_ += par2_B_deltaB_finish(s.lay, b, s.redbuf, m.ctl, st_);
+    } else {
+      launches_ += par2_B_deltaB(s.lay, b, m.ctl, st_);
+    }
     launches_ += par2_B_step2a(s.lay, b, m.ctl, st_);
     if (deferred) {
       launches_ += par2_B_form_prox_input(s.lay, b, m.V.p, m.ctl, st_);
@@ -1294,17 +1336,27 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
         launches_ += par2_tsmooth_prox(s.lay, m.V.p, s.rho2, m.con.p0, s.tdiag, m.Znew.p, m.ctl, st_);
       } else if (prox_supports_segments(m.con.kind)) {
         // :567-568: prox of every slice with its own rho_k - all K slices and R columns in ONE launch
-        launches_ += prox_apply_segments(m.con.kind, m.con.p0, m.con.p1, m.V.p, s.Jtot, m.Znew.p, s.Jtot, s.joff_dev, s.K,
-                                         s.Jmax, s.Jtot, s.R, s.rho2, prox_scratch_, st_, &m.ctl->done);
+        if (m.con.kind == AOADMM_CON_SIMPLEX_ROW)   // independent rows: this rank's stacked rows as one matrix
+          launches_ += apply_prox(m, m.V.p + s.jlo, s.Jtot, m.Znew.p + s.jlo, s.Jtot, s.jhi - s.jlo, s.R, s.rho2, &m.ctl->done);
+        else
+          launches_ += prox_apply_segments(m.con.kind, m.con.p0, m.con.p1, m.V.p, s.Jtot, m.Znew.p, s.Jtot, s.joff_dev + s.k0,
+                                           s.k1 - s.k0, s.Jmax, s.Jtot, s.R, s.rho2 + s.k0, prox_scratch_, st_, &m.ctl->done);
       } else {
         for (int k = 0; k < s.K; ++k)  // whole-matrix operators ('orthonormal', 'quadratic regularization'): per slice
           launches_ += apply_prox(m, m.V.p + s.joff[k], s.Jtot, m.Znew.p + s.joff[k], s.Jtot, s.joff[k + 1] - s.joff[k], s.R,
                                   s.rho2 + k, &m.ctl->done);
       }
     }
-    launches_ += par2_B_step2b(s.lay, b, tol, m.ctl, admm_counter_, st_);
+    if (s.sharded) {   // residual ratios averaged over ALL slices (:558-585): same exit test on every rank
+      launches_ += par2_B_step2b(s.lay, b, tol, m.ctl, admm_counter_, st_, s.redbuf);
+      allreduce(s.redbuf, 4);
+      launches_ += par2_B_finalize(s.lay, s.redbuf, tol, m.ctl, st_);
+    } else {
+      launches_ += par2_B_step2b(s.lay, b, tol, m.ctl, admm_counter_, st_);
+    }
   }
   par2_refresh_gram(s);
+  s.state_stale = s.sharded;
   ++m.version;
 }
 
@@ -1337,6 +1389,19 @@ void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, do
   sa.HHt = HHt;
   sa.ctl = m.ctl;
   launches_ += par2_sys_prep(s.lay, sa, st_);
+  if (s.sharded) {
+    // the third mode is updated on every rank (its K rows are few): gather the rows each rank prepared -
+    // right-hand sides, rho_k, inv(B_k) (or the directly solved rows of C, :236)
+    const size_t RR = (size_t)s.R * s.R;
+    launches_ += zero_rows_outside(ls_direct ? m.fac.p : m.A.p, s.K, s.R, s.k0, s.k1, st_);
+    allreduce(ls_direct ? m.fac.p : m.A.p, (size_t)s.K * s.R);
+    launches_ += zero_rows_outside(s.rho3, s.K, 1, s.k0, s.k1, st_);
+    allreduce(s.rho3, (size_t)s.K);
+    if (!ls_direct) {
+      launches_ += zero_rows_outside(s.Binv3, (long long)(s.K * RR), 1, (long long)(s.k0 * RR), (long long)(s.k1 * RR), st_);
+      allreduce(s.Binv3, (size_t)s.K * RR);
+    }
+  }
   launches_ += par2_rho_max(s.rho3, s.K, m.rho, st_);
 }
 
@@ -1469,18 +1534,19 @@ void Engine::em_step(bool impute) {
       ModeState &ma = mode(s.m1), &mb = mode(s.m2), &mc = mode(s.m3);
       // model of slice k: A diag(c_k) B_k' (:426)  =  A * W' on the stacked layout, W(j,:) = B(j,:) .* C(seg(j),:)
       launches_ += par2_scale_rows(s.lay, s.W.p, mb.fac.p, mc.fac.p, mc.rows, 1.0, nullptr, 0.0, st_);
-      a.X = s.X;
-      a.mask = s.mask;
+      a.X = s.X_alloc;              // this rank's slices (all of them on one GPU)
+      a.mask = s.mask_alloc;
       a.ldI = s.ldX;
       a.I = s.I;
-      a.J = s.Jtot;
+      a.J = s.jhi - s.jlo;
       a.K = 1;
       a.Fi = ma.fac.p;
       a.ldFi = ma.rows;
-      a.Fj = s.W.p;
+      a.Fj = s.W.p + s.jlo;
       a.ldFj = s.Jtot;
       a.Fk = nullptr;
       launches_ += em_pass(a, em_sums_ + 5 * p, st_);
+      if (s.sharded) allreduce(em_sums_ + 5 * p, 5);
       if (impute) s.T_version = 0;
     } else {
       if (o.mask == nullptr) continue;
@@ -1605,6 +1671,11 @@ void Engine::enqueue_objective(bool first) {
     if (first || s.explicit_residual)
       launches_ += par2_residual(s.lay, s.X, s.ldX, s.I, mode(s.m1).fac.p, mode(s.m1).rows, mb.fac.p, mode(s.m3).fac.p,
                                  mode(s.m3).rows, s.res_partials, admm_counter_, s.res, st_);
+    if (s.sharded) {
+      // per-slice terms of the other ranks' slices (zero here) and the partial residuals: one all-reduce gathers / sums
+      launches_ += zero_rows_outside(s.segn, (long long)s.K * 4, 1, (long long)s.k0 * 4, (long long)s.k1 * 4, st_);
+      allreduce(s.segn, (size_t)s.K * 4 + 1);
+    }
     AO_CUDA(cudaMemcpyAsync(s.segn_host, s.segn, sizeof(double) * (s.K * 4 + 1), cudaMemcpyDeviceToHost, st_));
   }
   if (has_missing_)
@@ -1783,6 +1854,26 @@ void Engine::set_state(int field, int index, int slice, const double* data, int6
     AO_CUDA(cudaMemcpyAsync(d->p, data, d->bytes(), cudaMemcpyHostToDevice, st_));
   AO_CUDA(cudaStreamSynchronize(st_));
   if (field == AOADMM_FIELD_FAC) ++modes_[index - 1].version;
+}
+
+// Sharded PARAFAC2 slices: during the solve every rank keeps only ITS rows of the stacked per-slice state (B_k, Z_k,
+// mu_Z_k, P_k, mu_DeltaB_k) up to date.  Before the state is read back the owners' rows are gathered (zero the foreign
+// rows, all-reduce).  Collective: every rank reads the state after a run (the bindings do).
+void Engine::par2_gather_state(Par2State& s) {
+  if (!s.sharded || !s.state_stale) return;
+  ModeState& mb = mode(s.m2);
+  for (DevMat* d : {&mb.fac, &mb.Z, &mb.muZ, &s.P, &s.muDB}) {
+    if (d->p == nullptr) continue;
+    launches_ += zero_rows_outside(d->p, d->rows, (int)d->cols, s.jlo, s.jhi, st_);
+    allreduce(d->p, (size_t)d->rows * d->cols);
+  }
+  AO_CUDA(cudaStreamSynchronize(st_));
+  s.state_stale = false;
+}
+
+void Engine::prepare_state_read() {
+  AO_CUDA(cudaSetDevice(device_));
+  for (auto& ps : par2_) par2_gather_state(ps);
 }
 
 void Engine::get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols) {
@@ -2207,7 +2298,7 @@ void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t r
   if (p < 0) throw CudaError(1, "nvecs: no object contains this mode");
   ObjectState& o = objects_[p];
   UnfoldSpec s;
-  bool reduce_over_ranks = false;
+  bool reduce_over_ranks = false, skip_local_gram = false;
   if (o.model == AOADMM_MODEL_CP) {
     if (slice != 0) throw CudaError(1, "nvecs: slice given for a CP mode");
     if (o.sharded && pos == o.order - 1) {
@@ -2245,14 +2336,19 @@ void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t r
     if (ps == nullptr) throw CudaError(1, "nvecs: PARAFAC2 state missing");
     if (pos == 0) {          // init_coupled_AOADMM_CMTF.m:55-60: slices side by side
       if (slice != 0) throw CudaError(1, "nvecs: slice given for PARAFAC2 mode A");
-      s.X = ps->X;
+      s.X = ps->X_alloc;     // this rank's slices; the partial Gram matrices are summed over the ranks
       s.layout = 0;
       s.n = ps->I;
       s.ld = ps->ldX;
-      s.ncols = ps->Jtot;
+      s.ncols = ps->jhi - ps->jlo;
+      reduce_over_ranks = ps->sharded;
     } else if (pos == 1) {   // :61-66: X_k' X_k
       if (slice < 1 || slice > ps->K) throw CudaError(1, "nvecs: PARAFAC2 slice out of range");
-      s.X = ps->X + ps->joff[slice - 1] * ps->ldX;
+      if (ps->sharded) {     // only the owner of the slice holds it: the others contribute a zero matrix to the sum
+        reduce_over_ranks = true;
+        skip_local_gram = (slice - 1 < ps->k0 || slice - 1 >= ps->k1);
+      }
+      s.X = skip_local_gram ? ps->X_alloc : ps->X + ps->joff[slice - 1] * ps->ldX;
       s.layout = 1;
       s.n = ps->joff[slice] - ps->joff[slice - 1];
       s.I = ps->I;
@@ -2271,7 +2367,8 @@ void Engine::nvecs_to_host(int mode_id, int slice, int r, double* out, int64_t r
     AO_CUDA(cudaMalloc(&Y, std::max<size_t>(nn * sizeof(double), 256)));
     AO_CUDA(cudaMalloc(&work, std::max<size_t>(unfold_gram_workspace(s) * sizeof(double), 256)));
     AO_CUDA(cudaMalloc(&U, std::max<size_t>((size_t)s.n * r * sizeof(double), 256)));
-    launches_ += unfold_gram(s, Y, work, st_);
+    if (skip_local_gram) AO_CUDA(cudaMemsetAsync(Y, 0, nn * sizeof(double), st_));
+    else launches_ += unfold_gram(s, Y, work, st_);
     if (reduce_over_ranks) allreduce(Y, nn);
     std::vector<double> theta(r);
     const EigInfo ei = top_eigvecs(Y, s.n, r, U, theta.data(), st_);

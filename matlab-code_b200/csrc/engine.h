@@ -111,8 +111,20 @@ struct Par2State {
   Par2Layout lay;
   long long* joff_dev = nullptr;
   int* seg_dev = nullptr;
-  double* X = nullptr;                   // I x Jtot (leading dimension ldX)
-  uint8_t* mask = nullptr;               // Z.miss{p}{k} side by side like X (nullptr: complete data)
+  double* X = nullptr;                   // I x Jtot (leading dimension ldX), addressed with GLOBAL column indices: with
+                                         // sharded slices only columns jlo..jhi-1 exist (X = X_alloc - jlo*ldX)
+  uint8_t* mask = nullptr;               // Z.miss{p}{k} side by side like X (nullptr: complete data), same addressing
+  double* X_alloc = nullptr;             // the allocations behind X / mask (this rank's columns)
+  uint8_t* mask_alloc = nullptr;
+  // multi-GPU: the K slices are sharded over the ranks in contiguous ranges k0..k1-1 (= stacked rows /
+  // columns jlo..jhi-1); per-slice work runs on the owner only, sums over k are all-reduced, the rows of the third mode
+  // are gathered.  sharded == false: every rank holds and updates all slices (one GPU, or objects the sharding does not
+  // cover: linear couplings on a PARAFAC2 mode, tPARAFAC2 / quadratic regularisation, fewer slices than ranks).
+  bool sharded = false;
+  int k0 = 0, k1 = 0;
+  int64_t jlo = 0, jhi = 0;
+  double* redbuf = nullptr;              // R*R + 8 doubles: local sums on their way through an all-reduce
+  bool state_stale = false;              // sharded: the non-local rows of the stacked state are not up to date
   Tensor3 view;                          // X as an I x Jtot x 1 tensor for the DMMA product kernels
   PackedFactor fW, fA, ones;
   DevMat W, T;                           // Jtot x R: scaled operand of the mode-A product; T = Xall' * A
@@ -164,6 +176,9 @@ class Engine {
   Engine& operator=(const Engine&) = delete;
   void set_state(int field, int index, int slice, const double* data, int64_t rows, int64_t cols);
   void get_state(int field, int index, int slice, double* data, int64_t rows, int64_t cols);
+  // collective over the ranks: makes the replicated copy of the state complete on every rank (gathers the rows of sharded
+  // PARAFAC2 slices from their owners).  Call on EVERY rank before get_state; a no-op when nothing is stale.
+  void prepare_state_read();
   void run(const aoadmm_options* opt, aoadmm_out* out);
   void generate_cp_data(int object, const double* const* factors, double noise, uint64_t seed);
   float time_mttkrp(int object, int pos, int reps);
@@ -230,6 +245,7 @@ class Engine {
   void par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, double* Bsys_out = nullptr,
                          const double* HHt = nullptr);
   void par2_refresh_gram(Par2State& s);
+  void par2_gather_state(Par2State& s);   // sharded slices: bring every rank's stacked rows up to date (get_state)
   DevMat* par2_field(int field, int index, int slice, int64_t* row_off, int64_t* nrows);
 
   ModeState& mode(int id) { return modes_[id - 1]; }

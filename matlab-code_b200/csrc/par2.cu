@@ -58,10 +58,10 @@ __device__ void cta_inverse_from_chol(const double* W, double* V, int R, double*
 __global__ void par2_scale_rows_kernel(Par2Layout L, double* __restrict__ out, const double* __restrict__ in,
                                        const double* __restrict__ C, long long ldc, double scale,
                                        const double* __restrict__ addend, double add_scale) {
-  const long long n = L.Jtot * L.R;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / L.Jtot, j = idx % L.Jtot;
+  const long long nloc = L.jhi - L.jlo, n = nloc * L.R;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / nloc, j = L.jlo + e % nloc;
+    const long long idx = j + r * L.Jtot;
     double v = scale * in[idx] * C[L.seg[j] + r * ldc];
     if (addend != nullptr) v += add_scale * addend[idx];
     out[idx] = v;
@@ -70,7 +70,7 @@ __global__ void par2_scale_rows_kernel(Par2Layout L, double* __restrict__ out, c
 
 __global__ void __launch_bounds__(kP2Threads) par2_batched_gram_kernel(Par2Layout L, const double* __restrict__ Bst,
                                                                         double* __restrict__ G2) {
-  const int k = blockIdx.x, R = L.R;
+  const int k = blockIdx.x + L.k0, R = L.R;
   const long long j0 = L.joff[k];
   const int Jk = (int)(L.joff[k + 1] - j0);
   double* out = G2 + (size_t)k * R * R;
@@ -97,14 +97,14 @@ __global__ void par2_modeA_had_kernel(Par2Layout L, const double* __restrict__ G
   const double* g = G2 + e;
   const size_t RR = (size_t)R * R;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int k = 0;
-  for (; k + 3 < L.K; k += 4) {
+  int k = L.k0;
+  for (; k + 3 < L.k1; k += 4) {
     a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
     a1 += (ca[k + 1] * g[(size_t)(k + 1) * RR]) * cb[k + 1];
     a2 += (ca[k + 2] * g[(size_t)(k + 2) * RR]) * cb[k + 2];
     a3 += (ca[k + 3] * g[(size_t)(k + 3) * RR]) * cb[k + 3];
   }
-  for (; k < L.K; ++k) a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
+  for (; k < L.k1; ++k) a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
   Csum[e] = (a0 + a1) + (a2 + a3);
 }
 
@@ -112,13 +112,13 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
   extern __shared__ double sm[];
   __shared__ double red[32];
   __shared__ double s_rho;
-  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
   double* W = sm;            // system matrix / Cholesky factor
   double* V = sm + RR;       // inverse of the factor
   double* rhs_s = sm + 2 * RR;  // R
   const long long j0 = L.joff[k];
   const int Jk = (int)(L.joff[k + 1] - j0);
-  if (k == 0 && tid == 0 && a.ctl != nullptr) {  // a new inner loop starts (err is sticky)
+  if (k == L.k0 && tid == 0 && a.ctl != nullptr) {  // a new inner loop starts (err is sticky)
     a.ctl->done = 0;
     a.ctl->iters = 0;
     a.ctl->res[0] = a.ctl->res[1] = a.ctl->res[2] = a.ctl->res[3] = 0.0;
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   if (ctl != nullptr && ctl->done != 0) return;
   extern __shared__ double sm[];
   __shared__ int s_rot;
-  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const long long j0 = L.joff[k], ld = L.Jtot;
   const int Jk = (int)(L.joff[k + 1] - j0);
@@ -501,30 +501,48 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   }
 }
 
-__global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl) {
+__global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl,
+                                                            double* __restrict__ sums_out) {
   if (ctl != nullptr && ctl->done != 0) return;
   __shared__ double red[32];
   __shared__ double s_sum;
-  const int R = L.R, RR = R * R, K = L.K;
+  const int R = L.R, RR = R * R, K0 = L.k0, K1 = L.k1;
   // sum_k rho_k (:542) in a fixed (strided + tree) order: deterministic, independent of the launch
   double s = 0.0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) s += a.rho_k[k];
+  for (int k = K0 + threadIdx.x; k < K1; k += blockDim.x) s += a.rho_k[k];
   s = block_sum(s, red);
   if (threadIdx.x == 0) s_sum = s;
   __syncthreads();
   const double tot = s_sum;
+  if (sums_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) sums_out[RR] = tot;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RR; e += gridDim.x * blockDim.x) {
     const double* c = a.contrib + e;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = 0;
-    for (; k + 3 < K; k += 4) {   // four independent load streams; fixed association => deterministic
+    int k = K0;
+    for (; k + 3 < K1; k += 4) {   // four independent load streams; fixed association => deterministic
       a0 += c[(size_t)k * RR];
       a1 += c[(size_t)(k + 1) * RR];
       a2 += c[(size_t)(k + 2) * RR];
       a3 += c[(size_t)(k + 3) * RR];
     }
-    for (; k < K; ++k) a0 += c[(size_t)k * RR];
-    a.DeltaB[e] = ((a0 + a1) + (a2 + a3)) / tot;      // :541-544
+    for (; k < K1; ++k) a0 += c[(size_t)k * RR];
+    if (sums_out != nullptr) sums_out[e] = (a0 + a1) + (a2 + a3);   // sharded slices: all-reduced, then divided
+    else a.DeltaB[e] = ((a0 + a1) + (a2 + a3)) / tot;               // :541-544
+  }
+}
+
+__global__ void par2_B_deltaB_finish_kernel(int RR, double* __restrict__ DeltaB, const double* __restrict__ sums,
+                                            const InnerCtl* ctl) {
+  if (ctl != nullptr && ctl->done != 0) return;
+  const double tot = sums[RR];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RR; e += gridDim.x * blockDim.x) DeltaB[e] = sums[e] / tot;
+}
+
+__global__ void zero_rows_outside_kernel(double* __restrict__ M, long long rows, int cols, long long lo, long long hi) {
+  const long long n = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e % rows;
+    if (r < lo || r >= hi) M[e] = 0.0;
   }
 }
 
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2a_kernel(Par2Layout L,
   if (ctl != nullptr && ctl->done != 0) return;
   extern __shared__ double sm[];
   __shared__ double red[32];
-  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
   const long long j0 = L.joff[k], ld = L.Jtot;
   const int Jk = (int)(L.joff[k + 1] - j0);
   double* dB = sm;
@@ -568,18 +586,43 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2a_kernel(Par2Layout L,
 
 __global__ void par2_B_form_prox_input_kernel(Par2Layout L, Par2BArgs a, double* __restrict__ V, const InnerCtl* ctl) {
   if (ctl != nullptr && ctl->done != 0) return;
-  const long long n = L.Jtot * L.R;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x)
+  const long long nloc = L.jhi - L.jlo, n = nloc * L.R;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long idx = L.jlo + e % nloc + (e / nloc) * L.Jtot;
     V[idx] = a.B[idx] + a.muZ[idx];
+  }
+}
+
+__device__ void par2_finalize_ctl(double rpk, double rdk, double rpc, double rdc, int K, const InnerTol& tol, InnerCtl* ctl) {
+  const double invK = 1.0 / (double)K;
+  rpk *= invK;
+  rdk *= invK;
+  rpc *= invK;
+  rdc *= invK;
+  ctl->res[0] = rpk;
+  ctl->res[1] = rdk;
+  ctl->res[2] = rpc;
+  ctl->res[3] = rdc;
+  ctl->iters += 1;
+  const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
+  if (!cont) ctl->done = 1;
+  // a NaN ratio (0/0 of a factor driven to zero) makes its comparison false and an Inf keeps the loop going, exactly
+  // as in the reference's while-test (:600, :633, :519); the run goes on and the event is only recorded
+  if (!isfinite(rpk + rdk + rpc + rdc)) ctl->warn = 4;
+}
+
+__global__ void par2_B_finalize_kernel(int K, const double* __restrict__ res_sums, InnerTol tol, InnerCtl* ctl) {
+  if (ctl->done != 0) return;
+  par2_finalize_ctl(res_sums[0], res_sums[1], res_sums[2], res_sums[3], K, tol, ctl);
 }
 
 __global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L, Par2BArgs a, InnerTol tol,
-                                                                    InnerCtl* ctl, unsigned* counter) {
+                                                                    InnerCtl* ctl, unsigned* counter,
+                                                                    double* __restrict__ res_out) {
   if (ctl->done != 0) return;
   __shared__ double red[32];
   __shared__ bool s_last;
-  const int k = blockIdx.x, R = L.R, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x + L.k0, R = L.R, tid = threadIdx.x, nt = blockDim.x;
   const long long j0 = L.joff[k], ld = L.Jtot;
   const int Jk = (int)(L.joff[k + 1] - j0);
   if (a.con_active) {
@@ -618,7 +661,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L,
   __threadfence();
   // residuals of :558-585, averaged over the slices in slice order (deterministic)
   double rpk = 0.0, rdk = 0.0, rpc = 0.0, rdc = 0.0;
-  for (int kk = tid; kk < L.K; kk += nt) {
+  for (int kk = L.k0 + tid; kk < L.k1; kk += nt) {
     const double* o = a.norms + (size_t)kk * 8;
     const double nB = sqrt(o[1]);
     rpk += sqrt(o[0]) / nB;
@@ -634,21 +677,14 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step2b_kernel(Par2Layout L,
   rpc = block_sum(rpc, red);
   rdc = block_sum(rdc, red);
   if (tid == 0) {
-    const double invK = 1.0 / (double)L.K;
-    rpk *= invK;
-    rdk *= invK;
-    rpc *= invK;
-    rdc *= invK;
-    ctl->res[0] = rpk;
-    ctl->res[1] = rdk;
-    ctl->res[2] = rpc;
-    ctl->res[3] = rdc;
-    ctl->iters += 1;
-    const bool cont = (rpk > tol.pr_coupl) || (rpc > tol.pr_constr) || (rdk > tol.du_coupl) || (rdc > tol.du_constr);
-    if (!cont) ctl->done = 1;
-    // a NaN ratio (0/0 of a factor driven to zero) makes its comparison false and an Inf keeps the loop going, exactly
-  // as in the reference's while-test (:600, :633, :519); the run goes on and the event is only recorded
-  if (!isfinite(rpk + rdk + rpc + rdc)) ctl->warn = 4;
+    if (res_out != nullptr) {   // sharded slices: local sums only, the exit test follows the all-reduce
+      res_out[0] = rpk;
+      res_out[1] = rdk;
+      res_out[2] = rpc;
+      res_out[3] = rdc;
+    } else {
+      par2_finalize_ctl(rpk, rdk, rpc, rdc, L.K, tol, ctl);
+    }
     *counter = 0u;
   }
 }
@@ -707,7 +743,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_seg_norms_kernel(Par2Layout L
                                                                      double* __restrict__ out) {
   extern __shared__ double sm[];
   __shared__ double red[32];
-  const int k = blockIdx.x, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
+  const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
   const long long j0 = L.joff[k], ld = L.Jtot;
   const int Jk = (int)(L.joff[k + 1] - j0);
   double* dB = sm;
@@ -786,11 +822,11 @@ __global__ void __launch_bounds__(256) par2_residual_kernel(Par2Layout L, const 
   __shared__ double red[32];
   __shared__ bool s_last;
   const int R = L.R;
-  const long long n = I * L.Jtot;
+  const long long n = I * (L.jhi - L.jlo);
   double acc = 0.0;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (long long)gridDim.x * blockDim.x) {
-    const long long i = idx % I, j = idx / I;
+    const long long i = idx % I, j = L.jlo + idx / I;
     const int k = L.seg[j];
     double m = 0.0;
     for (int r = 0; r < R; ++r) m = fma(A[i + r * ldA] * C[k + r * ldc], Bst[j + r * L.Jtot], m);
@@ -833,13 +869,13 @@ size_t par2_step1_smem_bytes(long long Jmax, int R) {
 
 int par2_scale_rows(const Par2Layout& L, double* out, const double* in, const double* C, long long ldc, double scale,
                     const double* addend, double add_scale, cudaStream_t st) {
-  par2_scale_rows_kernel<<<flat_grid(L.Jtot * L.R), 256, 0, st>>>(L, out, in, C, ldc, scale, addend, add_scale);
+  par2_scale_rows_kernel<<<flat_grid((L.jhi - L.jlo) * L.R), 256, 0, st>>>(L, out, in, C, ldc, scale, addend, add_scale);
   AO_CHECK_LAUNCH();
   return 1;
 }
 
 int par2_batched_gram(const Par2Layout& L, const double* Bst, double* G2, cudaStream_t st) {
-  par2_batched_gram_kernel<<<L.K, kP2Threads, 0, st>>>(L, Bst, G2);
+  par2_batched_gram_kernel<<<L.k1 - L.k0, kP2Threads, 0, st>>>(L, Bst, G2);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -853,7 +889,7 @@ int par2_modeA_had(const Par2Layout& L, const double* G2, const double* C, long 
 int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st) {
   const size_t smem = ((size_t)2 * L.R * L.R + L.R) * sizeof(double);
   opt_in_smem(par2_sys_prep_kernel, smem);
-  par2_sys_prep_kernel<<<L.K, 128, smem, st>>>(L, a);
+  par2_sys_prep_kernel<<<L.k1 - L.k0, 128, smem, st>>>(L, a);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -935,13 +971,32 @@ int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, i
   const size_t smem = par2_step1_smem_bytes(L.Jmax, L.R);
   const int use_gmem = (smem == (size_t)3 * L.R * L.R * sizeof(double)) ? 1 : 0;
   opt_in_smem(par2_B_step1_kernel, smem);
-  par2_B_step1_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl, use_gmem, warm);
+  par2_B_step1_kernel<<<L.k1 - L.k0, kP2Threads, smem, st>>>(L, a, ctl, use_gmem, warm);
   AO_CHECK_LAUNCH();
   return 1;
 }
 
-int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
-  par2_B_deltaB_kernel<<<(unsigned)ceil_div(L.R * L.R, 64), 256, 0, st>>>(L, a, ctl);
+int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st, double* sums_out) {
+  par2_B_deltaB_kernel<<<(unsigned)ceil_div(L.R * L.R, 64), 256, 0, st>>>(L, a, ctl, sums_out);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_deltaB_finish(const Par2Layout& L, const Par2BArgs& a, const double* sums, const InnerCtl* ctl, cudaStream_t st) {
+  par2_B_deltaB_finish_kernel<<<(unsigned)ceil_div(L.R * L.R, 256), 256, 0, st>>>(L.R * L.R, a.DeltaB, sums, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int par2_B_finalize(const Par2Layout& L, const double* res_sums, const InnerTol& tol, InnerCtl* ctl, cudaStream_t st) {
+  par2_B_finalize_kernel<<<1, 1, 0, st>>>(L.K, res_sums, tol, ctl);
+  AO_CHECK_LAUNCH();
+  return 1;
+}
+
+int zero_rows_outside(double* M, long long rows, int cols, long long lo, long long hi, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  zero_rows_outside_kernel<<<flat_grid(rows * cols), 256, 0, st>>>(M, rows, cols, lo, hi);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -949,20 +1004,20 @@ int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, 
 int par2_B_step2a(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st) {
   const size_t smem = (size_t)L.R * L.R * sizeof(double);
   opt_in_smem(par2_B_step2a_kernel, smem);
-  par2_B_step2a_kernel<<<L.K, kP2Threads, smem, st>>>(L, a, ctl);
+  par2_B_step2a_kernel<<<L.k1 - L.k0, kP2Threads, smem, st>>>(L, a, ctl);
   AO_CHECK_LAUNCH();
   return 1;
 }
 
 int par2_B_form_prox_input(const Par2Layout& L, const Par2BArgs& a, double* V, const InnerCtl* ctl, cudaStream_t st) {
-  par2_B_form_prox_input_kernel<<<flat_grid(L.Jtot * L.R), 256, 0, st>>>(L, a, V, ctl);
+  par2_B_form_prox_input_kernel<<<flat_grid((L.jhi - L.jlo) * L.R), 256, 0, st>>>(L, a, V, ctl);
   AO_CHECK_LAUNCH();
   return 1;
 }
 
 int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, InnerCtl* ctl, unsigned* counter,
-                  cudaStream_t st) {
-  par2_B_step2b_kernel<<<L.K, kP2Threads, 0, st>>>(L, a, tol, ctl, counter);
+                  cudaStream_t st, double* res_out) {
+  par2_B_step2b_kernel<<<L.k1 - L.k0, kP2Threads, 0, st>>>(L, a, tol, ctl, counter, res_out);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -980,7 +1035,7 @@ int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, cons
                    int reg_kind, double* out, cudaStream_t st) {
   const size_t smem = (size_t)L.R * L.R * sizeof(double);
   opt_in_smem(par2_seg_norms_kernel, smem);
-  par2_seg_norms_kernel<<<L.K, kP2Threads, smem, st>>>(L, Bst, Z, P, DeltaB, reg_kind, out);
+  par2_seg_norms_kernel<<<L.k1 - L.k0, kP2Threads, smem, st>>>(L, Bst, Z, P, DeltaB, reg_kind, out);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -988,7 +1043,7 @@ int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, cons
 int par2_residual(const Par2Layout& L, const double* X, long long ldX, long long I, const double* A, long long ldA,
                   const double* Bst, const double* C, long long ldc, double* partials, unsigned* counter, double* res,
                   cudaStream_t st) {
-  par2_residual_kernel<<<flat_grid(I * L.Jtot), 256, 0, st>>>(L, X, ldX, I, A, ldA, Bst, C, ldc, partials, counter, res);
+  par2_residual_kernel<<<flat_grid(I * (L.jhi - L.jlo)), 256, 0, st>>>(L, X, ldX, I, A, ldA, Bst, C, ldc, partials, counter, res);
   AO_CHECK_LAUNCH();
   return 1;
 }

@@ -23,6 +23,11 @@ struct Par2Layout {
   long long Jmax = 0;
   const long long* joff = nullptr;  // device, K+1 entries
   const int* seg = nullptr;         // device, Jtot entries: slice index of every stacked row
+  // Multi-GPU: the slices are sharded over the ranks in contiguous ranges.  Every per-slice array keeps its GLOBAL
+  // indexing (slice k at k, stacked row j at j), a rank only touches slices k0 .. k1-1 = stacked rows jlo .. jhi-1;
+  // one GPU: k0 = 0, k1 = K, jlo = 0, jhi = Jtot.
+  int k0 = 0, k1 = 0;
+  long long jlo = 0, jhi = 0;
 };
 
 // out(j,r) = scale * in(j,r) * C(seg(j), r)  [+ add_scale * addend(j,r)]     (all stacked Jtot x R, ld = Jtot)
@@ -114,14 +119,25 @@ struct Par2BArgs {
 // one inner iteration of ADMM_B_Parafac2 is  step1 -> deltaB -> step2a -> [prox of every slice] -> step2b
 // warm != 0: start the Jacobi iteration from the rotations of the previous call (a.Vprev)
 int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, int warm, cudaStream_t st);
-int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
+// sums_out == nullptr: DeltaB = sum_k contrib_k / sum_k rho_k over all slices (one GPU).  sums_out != nullptr (sharded
+// slices): only the local sums are written, sums_out[0..R*R-1] = sum_k contrib_k, sums_out[R*R] = sum_k rho_k; the caller
+// all-reduces them and finishes with par2_B_deltaB_finish.
+int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st, double* sums_out = nullptr);
+int par2_B_deltaB_finish(const Par2Layout& L, const Par2BArgs& a, const double* sums, const InnerCtl* ctl, cudaStream_t st);
 // coupling part: mu_k += B_k - P_k DeltaB ; per-slice norms 0..3
 int par2_B_step2a(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st);
 // V = B + muZ (input of a non element-wise prox)
 int par2_B_form_prox_input(const Par2Layout& L, const Par2BArgs& a, double* V, const InnerCtl* ctl, cudaStream_t st);
 // constraint part (element-wise prox inline, or Z taken from a.Znew) + residuals + exit test
+// res_out == nullptr: the last CTA averages the residual ratios over all slices and evaluates the exit test (one GPU).
+// res_out != nullptr (sharded slices): res_out[0..3] = the local sums of the four ratios; the caller all-reduces them
+// and par2_B_finalize evaluates the exit test (identically on every rank).
 int par2_B_step2b(const Par2Layout& L, const Par2BArgs& a, const InnerTol& tol, InnerCtl* ctl, unsigned* counter,
-                  cudaStream_t st);
+                  cudaStream_t st, double* res_out = nullptr);
+int par2_B_finalize(const Par2Layout& L, const double* res_sums, const InnerTol& tol, InnerCtl* ctl, cudaStream_t st);
+// zero every row outside [lo, hi) of a rows x cols column-major matrix (ld = rows): followed by an all-reduce this is the
+// all-gather of row ranges owned by different ranks
+int zero_rows_outside(double* M, long long rows, int cols, long long lo, long long hi, cudaStream_t st);
 
 // tPARAFAC2 prox over all slices at once (t_smoothness_prox.m:23-56): for every element (j,r) the K values solve the
 // tridiagonal system  diag(4l+rho_k; ends 2l+rho_k), off-diagonals -2l, right-hand side rho_k*V_k(j,r)  by the Thomas
@@ -135,6 +151,7 @@ int par2_seg_norms(const Par2Layout& L, const double* Bst, const double* Z, cons
                    int reg_kind, double* out, cudaStream_t st);
 
 // res = sum_k || X_k - A diag(c_k) B_k' ||_F^2  (explicit residual of :1254-1265); partials >= 148*8 doubles
+// (sharded slices: the sum over this rank's slices only; X is addressed with global column indices)
 int par2_residual(const Par2Layout& L, const double* X, long long ldX, long long I, const double* A, long long ldA,
                   const double* Bst, const double* C, long long ldc, double* partials, unsigned* counter, double* res,
                   cudaStream_t st);

@@ -44,18 +44,24 @@ for dims in [(64, 48, 40, 80, 8), (130, 90, 37, 100, 32), (40, 36, 30, 64, 64)]:
     same = bool(torch.equal(t, t0))
     if not same: print('rank', rank, 'state differs from rank 0'); ok = False
 # PARAFAC2 objects (replicated) next to a sharded CP tensor, and a linear coupling (type 4, type 1)
+nn = ('non-negativity',)
 extra = [('cp+par2', pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=3, noise=0.1)[:2]),
+         # PARAFAC2 slices sharded over the ranks (8 irregular slices, per-slice prox on B_k, ridge)
+         ('par2 sharded slices', pg.config_single_par2(seed=5, Jk=(10, 12, 9, 11, 13, 10, 8, 14), constrained=(1, 1, 1),
+                                                       ridge=[1e-3, 2e-3, 1e-3])[:2]),
+         ('par2 unimodal B_k', pg.config_single_par2(seed=8, Jk=(12, 9, 15, 11, 10, 13, 9, 12), constrained=(0, 1, 1),
+                                                     constraints=[None, ('unimodality', True), nn])[:2]),
          ('lin4', pg.config_linear_coupling(4, seed=4)[:2]), ('lin1', pg.config_linear_coupling(1, seed=1, second='tensor')[:2])]
 Zc, Gc, _ = pg.config_cp_matrix(40, 36, 30, 64, 5, seed=8)
 extra.append(('em', (pg.add_missing(Zc, 0.25, seed=3), Gc)))       # masks are sharded with the tensor
 for name, (Z, G) in extra:
-    opts = pg.default_options(MaxOuterIters=15)
+    opts = pg.default_options(MaxOuterIters=6 if 'B_k' in name or 'sharded slices' in name else 15)
     zn = pg.znorm_const(Z)
     Gd, od = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts, rank=rank, world_size=world, device=lr, unique_id=uid())
     if rank == 0:
         Go, oo = oracle_solve(Z, zn, G, options=opts)
         errs = []
-        for a, b in zip(Gd['fac'], Go['fac']):
+        for a, b in list(zip(Gd['fac'], Go['fac'])) + [(x, y) for x, y in zip(Gd.get('P') or [], Go.get('P') or []) if y is not None]:
             if isinstance(b, list):
                 errs += [np.linalg.norm(x - y) / np.linalg.norm(y) for x, y in zip(a, b)]
             else:

@@ -91,6 +91,22 @@ def test_single_process_multi_gpu_matches_oracle(ab, ngpu):
              ('4-way', pg.config_single_cp(sz=(12, 10, 9, 16), R=3, seed=9, noise=0.1, constraints=[('non-negativity',)] * 4)[:2], 15, ('fac',))]
     Zc, Gc, _ = pg.config_cp_matrix(40, 36, 30, 64, 5, seed=8)
     cases.append(('em', (pg.add_missing(Zc, 0.25, seed=3), Gc), 15, ('fac',)))
+    # PARAFAC2 slices sharded over the GPUs: irregular slices, per-slice prox on B_k (segmented launch),
+    # explicit-residual objective, mode A / mode C exactly coupled, EM on the slices; and the cases that stay replicated
+    nn = ('non-negativity',)
+    cases += [('par2 irregular, C last', pg.config_single_par2(seed=8, constrained=(1, 0, 1))[:2], 20, PAR2_KEYS),
+              ('par2 ALS on A and C', pg.config_single_par2(seed=8, constrained=(0, 0, 0))[:2], 20, PAR2_KEYS),
+              ('par2 nonneg B_k', pg.config_single_par2(seed=8, constrained=(1, 1, 1))[:2], 6, PAR2_KEYS),
+              ('par2 unimodal B_k', pg.config_single_par2(seed=8, constrained=(0, 1, 1),
+                                                          constraints=[None, ('unimodality', True), nn])[:2], 6, PAR2_KEYS),
+              ('par2 8 slices ridge', pg.config_single_par2(seed=5, Jk=(10, 12, 9, 11, 13, 10, 8, 14), constrained=(1, 1, 1),
+                                                            ridge=[1e-3, 2e-3, 1e-3])[:2], 6, PAR2_KEYS),
+              ('script2 matrix + par2 mode A', pg.config_script2(seed=2)[:2], 20, PAR2_KEYS),
+              ('script14 type 1 with par2 mode C (replicated)', pg.config_script14(seed=1)[:2], 12, PAR2_KEYS),
+              ('lin4 with par2 mode A (replicated)', pg.config_linear_coupling(4, seed=24, second='par2')[:2], 12, PAR2_KEYS),
+              ('tparafac2 (replicated)', pg.config_tparafac2(seed=2, eta=0.05)[:2], 12, PAR2_KEYS)]
+    Zp, Gp, _ = pg.config_cp_par2(I=24, J=20, K=18, Jk=16, Kp=10, R=3, seed=4, noise=0.05)
+    cases.append(('em cp+par2', (pg.add_missing(Zp, 0.2, seed=5), Gp), 15, PAR2_KEYS))
     for name, (Z, G), iters, keys in cases:
         zn = pg.znorm_const(Z)
         opts = pg.default_options(MaxOuterIters=iters)
@@ -98,9 +114,13 @@ def test_single_process_multi_gpu_matches_oracle(ab, ngpu):
         for n in worlds:
             Gd, od = ab.cmtf_fun_AOADMM(Z, zn, G, None, None, None, None, opts, n_gpus=n)
             assert od['OuterIterations'] == oo['OuterIterations'], (name, n)
-            assert np.max(np.abs(od['func_val_conv'] - oo['func_val_conv'])) < FIT_TOL, (name, n)
+            for key in ('func_val_conv', 'func_coupl_conv', 'func_constr_conv', 'func_PAR2_coupl'):
+                assert np.max(np.abs(od[key] - oo[key])) < FIT_TOL, (name, n, key)
             assert np.array_equal(od['innerIters'], oo['innerIters']), (name, n)
-            assert_state_close(Gd, Go, keys=keys + ('constraint_fac', 'constraint_dual_fac', 'coupling_fac', 'coupling_dual_fac'))
+            try:
+                assert_state_close(Gd, Go, keys=tuple(keys) + ('constraint_fac', 'constraint_dual_fac', 'coupling_fac', 'coupling_dual_fac'))
+            except AssertionError as e:
+                raise AssertionError('%s on %d GPUs: %s' % (name, n, e))
 
 
 def test_single_process_multi_gpu_medium_tensor_and_helpers(ab, ngpu):
@@ -139,6 +159,28 @@ def test_single_process_multi_gpu_medium_tensor_and_helpers(ab, ngpu):
     assert np.max(np.abs(od['func_val_conv'] - oo['func_val_conv'])) < FIT_TOL
     for m in range(5):
         assert rel(Gd['fac'][m], Go['fac'][m]) < FAC_TOL, m
+
+
+def test_single_process_multi_gpu_parafac2_nvecs_and_front_end(ab, ngpu):
+    """nvecs initialisation of a PARAFAC2 object whose slices are sharded: mode A = Gram of the slices side by side (partial
+    Gram matrices summed over the GPUs), B_k = X_k'X_k computed by the owner of slice k; then a solve from that init."""
+    if ngpu < 2:
+        pytest.skip('needs at least 2 GPUs')
+    Z, _, _ = pg.config_cp_par2(seed=4, noise=0.1)
+    R = 3
+    r1, r2 = np.random.RandomState(21), np.random.RandomState(21)
+    io = {'lambdas_init': [[1.0] * R] * 2, 'nvecs': 1, 'normalize': 1}
+    Gd = ab.init_coupled_AOADMM_CMTF(Z, dict(io, distr=[lambda a, b: r1.rand(a, b)] * len(Z['size'])), rng=r1, n_gpus=ngpu)
+    Go = pg.init_coupled_AOADMM_CMTF(Z, dict(io, distr=[pg.d_rand] * len(Z['size'])), r2)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+    opts = pg.default_options(MaxOuterIters=5, **ZERO_TOL)
+    Fd, od = ab.cmtf_fun_AOADMM(Z, pg.znorm_const(Z), Gd, None, None, None, None, opts, n_gpus=ngpu)
+    Fo, oo = oracle_solve(Z, pg.znorm_const(Z), Go, options=opts)
+    assert_state_close(Fd, Fo, tol=1e-7, keys=PAR2_KEYS)
+    assert abs(od['f_tensors'] - oo['f_tensors']) <= 1e-8 * abs(oo['f_tensors'])
+    # Znorm_const computed on device from sharded slices (NaN = ask the engine)
+    _, o2 = ab.cmtf_fun_AOADMM(Z, [float('nan')] * 2, Go, None, None, None, None, opts, n_gpus=ngpu)
+    assert np.max(np.abs(o2['func_val_conv'] - oo['func_val_conv'])) < 1e-10
 
 
 # ------------------------------------------------------------------------------------------ one process per GPU
