@@ -332,12 +332,22 @@ def main():
     solver.run(zero_tol_options(1))    # leaves the FP64 precision selected for time_mttkrp
     mode_ms = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
     tsum = sum(mode_ms)
-    # the opt-in reduced-precision MTTKRP (options.mttkrp_precision=1: TF32 operands, FP32 tile accumulation); reported
-    # beside the FP64 number, never as `value`
+    # the opt-in reduced-precision MTTKRPs (options.mttkrp_precision: 1 = TF32 and 2 = BF16 on tcgen05 / TMEM, 3 = TF32 on
+    # the mma.sync variant of the FP64 kernels); reported beside the FP64 number, never as `value`
     n32 = max(3, args.steps // 2)
-    tf32_ms, _, _, _, out32 = timed_run(solver, G, lambda it: dict(zero_tol_options(it), mttkrp_precision=1), n32)
-    tf32_ms /= n32
-    tf32_mode_ms = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
+    reduced = {}
+    for prec, key, what in ((1, 'tf32_opt_in', 'TF32 operands, tcgen05.mma.kind::tf32, FP32 accumulation in TMEM per slab, FP64 across slabs'),
+                            (2, 'bf16_opt_in', 'BF16 operands, tcgen05.mma.kind::f16, FP32 accumulation in TMEM per slab, FP64 across slabs'),
+                            (3, 'tf32_mma_sync', 'TF32 operands on HMMA.1688.F32.TF32 (mma.sync variant of the FP64 kernels), kept for comparison')):
+        ms_lo, _, _, _, out_lo = timed_run(solver, G, lambda it, p=prec: dict(zero_tol_options(it), mttkrp_precision=p), n32)
+        ms_lo /= n32
+        mode_lo = [solver.time_mttkrp(1, pos, 3) for pos in (1, 2, 3)]
+        reduced[key] = {'value': 1e3 / ms_lo, 'ms_per_step': ms_lo, 'mttkrp_ms_per_mode': mode_lo,
+                        'mttkrp_gbs': [bytes_mode / (t * 1e-3) / 1e9 for t in mode_lo],
+                        'hbm_frac': [bytes_mode / (t * 1e-3) / 1e9 / 6557.1 for t in mode_lo],
+                        'final_f_tensors': out_lo['f_tensors'],
+                        'note': 'options.mttkrp_precision=%d (opt-in, not the parity mode): %s; the tensor stays FP64 in HBM, so '
+                                'the pass is bound by the 8-byte read' % (prec, what)}
     achieved = 3 * flops_mode / (tsum * 1e-3) / 1e12
     hbm_peak = 6557.1
     try:
@@ -494,12 +504,7 @@ def main():
                             ('same step with options.dimtree=1 (engine knob, not the default of this line): the mode-2 pass '
                              'also emits T = X x_1 A and mode 3 is a pass over T - 2 tensor passes per step, results equal '
                              'to rounding (parity-tested)')},
-                'tf32_opt_in': {'value': 1e3 / tf32_ms, 'ms_per_step': tf32_ms, 'mttkrp_ms_per_mode': tf32_mode_ms,
-                                'mttkrp_gbs': [bytes_mode / (t * 1e-3) / 1e9 for t in tf32_mode_ms],
-                                'final_f_tensors': out32['f_tensors'],
-                                'note': 'options.mttkrp_precision=1 (opt-in, not the parity mode): TF32 operands on '
-                                        'HMMA.1688.F32.TF32, FP32 accumulation per tile, FP64 across tiles; the pass '
-                                        'becomes HBM-bound'},
+                'tf32_opt_in': reduced['tf32_opt_in'], 'bf16_opt_in': reduced['bf16_opt_in'], 'tf32_mma_sync': reduced['tf32_mma_sync'],
                 'c3_full': c3_full,
                 'final_f_tensors': out['f_tensors'],
                 'call_ms': call_ms,

@@ -152,9 +152,11 @@ typedef struct {
   int32_t has_increase_factor_rhoBk;
   double increase_factor_rhoBk;
   /* engine-only knobs (0 = default) */
-  int32_t mttkrp_precision;   /* 0: FP64 DMMA (default, the parity mode); 1: opt-in TF32 tensor cores for the tensor
-                                 MTTKRPs (inputs rounded to TF32, FP32 accumulate per tile, FP64 across tiles; ~1e-3
-                                 relative accuracy, the pass becomes HBM bound); everything else stays FP64 */
+  int32_t mttkrp_precision;   /* 0: FP64 DMMA (default, the parity mode).  Opt-in reduced precision for the MTTKRPs of
+                                 3-way tensors (the tensor stays FP64 in HBM, the pass becomes HBM bound; everything else
+                                 stays FP64): 1 = TF32 operands, 2 = BF16 operands, both on the 5th-generation tensor cores
+                                 (tcgen05.mma, FP32 accumulation in TMEM per slab, FP64 across slabs; operand rounding
+                                 2^-11 / 2^-8); 3 = TF32 on the mma.sync variant of the FP64 kernels (kept for comparison) */
   int32_t dimtree;            /* 0: three independent MTTKRP passes (reference flop/byte count) */
   int32_t fuse_inner;         /* 0 (default): run the whole inner ADMM loop of a group in one cooperative launch when
                                  possible; -1: one launch per inner iteration; results are identical */
@@ -264,7 +266,7 @@ int aoadmm_get_object_data(aoadmm_handle *h, int32_t object, double *out, int64_
  * chunk by chunk with NCCL point-to-point transfers. */
 int aoadmm_nvecs(aoadmm_handle *h, int32_t mode, int32_t slice, int32_t r, double *out, int64_t rows, double *info);
 /* MTTKRP of the resident CP object `object` in mode position `pos` (1-based) with the factors currently in the handle
- * (cmtf_fun_AOADMM.m:97), at `precision` (0 FP64, 1 TF32 opt-in: see aoadmm_options.mttkrp_precision), summed over
+ * (cmtf_fun_AOADMM.m:97), at `precision` (0 FP64, 1/2/3 reduced precision: see aoadmm_options.mttkrp_precision), summed over
  * ranks; out: rows(mode) x R host buffer. */
 int aoadmm_object_mttkrp(aoadmm_handle *h, int32_t object, int32_t pos, int32_t precision, double *out);
 /* one timed MTTKRP of object `object` in mode position `pos` (1-based position inside the object)

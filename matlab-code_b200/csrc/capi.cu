@@ -278,7 +278,7 @@ int aoadmm_nvecs(aoadmm_handle* h, int32_t mode, int32_t slice, int32_t r, doubl
 }
 
 int aoadmm_object_mttkrp(aoadmm_handle* h, int32_t object, int32_t pos, int32_t precision, double* out) {
-  if (!h || !out || precision < 0 || precision > 1) return AOADMM_ERR_INVALID_ARG;
+  if (!h || !out || precision < 0 || precision > 3) return AOADMM_ERR_INVALID_ARG;
   return guard(h, [&] {
     const int n = (int)h->eng.size();
     std::vector<std::vector<double>> tmp(n);

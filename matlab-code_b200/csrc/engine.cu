@@ -844,6 +844,7 @@ void Engine::release() {
   }
   par2_.clear();
   dfree(mws_.ws);
+  tc_operand_free(tc_op_);
   dfree(gram_ws_);
   dfree(admm_partials_);
   dfree(admm_sums_);
@@ -1026,18 +1027,54 @@ void Engine::compute_mttkrp(ObjectState& o, int pos, double scale, double* out, 
     emit = o.Tbuf;
     o.T_version = v1;
   }
+  const int prec = opt_.mttkrp_precision;
+  if ((prec == 1 || prec == 2) && o.order == 3) {
+    // opt-in reduced precision (3-way tensors): tcgen05 / TMEM kernels straight from the column-major factors
+    phase_begin(0);
+    if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
+    launches_ += tc_mttkrp(o, pos, scale, out + v.out_offset, ldout, emit, prec);
+    if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
+    phase_end();
+    return;
+  }
+  const int legacy = (prec == 3 && o.order >= 3) ? 1 : 0;   // 3: the TF32 mma.sync variant of the DMMA kernels
   pack_operand(v, 0);
   pack_operand(v, 1);
-  if (opt_.mttkrp_precision == 1) {
+  if (legacy) {
     packed_factor_to_tf32(v.f0, st_, nullptr);
     ++launches_;
   }
   phase_begin(o.order >= 3 ? 0 : 1);
   if (last_sharded) AO_CUDA(cudaMemsetAsync(out, 0, (size_t)ldout * R * sizeof(double), st_));
-  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit,
-                       opt_.mttkrp_precision);
+  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, scale, out + v.out_offset, ldout, mws_, st_, nullptr, emit, legacy);
   if (v.needs_allreduce) allreduce(out, (size_t)ldout * R);
   phase_end();
+}
+
+// reduced-precision MTTKRP of a 3-way object (mttkrp_tc.cu): the contracted factor F0 and the epilogue factor Fe per mode
+int Engine::tc_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout, double* emit, int prec) {
+  View3& v = o.views[pos];
+  const ModeState &mi = mode(o.modes[0]), &mj = mode(o.modes[1]), &mk = mode(o.modes[2]);
+  const int R = mi.R;
+  if (tc_op_.data == nullptr) {
+    int64_t mx = 1;
+    for (auto& ob : objects_)
+      if (ob.model == AOADMM_MODEL_CP && ob.order == 3) mx = std::max<int64_t>(mx, std::max(ob.dims[0], ob.dims[1]));
+    int Rmax = 1;
+    for (auto& m : modes_) Rmax = std::max(Rmax, m.R);
+    tc_operand_alloc(tc_op_, mx, Rmax);
+  }
+  const double* Fk = mk.fac.p + o.shard_offset;   // this rank's rows of the (possibly sharded) last mode
+  const double *F0, *Fe;
+  int64_t ld0, ldfe;
+  if (pos == 0) {
+    F0 = mj.fac.p, ld0 = mj.rows, Fe = Fk, ldfe = mk.rows;
+  } else if (pos == 1) {
+    F0 = mi.fac.p, ld0 = mi.rows, Fe = Fk, ldfe = mk.rows;
+  } else {
+    F0 = mi.fac.p, ld0 = mi.rows, Fe = mj.fac.p, ldfe = mj.rows;
+  }
+  return mttkrp3_tc(v.t, pos, tc_op_, F0, ld0, Fe, ldfe, R, scale, out, ldout, mws_, st_, nullptr, emit, prec);
 }
 
 void Engine::refresh_gram(ModeState& m) {
@@ -2047,6 +2084,8 @@ void Engine::run(const aoadmm_options* opt, aoadmm_out* out) {
   AO_CUDA(cudaSetDevice(device_));
   opt_ = *opt;
   if (opt_.MaxInnerIters < 1) throw CudaError(1, "MaxInnerIters must be >= 1");
+  if (opt_.mttkrp_precision < 0 || opt_.mttkrp_precision > 3)
+    throw CudaError(2, "mttkrp_precision: 0 (FP64), 1 (TF32, tcgen05), 2 (BF16, tcgen05) or 3 (TF32, mma.sync)");
   out->error_mode = 0;
   out->non_finite_mode = 0;
   if (run_ev_[0] == nullptr) {
@@ -2533,14 +2572,19 @@ float Engine::time_mttkrp(int object, int pos, int reps) {
   AO_CUDA(cudaEventCreate(&b));
   const int R = m.R;
   const int prec = opt_.mttkrp_precision;  // precision of the last aoadmm_run (0 before any run)
-  if (prec == 1) {
+  const bool tc = (prec == 1 || prec == 2) && o.order == 3;
+  const int legacy = (prec == 3 && o.order >= 3) ? 1 : 0;
+  if (legacy) {
     packed_factor_to_tf32(v.f0, st_, nullptr);
     ++launches_;
   }
-  launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, prec);  // warm-up
+  auto one = [&]() {
+    if (tc) return tc_mttkrp(o, pos - 1, 1.0, m.Alast.p + v.out_offset, m.rows, nullptr, prec);
+    return mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, legacy);
+  };
+  launches_ += one();  // warm-up
   AO_CUDA(cudaEventRecord(a, st_));
-  for (int r = 0; r < reps; ++r)
-    launches_ += mttkrp3(v.t, v.kernel_pos, v.f0, v.f1, R, 1.0, m.Alast.p + v.out_offset, m.rows, mws_, st_, nullptr, nullptr, prec);
+  for (int r = 0; r < reps; ++r) launches_ += one();
   AO_CUDA(cudaEventRecord(b, st_));
   AO_CUDA(cudaEventSynchronize(b));
   float ms = 0.f;

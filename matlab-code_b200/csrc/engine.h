@@ -212,6 +212,7 @@ class Engine {
   // sweep pieces
   void refresh_gram(ModeState& m);
   void compute_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout);
+  int tc_mttkrp(ObjectState& o, int pos, double scale, double* out, int64_t ldout, double* emit, int prec);
   void pack_operand(View3& v, int which);
   void precompute_mode(ModeState& m, int n_rho_terms, bool do_chol);
   void fill_prep(ModeState& m, PrepArgs& a, int n_rho_terms, bool do_chol);
@@ -270,6 +271,7 @@ class Engine {
   cudaStream_t st2_ = nullptr;   // side stream: system preparation overlaps the MTTKRP of the same mode
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   MttkrpWorkspace mws_;
+  TcOperand tc_op_;              // low-precision operand scratch of the opt-in tcgen05 MTTKRP (allocated on first use)
   double* gram_ws_ = nullptr;
   double* admm_partials_ = nullptr;
   double* admm_sums_ = nullptr;

@@ -771,7 +771,8 @@ void packed_factor_pack_kr(const PackedFactor& p, const double* Fa, int64_t rows
 size_t mttkrp_workspace_bytes(const Tensor3& t, int R) {
   const int NC = mttkrp_chunk_cols(R);
   const int nchunk = (int)ceil_div(R, NC);
-  const long long Rp = (long long)nchunk * NC;
+  // (the reduced-precision kernels of mttkrp_tc.cu always work on 64-column chunks)
+  const long long Rp = std::max<long long>((long long)nchunk * NC, ceil_div(R, 64) * 64);
   const long long maxdim = std::max(t.I, std::max(t.J, t.K)) + 2;
   // splits never exceed 4 waves of CTAs; epilogue-1 partials are one per j tile
   const long long parts = std::max<long long>(4LL * sm_count(), ceil_div(t.J, 128));
@@ -815,7 +816,7 @@ int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFacto
     if (precision == 1) AO_DISPATCH_P(NT, WNN, 1); \
     AO_DISPATCH_P(NT, WNN, 0);               \
   } while (0)
-  if (precision != 0 && precision != 1) throw CudaError(2, "mttkrp_precision: 0 (FP64) or 1 (TF32 opt-in)");
+  if (precision != 0 && precision != 1) throw CudaError(2, "mttkrp3: precision 0 (FP64 DMMA) or 1 (TF32 on mma.sync)");
   switch (NC) {
     case 8: AO_DISPATCH(1, 1);
     case 16: AO_DISPATCH(2, 1);

@@ -67,6 +67,25 @@ int mttkrp3(const Tensor3& t, int pos, const PackedFactor& f0, const PackedFacto
             double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip,
             double* Tbuf = nullptr, int precision = 0);  // precision 1: opt-in TF32 tensor-core path (FP32 accumulate)
 size_t mttkrp_T_bytes(const Tensor3& t, int R);
+
+// ---- opt-in reduced-precision path on tcgen05 / TMEM (mttkrp_tc.cu) --------------------------------------------------
+// Scratch for the low-precision copy of the contracted factor (packed per call in the swizzled UMMA operand layout).
+struct TcOperand {
+  uint8_t* data = nullptr;
+  size_t bytes = 0;
+};
+size_t tc_operand_bytes(int64_t rows, int R);
+void tc_operand_alloc(TcOperand& op, int64_t max_rows, int R);
+void tc_operand_free(TcOperand& op);
+// Same contract as mttkrp3 for a 3-way view, from the plain column-major FP64 factors:
+//   pos 0: out(i,:) = sum_k Fe(k,:) .* sum_j X(i,j,k) F0(j,:)      F0 = Fj (J x R), Fe = Fk (K x R)
+//   pos 1: out(j,:) = sum_k Fe(k,:) .* sum_i X(i,j,k) F0(i,:)      F0 = Fi (I x R), Fe = Fk (K x R); Tbuf != nullptr also
+//          emits T(j,k,:) = sum_i X(i,j,k) F0(i,:) for mttkrp3_from_T
+//   pos 2: out(k,:) = sum_j Fe(j,:) .* sum_i X(i,j,k) F0(i,:)      F0 = Fi (I x R), Fe = Fj (J x R)
+// precision 1: TF32 operands, 2: BF16 operands; FP32 accumulation in TMEM per slab, FP64 across slabs.
+int mttkrp3_tc(const Tensor3& t, int pos, const TcOperand& op, const double* F0, int64_t ld0, const double* Fe, int64_t ldfe,
+               int R, double scale, double* out, int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip,
+               double* Tbuf, int precision);
 // out(k,r) = scale * sum_j T(j,k,r) * Fj(j,r)   (Fj: J x R column-major, leading dimension ldf)
 int mttkrp3_from_T(const Tensor3& t, const double* Tbuf, int R, const double* Fj, int64_t ldf, double scale,
                    double* out, int64_t ldout, cudaStream_t st, const int* skip);
