@@ -140,6 +140,16 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) fa[mi][nt][0] = fa[mi][nt][1] = 0.f;
 
+  // PREC 0: the Khatri-Rao scale Fk(k,:) is NOT multiplied into the B fragments (those DMULs would share the FP64 pipe
+  // with the DMMAs, 32 per stage and warp): the products of one slab k are accumulated unscaled in accp and folded into
+  // acc with one FMA per accumulator when the stage sequence moves on to the next k (every njt stages).
+  double accp[4][NT][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) accp[a][b][0] = accp[a][b][1] = 0.0;
+  int jtc = (int)(q0 % njt);   // j-tile index of the current stage inside its slab
+
   for (long long q = q0; q < q1; ++q) {
     const long long ql = q - q0;
     const int s = (int)(ql % kStages);
@@ -148,7 +158,7 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
     const uint32_t xs = sX + s * kXBytes, fs = sF + s * C::FBYTES + boff, cs = sC + s * C::CBYTES;
     double ck[NT];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) ck[nt] = lds_f64(cs + (wn * C::WN + 8 * nt + m) * 8);
+    for (int nt = 0; nt < NT; ++nt) ck[nt] = (PREC == 0) ? 0.0 : lds_f64(cs + (wn * C::WN + 8 * nt + m) * 8);
     if (PREC == 0) {
 #pragma unroll
       for (int tt = 0; tt < TCOUNT; ++tt) {
@@ -159,11 +169,27 @@ mttkrp_lead_kernel(const __grid_constant__ CUtensorMap tmap, const double* __res
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(xs + abase[mi] + rowoff + (axor[mi] ^ flip));
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8)) * ck[nt];
+        for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(fs + (uint32_t)((t * 4 * C::LDC + 8 * nt) * 8));
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mi][nt][0], acc[mi][nt][1], a[mi], b[nt]);
+          for (int nt = 0; nt < NT; ++nt) dmma884(accp[mi][nt][0], accp[mi][nt][1], a[mi], b[nt]);
+      }
+      // last stage of this slab (or of this CTA's range): fold the slab into acc with its scale Fk(k, :), read from the
+      // stage's own copy of the row while the slot is still ours
+      if (++jtc == njt || q + 1 == q1) {
+        jtc = (jtc == njt) ? 0 : jtc;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const double c0 = lds_f64(cs + (wn * C::WN + 8 * nt + 2 * kk) * 8);
+          const double c1 = lds_f64(cs + (wn * C::WN + 8 * nt + 2 * kk + 1) * 8);
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            acc[mi][nt][0] = fma(accp[mi][nt][0], c0, acc[mi][nt][0]);
+            acc[mi][nt][1] = fma(accp[mi][nt][1], c1, acc[mi][nt][1]);
+            accp[mi][nt][0] = accp[mi][nt][1] = 0.0;
+          }
+        }
       }
     } else {
       // operand 0 arrives in the TF32 operand format (packed_factor_to_tf32: the high word of every 8-byte slot is the

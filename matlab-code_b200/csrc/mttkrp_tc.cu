@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace aoadmm {
 
@@ -114,6 +115,26 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
+// A operand taken from tensor memory (128 lanes x K columns of 32 bits), B from shared memory
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one row of 32 consecutive 32-bit columns per lane (lanes 32*(warp%4) .. +31 of tensor memory)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -140,7 +161,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 //   CONV 1: rows = i, reduction over j (nst = ceil(J/32) stages per slab), tensor map box 16(i) x 32(j)
 //   EPI 0 : ws[(split*Rp + r)*ldo + row] = sum_k T_k(row,r) Fe(k,r);  Tbuf != nullptr additionally stores T_k (dimension tree)
 //   EPI 1 : ws[(tile *Rp + r)*ldo + k]   = sum_rows T_k(row,r) Fe(row,r)
-template <int PREC, int CONV, int EPI>
+//   ATMEM : (TF32) the converters write the A operand into TENSOR MEMORY (tcgen05.st, 3 x 32 columns behind the two
+//           accumulator buffers) and the MMA takes A from there: the 16 KB operand tile then neither goes into nor comes
+//           out of shared memory, whose bandwidth (TMA writes + converter reads + operand reads) is what bounds the TF32
+//           variant with both operands in shared memory
+template <int PREC, int CONV, int EPI, int ATMEM>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ Bpack, int nblk,
                  const double* __restrict__ Fe, long long ldfe, double* __restrict__ ws, int rows_total, int K, int nst,
@@ -157,6 +182,9 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
                  acc_empty = acc_full + 2 * 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + S::OFF_TMEM);
 
+  // TMEM columns: [0,128) two accumulator buffers; ATMEM: [128,224) three A-operand buffers of 32 columns
+  constexpr int kTmemCols = ATMEM ? 256 : 128;
+  constexpr int kACol0 = 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y, chunk = blockIdx.z;
   const int k0 = (int)((long long)K * split / nsplit), k1 = (int)((long long)K * (split + 1) / nsplit);
@@ -183,7 +211,7 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
     mbar_fence_init();
   }
   if (warp == 0) {   // TMEM: two 64-column FP32 accumulator buffers (allocation granularity: power of two >= 32 columns)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::OFF_TMEM), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + S::OFF_TMEM), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -213,8 +241,8 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
       }
     }
   } else if (warp <= 4) {
-    // ===== converters: thread t owns GEMM row t of the tile =====
-    const int t = threadIdx.x - 32;
+    // ===== converters: thread owns GEMM row t of the tile (ATMEM: the row inside the warp's own TMEM lane quarter) =====
+    const int t = ATMEM ? ((warp & 3) * 32 + lane) : (threadIdx.x - 32);
     for (long long n = 0; n < total; ++n) {
       const int sx = (int)(n % kNX), ca = (int)(n % kNA);
       mbar_wait(x_full + sx * 8, (uint32_t)((n / kNX) & 1));
@@ -224,7 +252,17 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         // row j = t of the FP64 tile: 32 consecutive i in two boxes; pair q of box b at ((q ^ (j&7)) << 4)
         const uint32_t rbase = xs + (uint32_t)(t * 128);
         const int sw = t & 7;
-        if (PREC == 1) {
+        if (PREC == 1 && ATMEM) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {         // pair c = reduction indices 2c, 2c+1
+            double x0, x1;
+            lds128(rbase + (c >> 3) * 16384 + (((c & 7) ^ sw) << 4), x0, x1);
+            v[2 * c] = to_tf32(x0);
+            v[2 * c + 1] = to_tf32(x1);
+          }
+          tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kACol0 + ca * 32), v);
+        } else if (PREC == 1) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {          // output chunk c = reduction indices 4c .. 4c+3
             const int b = c >> 2, q = 2 * (c & 3);
@@ -249,7 +287,12 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         const int il = t & 15;
         const uint32_t cbase = xs + (uint32_t)((t >> 4) * 4096 + (il & 1) * 8);
         const int half = il >> 1;
-        if (PREC == 1) {
+        if (PREC == 1 && ATMEM) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = to_tf32(lds_f64(cbase + (uint32_t)(j * 128 + ((half ^ (j & 7)) << 4))));
+          tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kACol0 + ca * 32), v);
+        } else if (PREC == 1) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             double x[4];
@@ -274,7 +317,8 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
           }
         }
       }
-      fence_async_smem();     // the tensor core reads shared memory through the async proxy
+      if (ATMEM) tc_fence_before();   // the tcgen05.st above has completed (wait::st); order it before the hand-over
+      else fence_async_smem();        // the tensor core reads shared memory through the async proxy
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(a_full + ca * 8);
@@ -296,8 +340,13 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
         tc_fence_after();
         const uint64_t adesc = make_desc<PREC>(sA + ca * 16384), bdesc = make_desc<PREC>(sB + sb * 8192);
 #pragma unroll
-        for (int kk = 0; kk < NMMA; ++kk)   // advancing 32 bytes along K inside the swizzle atom = +2 in the address field
-          umma<PREC>(tmem_base + (uint32_t)(buf * kNCols), adesc + 2 * kk, bdesc + 2 * kk, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < NMMA; ++kk) {  // advancing 32 bytes along K inside the swizzle atom = +2 in the address field
+          if (ATMEM)                         // (A in tensor memory: 8 TF32 columns per instruction)
+            umma_ts_tf32(tmem_base + (uint32_t)(buf * kNCols), tmem_base + (uint32_t)(kACol0 + ca * 32 + kk * 8), bdesc + 2 * kk,
+                         idesc, (st > 0 || kk > 0) ? 1u : 0u);
+          else
+            umma<PREC>(tmem_base + (uint32_t)(buf * kNCols), adesc + 2 * kk, bdesc + 2 * kk, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+        }
         umma_commit(a_empty + ca * 8);
         umma_commit(b_empty + sb * 8);
         if (st == nst - 1) umma_commit(acc_full + buf * 8);
@@ -369,7 +418,7 @@ mttkrp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __rest
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
@@ -433,7 +482,7 @@ int tc_choose_splits(long long tiles, long long max_splits, long long cap) {
   return best;
 }
 
-template <int PREC, int CONV, int EPI>
+template <int PREC, int CONV, int EPI, int ATMEM>
 int launch_tc(const Tensor3& t, const uint8_t* Bpack, int nblk, int nchunk, const double* Fe, int64_t ldfe, int R,
               double scale, double* out, int64_t ldout, const MttkrpWorkspace& w, double* Tbuf, cudaStream_t st,
               const int* skip) {
@@ -448,7 +497,7 @@ int launch_tc(const Tensor3& t, const uint8_t* Bpack, int nblk, int nchunk, cons
   if (cap < 1 || (EPI == 1 && cap < ntiles)) throw CudaError(1, "mttkrp workspace too small (reduced-precision path)");
   const int nsplit = tc_choose_splits((long long)ntiles * nchunk, t.K, EPI == 0 ? cap : (long long)t.K);
   const int nparts = (EPI == 0) ? nsplit : ntiles;
-  auto kern = mttkrp_tc_kernel<PREC, CONV, EPI>;
+  auto kern = mttkrp_tc_kernel<PREC, CONV, EPI, ATMEM>;
   ensure_dynamic_smem(reinterpret_cast<const void*>(kern), S::BYTES);
   int RpT = 0;
   long long ldt = 0;
@@ -481,9 +530,19 @@ int dispatch_tc(const Tensor3& t, int pos, const TcOperand& op, const double* F0
       op.data, nblk, nchunk, F0, red_rows, ld0, R, skip);
   AO_CHECK_LAUNCH();
   int n = 1;
-  if (pos == 0) n += launch_tc<PREC, 1, 0>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
-  else if (pos == 1) n += launch_tc<PREC, 0, 0>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, Tbuf, st, skip);
-  else n += launch_tc<PREC, 0, 1>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
+  // TF32: A operand through tensor memory (AOADMM_TC_A_SMEM=1 keeps it in shared memory, for comparison); BF16: the
+  // operand tile is half the size and the pass is already HBM bound with both operands in shared memory
+  static const bool a_smem = (std::getenv("AOADMM_TC_A_SMEM") != nullptr);
+  constexpr int AT = (PREC == 1) ? 1 : 0;
+  if (PREC == 1 && a_smem) {
+    if (pos == 0) n += launch_tc<PREC, 1, 0, 0>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
+    else if (pos == 1) n += launch_tc<PREC, 0, 0, 0>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, Tbuf, st, skip);
+    else n += launch_tc<PREC, 0, 1, 0>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
+    return n;
+  }
+  if (pos == 0) n += launch_tc<PREC, 1, 0, AT>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
+  else if (pos == 1) n += launch_tc<PREC, 0, 0, AT>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, Tbuf, st, skip);
+  else n += launch_tc<PREC, 0, 1, AT>(t, op.data, nblk, nchunk, Fe, ldfe, R, scale, out, ldout, w, nullptr, st, skip);
   return n;
 }
 
