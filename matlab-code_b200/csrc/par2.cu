@@ -37,14 +37,21 @@ __device__ bool cta_cholesky(double* W, int R) {
 // V (row i, column c at V[i*R + c]) = inv(L) for the lower factor held in W; then out = inv(L)' * inv(L)
 __device__ void cta_inverse_from_chol(const double* W, double* V, int R, double* out) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int c = tid; c < R; c += nt) {
-    for (int i = 0; i < R; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) s = fma(-W[k * R + i], V[k * R + c], s);
-      V[i * R + c] = s / W[i * R + i];
-    }
-  }
+  // forward substitution on all columns at once (see prep_system_kernel): same FMAs in the same order per entry as a
+  // column-by-column substitution, spread over the whole CTA
+  for (int e = tid; e < R * R; e += nt) V[e] = (e / R == e % R) ? 1.0 : 0.0;
   __syncthreads();
+  for (int j = 0; j < R; ++j) {
+    const double d = W[j * R + j];
+    for (int c = tid; c <= j; c += nt) V[j * R + c] = V[j * R + c] / d;
+    __syncthreads();
+    const int ncol = j + 1, nent = (R - j - 1) * ncol;
+    for (int e = tid; e < nent; e += nt) {
+      const int i = j + 1 + e / ncol, c = e % ncol;
+      V[i * R + c] = fma(-W[j * R + i], V[j * R + c], V[i * R + c]);
+    }
+    __syncthreads();
+  }
   for (int e = tid; e < R * R; e += nt) {
     const int ca = e / R, cb = e % R;
     const int lo = ca > cb ? ca : cb;

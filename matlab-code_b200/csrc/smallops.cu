@@ -142,19 +142,25 @@ __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const i
       if (ri == ci) a.invdiag[ri] = 1.0 / v;
     }
     if (a.Binv != nullptr && s_err == 0) {
-      // inv(L): thread c owns column c (forward substitution of L x = e_c); V(i,c) kept in V[i + c*R]
+      // inv(L) by forward substitution on all columns at once: V = I; for every pivot j, row j is divided by L(j,j) and
+      // L(i,j) * row j is subtracted from the rows below.  Each entry sees the same FMAs in the same order as a
+      // column-by-column substitution (bitwise the same result), but a step updates (R-j-1) x (j+1) entries across the
+      // whole CTA instead of R threads walking R^2/2 dependent FMAs.  V(i,c) lives at V[i*R + c] (zeros above the diagonal).
       double* V = use_smem ? (S + RR) : a.Binv;
       __syncthreads();
-      // V(i,c) lives at V[i*R + c]: the loops are uniform across threads (rows above the diagonal come out as
-      // exact zeros), so L is read as a broadcast and V without bank conflicts.
-      for (int c = tid; c < R; c += nt) {
-        for (int i2 = 0; i2 < R; ++i2) {
-          double sacc = (i2 == c) ? 1.0 : 0.0;
-          for (int k = 0; k < i2; ++k) sacc = fma(-W[k * R + i2], V[k * R + c], sacc);
-          V[i2 * R + c] = sacc / W[i2 * R + i2];
-        }
-      }
+      for (int e = tid; e < RR; e += nt) V[e] = (e / R == e % R) ? 1.0 : 0.0;
       __syncthreads();
+      for (int j = 0; j < R; ++j) {
+        const double d = W[j * R + j];
+        for (int c = tid; c <= j; c += nt) V[j * R + c] = V[j * R + c] / d;
+        __syncthreads();
+        const int ncol = j + 1, nent = (R - j - 1) * ncol;
+        for (int e = tid; e < nent; e += nt) {
+          const int i2 = j + 1 + e / ncol, c = e % ncol;
+          V[i2 * R + c] = fma(-W[j * R + i2], V[j * R + c], V[i2 * R + c]);
+        }
+        __syncthreads();
+      }
       // inv(B) = inv(L)' * inv(L)
       if (use_smem) {
         for (int e = tid; e < RR; e += nt) {
