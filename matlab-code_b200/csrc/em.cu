@@ -24,16 +24,25 @@ constexpr int kTile = 64;
 constexpr int kRC = 32;          // rank chunk staged per pass
 constexpr int kPitch = kTile + 4;  // smem row pitch: the 4 x 8 fragment footprint of a DMMA operand hits 32 distinct banks
 
+constexpr int kMP = kTile + 2;     // pitch of the model tile: C-fragment stores and 16-byte row reads are conflict-free
+
 // The model of slab k is a rank-R GEMM, M_k = (Fi diag(Fk(k,:))) * Fj': it runs on the FP64 tensor cores like the
 // MTTKRP (mma.m8n8k4, SASS DMMA.8x8x4).  CTA tile 64 (i) x 64 (j), 8 warps as 4 (i) x 2 (j), warp tile 16 x 32 =
 // 2 x 4 accumulator tiles.  The unscaled factor tiles are staged in shared memory once per CTA (once per rank chunk
 // when R > 32) and reused for every k of the CTA's range; the k-dependent scale Fk(k,r) is applied to the A fragment
-// in registers (2 DMUL per 8 DMMA).  Epilogue per k: the 16 model values of a lane are compared with the stored
-// element and the mask byte, missing entries are overwritten, five sums are accumulated.
+// in registers (2 DMUL per 8 DMMA).
+// Epilogue per k: the accumulators go through shared memory so that the comparison with the stored data runs in the
+// data's own layout - warp w owns 8 columns j, lane l the rows 2l, 2l+1: one 16-byte load of X and one 2-byte load of
+// the mask per column and lane (a warp reads one whole 512-byte column segment), requested BEFORE the tensor-core loop
+// so that the DRAM latency hides behind it.  (The first DMMA version compared in the accumulator layout: 32 scalar
+// loads with their own 64-bit addresses per lane and k made it issue bound - 1080 instructions per warp and k, FP64
+// pipe 7 % busy, profiles/r02_ncu_em_summary.md.)
 __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
-  __shared__ double As[kRC][kPitch];
-  __shared__ double Bs[kRC][kPitch];
-  __shared__ double cs[kRC];
+  extern __shared__ __align__(16) double em_smem[];   // 68.4 KB: beyond the static limit, two CTAs per SM
+  double* Ms = em_smem;                                                     // kTile x kMP model tile
+  double (*As)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTile * kMP);
+  double (*Bs)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTile * kMP + kRC * kPitch);
+  double* cs = em_smem + kTile * kMP + 2 * kRC * kPitch;
   __shared__ double red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wi = warp & 3, wj = warp >> 2;
@@ -41,6 +50,9 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
   const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTile;
   const int k0 = blockIdx.z * kper, k1 = min(a.K, k0 + kper);
   const int nchunk = (a.R + kRC - 1) / kRC;
+  // epilogue ownership: rows ie, ie+1 of the columns j0 + 8*warp + c, c = 0..7
+  const long long ie = i0 + 2 * lane;
+  const int nrow = (ie + 1 < a.I) ? 2 : ((ie < a.I) ? 1 : 0);
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int k = k0; k < k1; ++k) {
     double acc[2][4][2];
@@ -48,27 +60,31 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    // The stored elements and mask bytes of this lane's 16 outputs are requested BEFORE the tensor-core loop, so their
-    // DRAM latency hides behind it: accumulator (mt, nt, e) is element i = i0 + 16 wi + 8 mt + p, j = j0 + 32 wj + 8 nt + 2 q + e.
-    double xv[2][4][2];
-    uint8_t mk[2][4][2];
+    double x0[8], x1[8];
+    unsigned mk[8];   // bit 0 / bit 8: element 0 / 1 observed; 0xFFFF0000: column outside the object
+    {
+      const long long colbase = ie + a.ldI * (j0 + 8 * warp + (long long)a.J * k);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const long long i = i0 + 16 * wi + 8 * mt + p;
-          const bool in = (i < a.I) && (j < a.J);
-          const long long idx = in ? i + a.ldI * (j + (long long)a.J * k) : 0;
-          xv[mt][nt][e] = in ? a.X[idx] : 0.0;
-          mk[mt][nt][e] = in ? (uint8_t)(a.mask[idx] != 0) : (uint8_t)2;   // any non-zero byte = observed; 2 = outside
+      for (int c = 0; c < 8; ++c) {
+        const long long idx = colbase + a.ldI * c;
+        const bool col_ok = (j0 + 8 * warp + c < a.J);
+        x0[c] = x1[c] = 0.0;
+        mk[c] = 0xFFFF0000u;
+        if (col_ok && nrow == 2) {   // idx is even (ldI and ie are): 16-byte / 2-byte aligned vector loads
+          const double2 xv = *reinterpret_cast<const double2*>(a.X + idx);
+          const unsigned short mv = *reinterpret_cast<const unsigned short*>(a.mask + idx);
+          x0[c] = xv.x;
+          x1[c] = xv.y;
+          mk[c] = mv;
+        } else if (col_ok && nrow == 1) {
+          x0[c] = a.X[idx];
+          mk[c] = 0x0000FF00u | a.mask[idx];   // second row outside: marked neither observed nor missing below
         }
       }
+    }
     for (int c = 0; c < nchunk; ++c) {
       const int r0 = c * kRC;
-      __syncthreads();   // every warp has finished reading cs / As / Bs of the previous (k, chunk)
+      __syncthreads();   // every warp has finished reading cs / As / Bs / Ms of the previous (k, chunk)
       if (nchunk > 1 || k == k0) {
         for (int e = tid; e < kRC * kTile; e += 256) {
           const int ii = e % kTile, rr = e / kTile;
@@ -97,29 +113,46 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
           for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
     }
-    // epilogue: compare the model with the stored elements loaded above / impute
+    // accumulator (mt, nt, e) of this lane is model element (i = 16 wi + 8 mt + p, j = 32 wj + 8 nt + 2 q + e) of the tile
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const long long j = j0 + 32 * wj + 8 * nt + 2 * q + e;
+      for (int nt = 0; nt < 4; ++nt) {
+        Ms[(32 * wj + 8 * nt + 2 * q) * kMP + 16 * wi + 8 * mt + p] = acc[mt][nt][0];
+        Ms[(32 * wj + 8 * nt + 2 * q + 1) * kMP + 16 * wi + 8 * mt + p] = acc[mt][nt][1];
+      }
+    __syncthreads();
+    {
+      const long long colbase = ie + a.ldI * (j0 + 8 * warp + (long long)a.J * k);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const long long i = i0 + 16 * wi + 8 * mt + p;
-          const double x = xv[mt][nt][e], m = acc[mt][nt][e];
-          if (mk[mt][nt][e] == 1) {
-            s[2] = fma(x, m, s[2]);
-            s[3] = fma(m, m, s[3]);
-            const double d = x - m;
-            s[4] = fma(d, d, s[4]);
-          } else if (mk[mt][nt][e] == 0) {
-            const double d = m - x;
-            s[0] = fma(d, d, s[0]);
-            s[1] = fma(x, x, s[1]);
-            if (a.impute) a.X[i + a.ldI * (j + (long long)a.J * k)] = m;
-          }
+      for (int c = 0; c < 8; ++c) {
+        const double2 mv = *reinterpret_cast<const double2*>(&Ms[(8 * warp + c) * kMP + 2 * lane]);
+        const unsigned m16 = mk[c];
+        const bool in0 = (m16 >> 16) == 0, in1 = in0 && ((m16 & 0xFF00u) != 0xFF00u || nrow == 2);
+        // branch-free sums; only the store of an imputed value is predicated
+        const bool ob0 = in0 && (m16 & 0xFFu) != 0, ob1 = in1 && (m16 & 0xFF00u) != 0;
+        const bool mi0 = in0 && !ob0, mi1 = in1 && !ob1;
+        const double xo0 = ob0 ? x0[c] : 0.0, mo0 = ob0 ? mv.x : 0.0, xo1 = ob1 ? x1[c] : 0.0, mo1 = ob1 ? mv.y : 0.0;
+        const double xm0 = mi0 ? x0[c] : 0.0, mm0 = mi0 ? mv.x : 0.0, xm1 = mi1 ? x1[c] : 0.0, mm1 = mi1 ? mv.y : 0.0;
+        s[2] = fma(xo0, mo0, s[2]);
+        s[2] = fma(xo1, mo1, s[2]);
+        s[3] = fma(mo0, mo0, s[3]);
+        s[3] = fma(mo1, mo1, s[3]);
+        const double do0 = xo0 - mo0, do1 = xo1 - mo1;
+        s[4] = fma(do0, do0, s[4]);
+        s[4] = fma(do1, do1, s[4]);
+        const double dm0 = mm0 - xm0, dm1 = mm1 - xm1;
+        s[0] = fma(dm0, dm0, s[0]);
+        s[0] = fma(dm1, dm1, s[0]);
+        s[1] = fma(xm0, xm0, s[1]);
+        s[1] = fma(xm1, xm1, s[1]);
+        if (a.impute) {
+          const long long idx = colbase + a.ldI * c;
+          if (mi0) a.X[idx] = mv.x;
+          if (mi1) a.X[idx + 1] = mv.y;
         }
       }
+    }
   }
   const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
 #pragma unroll
@@ -212,7 +245,9 @@ int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
   int kper;
   em_grid(a, g, kper);
   if (g.y > 65535) throw CudaError(2, "EM imputation: object too wide");
-  em_kernel<<<g, 256, 0, st>>>(a, kper);
+  constexpr size_t kEmSmem = (size_t)(kTile * kMP + 2 * kRC * kPitch + kRC) * sizeof(double);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(em_kernel), kEmSmem);
+  em_kernel<<<g, 256, kEmSmem, st>>>(a, kper);
   AO_CHECK_LAUNCH();
   em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
   AO_CHECK_LAUNCH();

@@ -22,7 +22,7 @@ namespace {
 // =====================================================================================================
 // Gram
 // =====================================================================================================
-constexpr int kGramChunk = 256;
+constexpr int kGramChunk = 64;   // rows per CTA: a 4096-row factor gives 64 x (R/32)^2 CTAs instead of 16 (the kernel is latency bound)
 
 __global__ void gram_partial_kernel(const double* __restrict__ F, long long rows, long long ld, int R,
                                     double* __restrict__ ws, const int* __restrict__ skip) {
