@@ -93,26 +93,23 @@ __global__ void __launch_bounds__(kP2Threads) par2_batched_gram_kernel(Par2Layou
   }
 }
 
-__global__ void par2_modeA_had_kernel(Par2Layout L, const double* __restrict__ G2, const double* __restrict__ C,
-                                      long long ldc, double* __restrict__ Csum) {
-  const int R = L.R;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= R * R) return;
+// one warp per element of the R x R result: the lanes stride over the slices (fixed order), then a butterfly sum - the
+// K-long sum is latency bound when one thread walks it (138 us at K = 512), a warp finishes it in a few microseconds
+__global__ void __launch_bounds__(256) par2_modeA_had_kernel(Par2Layout L, const double* __restrict__ G2,
+                                                             const double* __restrict__ C, long long ldc,
+                                                             double* __restrict__ Csum) {
+  const int R = L.R, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= R * R) return;   // whole warps leave together
   const int a = e % R, b = e / R;
   const double* ca = C + a * ldc;
   const double* cb = C + b * ldc;
   const double* g = G2 + e;
   const size_t RR = (size_t)R * R;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int k = L.k0;
-  for (; k + 3 < L.k1; k += 4) {
-    a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
-    a1 += (ca[k + 1] * g[(size_t)(k + 1) * RR]) * cb[k + 1];
-    a2 += (ca[k + 2] * g[(size_t)(k + 2) * RR]) * cb[k + 2];
-    a3 += (ca[k + 3] * g[(size_t)(k + 3) * RR]) * cb[k + 3];
-  }
-  for (; k < L.k1; ++k) a0 += (ca[k] * g[(size_t)k * RR]) * cb[k];
-  Csum[e] = (a0 + a1) + (a2 + a3);
+  double acc = 0.0;
+  for (int k = L.k0 + lane; k < L.k1; k += 32) acc += (ca[k] * g[(size_t)k * RR]) * cb[k];
+  acc = warp_sum(acc);
+  if (lane == 0) Csum[e] = acc;
 }
 
 __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2SysArgs a) {
@@ -508,6 +505,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   }
 }
 
+// one warp per element of DeltaB (see par2_modeA_had_kernel): 8 elements per CTA
 __global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl,
                                                             double* __restrict__ sums_out) {
   if (ctl != nullptr && ctl->done != 0) return;
@@ -522,19 +520,16 @@ __global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BA
   __syncthreads();
   const double tot = s_sum;
   if (sums_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) sums_out[RR] = tot;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RR; e += gridDim.x * blockDim.x) {
-    const double* c = a.contrib + e;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = K0;
-    for (; k + 3 < K1; k += 4) {   // four independent load streams; fixed association => deterministic
-      a0 += c[(size_t)k * RR];
-      a1 += c[(size_t)(k + 1) * RR];
-      a2 += c[(size_t)(k + 2) * RR];
-      a3 += c[(size_t)(k + 3) * RR];
-    }
-    for (; k < K1; ++k) a0 += c[(size_t)k * RR];
-    if (sums_out != nullptr) sums_out[e] = (a0 + a1) + (a2 + a3);   // sharded slices: all-reduced, then divided
-    else a.DeltaB[e] = ((a0 + a1) + (a2 + a3)) / tot;               // :541-544
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= RR) return;
+  const double* c = a.contrib + e;
+  double acc = 0.0;
+  for (int k = K0 + lane; k < K1; k += 32) acc += c[(size_t)k * RR];   // lanes stride over the slices, fixed order
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (sums_out != nullptr) sums_out[e] = acc;   // sharded slices: all-reduced, then divided
+    else a.DeltaB[e] = acc / tot;                 // :541-544
   }
 }
 
@@ -888,7 +883,7 @@ int par2_batched_gram(const Par2Layout& L, const double* Bst, double* G2, cudaSt
 }
 
 int par2_modeA_had(const Par2Layout& L, const double* G2, const double* C, long long ldc, double* Csum, cudaStream_t st) {
-  par2_modeA_had_kernel<<<(unsigned)ceil_div(L.R * L.R, 128), 128, 0, st>>>(L, G2, C, ldc, Csum);
+  par2_modeA_had_kernel<<<(unsigned)ceil_div(L.R * L.R, 8), 256, 0, st>>>(L, G2, C, ldc, Csum);
   AO_CHECK_LAUNCH();
   return 1;
 }
@@ -984,7 +979,7 @@ int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, i
 }
 
 int par2_B_deltaB(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, cudaStream_t st, double* sums_out) {
-  par2_B_deltaB_kernel<<<(unsigned)ceil_div(L.R * L.R, 64), 256, 0, st>>>(L, a, ctl, sums_out);
+  par2_B_deltaB_kernel<<<(unsigned)ceil_div(L.R * L.R, 8), 256, 0, st>>>(L, a, ctl, sums_out);
   AO_CHECK_LAUNCH();
   return 1;
 }
