@@ -694,6 +694,26 @@ int choose_splits(long long tiles, long long max_splits) {
   return best;
 }
 
+// INNER kernels split the slab range in WHOLE slabs, so a CTA's work is ceil(K / splits) slabs and the pass lasts
+// ceil(K / splits) * waves slab-times: pick the split count that minimises that makespan (e.g. K = 128 on 32 tiles:
+// 9 splits -> 15 slabs x 2 waves = 30, 32 splits -> 4 x 7 = 28, ideal 27.7).  Ties go to fewer splits (less to reduce).
+int choose_splits_slabs(long long tiles, long long slabs, long long max_splits) {
+  const int sms = sm_count();
+  long long best = 1;
+  double best_cost = 1e300;
+  const long long hi = std::max<long long>(1, std::min<long long>(std::min(slabs, max_splits), 592));
+  for (long long ns = 1; ns <= hi; ++ns) {
+    const long long waves = ceil_div(tiles * ns, sms);
+    // per-CTA fixed cost (pipeline fill, epilogue, partial-result traffic) ~ a quarter of a slab-time per wave
+    const double cost = (double)ceil_div(slabs, ns) * (double)waves + 0.25 * (double)waves;
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = ns;
+    }
+  }
+  return (int)best;
+}
+
 template <int NT, int WARPS_N, int PREC>
 int launch_lead(const Tensor3& t, const PackedFactor& fj, const PackedFactor& fk, int R, double scale, double* out,
                 int64_t ldout, const MttkrpWorkspace& w, cudaStream_t st, const int* skip) {
@@ -721,7 +741,7 @@ int launch_inner(const Tensor3& t, const PackedFactor& fi, const PackedFactor& f
                  int64_t ldout, const MttkrpWorkspace& w, double* Tbuf, cudaStream_t st, const int* skip) {
   using C = Cfg<NT, WARPS_N>;
   const int jtiles = (int)ceil_div(t.J, 128), nit = (int)ceil_div(t.I, 32), nchunk = fi.nchunk;
-  const int nsplit = choose_splits((long long)jtiles * nchunk, t.K);
+  const int nsplit = choose_splits_slabs((long long)jtiles * nchunk, t.K, 592);
   const int Rp_total = nchunk * C::NC;
   const long long rows = (EPI == 0) ? t.J : t.K;
   const long long ldo = round_up(rows, 2);

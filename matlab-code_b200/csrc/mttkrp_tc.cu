@@ -467,22 +467,22 @@ int tc_sm_count() {
   return n;
 }
 
-// number of slab-range splits so that tiles*splits fills whole waves of one CTA per SM
-int tc_choose_splits(long long tiles, long long max_splits, long long cap) {
+// The slab range is split in WHOLE slabs: a CTA's work is ceil(K / splits) slabs and the pass lasts ceil(K / splits) *
+// waves slab-times; pick the split count that minimises that makespan (ties: fewer splits, less to reduce).
+int tc_choose_splits(long long tiles, long long slabs, long long cap) {
   const int sms = tc_sm_count();
-  int best = 1;
-  double best_eff = 0.0;
-  for (int w = 1; w <= 4; ++w) {
-    long long ns = ((long long)sms * w) / tiles;
-    ns = std::max<long long>(1, std::min(ns, std::min(max_splits, cap)));
-    const long long ctas = tiles * ns;
-    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
-      best = (int)ns;
+  long long best = 1;
+  double best_cost = 1e300;
+  const long long hi = std::max<long long>(1, std::min<long long>(std::min(slabs, cap), 592));
+  for (long long ns = 1; ns <= hi; ++ns) {
+    const long long waves = ceil_div(tiles * ns, sms);
+    const double cost = (double)ceil_div(slabs, ns) * (double)waves + 0.25 * (double)waves;
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = ns;
     }
   }
-  return best;
+  return (int)best;
 }
 
 template <int PREC, int CONV, int EPI, int ATMEM>

@@ -68,6 +68,13 @@ def test_invalid_arguments_rejected_without_device(ab):
     assert b'NULL' in c.lib.aoadmm_last_error(None)
     assert c.lib.aoadmm_run(None, None, None) == 1
     assert c.lib.aoadmm_destroy(None) == 0
+    # the one-caller multi-GPU form (ABI 4): same conventions
+    assert c.lib.aoadmm_create_multi(None, 2, None, None) == 1
+    assert c.lib.aoadmm_create_multi(None, 2, None, ctypes.byref(h)) != 0 and not h.value
+    assert b'NULL' in c.lib.aoadmm_last_error(None)
+    n = ctypes.c_int32(7)
+    assert c.lib.aoadmm_gpu_count(None, ctypes.byref(n)) == 1
+    assert c.lib.aoadmm_comm_release() == 0           # nothing cached: a no-op
 
 
 def test_constraint_spec_mapping(ab):
