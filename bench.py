@@ -355,16 +355,17 @@ def main():
             hbm_peak = float(json.load(f)['hbm_gbs'])
     except Exception:
         pass
-    # dram bytes per launch from the ncu --set full captures of profiles/r01_ncu_mttkrp_summary.md: 1.004x (R=32, the
-    # C2 launch itself) / 1.005x (R=64, captured on a K=64 slab of the same 4096x4096 tile shape) the algorithmic bytes
-    traffic_ratio = {'c2': 1.004, 'c3k1024': 1.005, 'c3': 1.005}.get(args.workload)
+    # dram bytes per launch from the ncu --set full captures: 1.004x the algorithmic bytes at R=32 (the C2 launch itself,
+    # profiles/r01_ncu_mttkrp_summary.md), 1.008x at R=64 (round-2 LEAD kernel on a K=64 slab of the same 4096x4096 tile
+    # shape, profiles/r02_ncu_mttkrp_summary.md: 8.646 GB read + 15.8 MB written for 8.590 GB)
+    traffic_ratio = {'c2': 1.004, 'c3k1024': 1.008, 'c3': 1.008}.get(args.workload)
     passes = 2 if DIMTREE else 3
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': FP64_DMMA_PEAK_TFLOPS, 'unit': 'TFLOP/s',
                 'frac': achieved / FP64_DMMA_PEAK_TFLOPS,
                 'peak_nominal': FP64_NOMINAL_TFLOPS, 'frac_nominal': achieved / FP64_NOMINAL_TFLOPS,
                 'traffic': bytes_mode * traffic_ratio if traffic_ratio else None,
                 'traffic_note': 'dram__bytes_read+write per launch = %.3f x algorithmic bytes (ncu --set full, '
-                                'profiles/r01_mttkrp_*_full_raw.csv)' % traffic_ratio if traffic_ratio else None,
+                                'profiles/r02_ncu_mttkrp_summary.md)' % traffic_ratio if traffic_ratio else None,
                 'kernel': 'mttkrp_lead_kernel / mttkrp_inner_kernel (FP64 DMMA.8x8x4 + TMA), 3 modes',
                 'per_mode_ms': mode_ms, 'per_mode_tflops': [flops_mode / (m * 1e-3) / 1e12 for m in mode_ms],
                 'per_mode_hbm_gbs': [bytes_mode / (m * 1e-3) / 1e9 for m in mode_ms], 'hbm_peak_gbs_measured': hbm_peak,

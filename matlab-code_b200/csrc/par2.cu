@@ -419,11 +419,23 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
     S[j + c * Jk] = x;
   }
   __syncthreads();
-  // one-sided Jacobi: S <- S*V with orthogonal columns
+  // one-sided Jacobi: S <- S*V with orthogonal columns.  The round is issue bound (eight warps, one column pair each), so
+  // it carries as few instructions as possible: the squared column norms are kept in shared memory, refreshed exactly at
+  // the start of every sweep and updated by the rotation identities al' = al - t*ga, be' = be + t*ga in between (one dot
+  // product and one warp reduction per pair instead of three); the round-robin partner indices use a conditional subtract
+  // instead of a modulo; tan(theta) = 2ga / (tau + sign(tau) sqrt(tau^2 + 4ga^2)) needs one division and one square root.
   const int Re = (R + 1) & ~1, npairs = Re / 2;
+  __shared__ double nrm[64];   // squared column norms (R <= 64)
   const double tol2 = 2.220446049250313e-16 * 2.220446049250313e-16 * (double)Jk;
   for (int sweep = 0; sweep < 60; ++sweep) {
     if (tid == 0) s_rot = 0;
+    for (int r = warp; r < R; r += nw) {
+      const double* x = S + (size_t)r * Jk;
+      double al = 0.0;
+      for (int j = lane; j < Jk; j += 32) al = fma(x[j], x[j], al);
+      al = warp_sum(al);
+      if (lane == 0) nrm[r] = al;
+    }
     __syncthreads();
     for (int rd = 0; rd < Re - 1; ++rd) {
       for (int q = warp; q < npairs; q += nw) {
@@ -432,8 +444,10 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
           p1 = Re - 1;
           p2 = rd;
         } else {
-          p1 = (rd + q) % (Re - 1);
-          p2 = (rd - q + Re - 1) % (Re - 1);
+          p1 = rd + q;                 // < 2 (Re - 1)
+          p2 = rd - q + Re - 1;        // in [0, 2 (Re - 1))
+          if (p1 >= Re - 1) p1 -= Re - 1;
+          if (p2 >= Re - 1) p2 -= Re - 1;
         }
         if (p1 > p2) {
           const int t = p1;
@@ -443,20 +457,14 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
         if (p2 >= R) continue;  // bye (odd R)
         double* x = S + (size_t)p1 * Jk;
         double* y = S + (size_t)p2 * Jk;
-        double al = 0.0, be = 0.0, ga = 0.0;
-        for (int j = lane; j < Jk; j += 32) {
-          const double xv = x[j], yv = y[j];
-          al = fma(xv, xv, al);
-          be = fma(yv, yv, be);
-          ga = fma(xv, yv, ga);
-        }
-        al = warp_sum(al);
-        be = warp_sum(be);
+        const double al = nrm[p1], be = nrm[p2];
+        double ga = 0.0;
+        for (int j = lane; j < Jk; j += 32) ga = fma(x[j], y[j], ga);
         ga = warp_sum(ga);
         if (ga * ga > tol2 * (al * be)) {
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
+          const double tau = be - al, g2 = 2.0 * ga;
+          const double t = g2 / (tau + copysign(sqrt(fma(tau, tau, g2 * g2)), tau));
+          const double cs = rsqrt(fma(t, t, 1.0)), sn = cs * t;
           for (int j = lane; j < Jk; j += 32) {
             const double xv = x[j], yv = y[j];
             x[j] = cs * xv - sn * yv;
@@ -467,7 +475,11 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
             V[i + p1 * R] = cs * xv - sn * yv;
             V[i + p2 * R] = sn * xv + cs * yv;
           }
-          if (lane == 0) s_rot = 1;
+          if (lane == 0) {
+            nrm[p1] = al - t * ga;
+            nrm[p2] = be + t * ga;
+            s_rot = 1;
+          }
         }
       }
       __syncthreads();

@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, call M (1 GPU): PARAFAC2 parity + C4 rate after the leaner Jacobi rounds
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -x -k "parafac2 or par2 or script1a or script2 or script14 or script11 or config4 or degenerate or em_imputation_cp_coupled or front_end" > gpurun_out/r2m_pytest_par2.log 2>&1
+echo "par2 rc=$?"; tail -4 gpurun_out/r2m_pytest_par2.log
+timeout 600 python tools/bench_configs.py c4 --iters 20 > gpurun_out/r2m_bench_c4.jsonl 2>&1; cut -c1-330 gpurun_out/r2m_bench_c4.jsonl
