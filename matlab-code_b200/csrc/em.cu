@@ -20,14 +20,17 @@ namespace aoadmm {
 
 namespace {
 
-constexpr int kTile = 64;
+constexpr int kTile = 64;          // tile rows (i)
+constexpr int kTJ = 32;            // tile columns (j): 64 x 32 tiles with 4 warps give four resident CTAs per SM whose
+                                   // load / tensor-core / epilogue phases interleave (64 x 64 with 8 warps: two)
+constexpr int kEmThreads = 128;
 constexpr int kRC = 32;          // rank chunk staged per pass
 constexpr int kPitch = kTile + 4;  // smem row pitch: the 4 x 8 fragment footprint of a DMMA operand hits 32 distinct banks
 
 constexpr int kMP = kTile + 2;     // pitch of the model tile: C-fragment stores and 16-byte row reads are conflict-free
 
 // The model of slab k is a rank-R GEMM, M_k = (Fi diag(Fk(k,:))) * Fj': it runs on the FP64 tensor cores like the
-// MTTKRP (mma.m8n8k4, SASS DMMA.8x8x4).  CTA tile 64 (i) x 64 (j), 8 warps as 4 (i) x 2 (j), warp tile 16 x 32 =
+// MTTKRP (mma.m8n8k4, SASS DMMA.8x8x4).  CTA tile 64 (i) x 32 (j), 4 warps along i, warp tile 16 x 32 =
 // 2 x 4 accumulator tiles.  The unscaled factor tiles are staged in shared memory once per CTA (once per rank chunk
 // when R > 32) and reused for every k of the CTA's range; the k-dependent scale Fk(k,r) is applied to the A fragment
 // in registers (2 DMUL per 8 DMMA).
@@ -37,17 +40,17 @@ constexpr int kMP = kTile + 2;     // pitch of the model tile: C-fragment stores
 // so that the DRAM latency hides behind it.  (The first DMMA version compared in the accumulator layout: 32 scalar
 // loads with their own 64-bit addresses per lane and k made it issue bound - 1080 instructions per warp and k, FP64
 // pipe 7 % busy, profiles/r02_ncu_em_summary.md.)
-__global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
+__global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
   extern __shared__ __align__(16) double em_smem[];   // 68.4 KB: beyond the static limit, two CTAs per SM
-  double* Ms = em_smem;                                                     // kTile x kMP model tile
-  double (*As)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTile * kMP);
-  double (*Bs)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTile * kMP + kRC * kPitch);
-  double* cs = em_smem + kTile * kMP + 2 * kRC * kPitch;
+  double* Ms = em_smem;                                                     // kTJ x kMP model tile (column-major)
+  double (*As)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTJ * kMP);
+  double (*Bs)[kPitch] = reinterpret_cast<double (*)[kPitch]>(em_smem + kTJ * kMP + kRC * kPitch);
+  double* cs = em_smem + kTJ * kMP + 2 * kRC * kPitch;
   __shared__ double red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wi = warp & 3, wj = warp >> 2;
+  const int wi = warp, wj = 0;   // 4 warps along i, each 16 (i) x 32 (j)
   const int q = lane & 3, p = lane >> 2;
-  const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTile;
+  const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTJ;
   const int k0 = blockIdx.z * kper, k1 = min(a.K, k0 + kper);
   const int nchunk = (a.R + kRC - 1) / kRC;
   // epilogue ownership: rows ie, ie+1 of the columns j0 + 8*warp + c, c = 0..7
@@ -86,11 +89,11 @@ __global__ void __launch_bounds__(256, 2) em_kernel(EmArgs a, int kper) {
       const int r0 = c * kRC;
       __syncthreads();   // every warp has finished reading cs / As / Bs / Ms of the previous (k, chunk)
       if (nchunk > 1 || k == k0) {
-        for (int e = tid; e < kRC * kTile; e += 256) {
+        for (int e = tid; e < kRC * kTile; e += kEmThreads) {
           const int ii = e % kTile, rr = e / kTile;
           const int r = r0 + rr;
           As[rr][ii] = (r < a.R && i0 + ii < a.I) ? a.Fi[i0 + ii + (long long)r * a.ldFi] : 0.0;
-          Bs[rr][ii] = (r < a.R && j0 + ii < a.J) ? a.Fj[j0 + ii + (long long)r * a.ldFj] : 0.0;
+          if (ii < kTJ) Bs[rr][ii] = (r < a.R && j0 + ii < a.J) ? a.Fj[j0 + ii + (long long)r * a.ldFj] : 0.0;
         }
       }
       if (tid < kRC) {
@@ -221,7 +224,7 @@ __global__ void em_khatri_rao_kernel(KrArgs a, double* __restrict__ out, long lo
 }
 
 void em_grid(const EmArgs& a, dim3& grid, int& kper) {
-  const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTile);
+  const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTJ);
   // enough CTAs for a few waves of 148 SMs, but several k per CTA so that the Fj tile is reused
   long long kz = std::min<long long>(a.K, std::max<long long>(1, (148LL * 8) / std::max<long long>(ti * tj, 1)));
   kz = std::min<long long>(kz, 65535);
@@ -245,9 +248,9 @@ int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
   int kper;
   em_grid(a, g, kper);
   if (g.y > 65535) throw CudaError(2, "EM imputation: object too wide");
-  constexpr size_t kEmSmem = (size_t)(kTile * kMP + 2 * kRC * kPitch + kRC) * sizeof(double);
+  constexpr size_t kEmSmem = (size_t)(kTJ * kMP + 2 * kRC * kPitch + kRC) * sizeof(double);
   ensure_dynamic_smem(reinterpret_cast<const void*>(em_kernel), kEmSmem);
-  em_kernel<<<g, 256, kEmSmem, st>>>(a, kper);
+  em_kernel<<<g, kEmThreads, kEmSmem, st>>>(a, kper);
   AO_CHECK_LAUNCH();
   em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
   AO_CHECK_LAUNCH();

@@ -410,7 +410,7 @@ void solve(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   o.has_increase_factor_rhoBk = field(opt, "increase_factor_rhoBk", false) != nullptr;            // :196-198
   o.increase_factor_rhoBk = opt_scalar(opt, "increase_factor_rhoBk", 1.0);
   o.dimtree = (int32_t)opt_scalar(opt, "b200_dimtree", 1.0);  // engine knob, results equal to rounding
-  o.mttkrp_precision = (int32_t)opt_scalar(opt, "b200_mttkrp_precision", 0.0);  // 1: opt-in TF32 MTTKRP
+  o.mttkrp_precision = (int32_t)opt_scalar(opt, "b200_mttkrp_precision", 0.0);  // opt-in: 1 TF32, 2 BF16 (tcgen05), 3 TF32 (mma.sync)
   o.fuse_inner = (int32_t)opt_scalar(opt, "b200_fuse_inner", 0.0);
   o.graph = (int32_t)opt_scalar(opt, "b200_graph", 0.0);      // engine knob: 0 auto, 1 on, -1 off
 
