@@ -517,6 +517,305 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same step for SMALL slices (R <= 16, J_k <= 128): one WARP per slice, the slice in REGISTERS.
+// The CTA kernel above is issue bound on such slices: each of its eight warps executes the scalar rotation arithmetic
+// (an FP64 division, square root and reciprocal square root, ~150 instructions) of its own column pair with all 32
+// lanes, every column element is a shared-memory round trip, and every round ends in a CTA barrier.  Here
+//   * lane l owns the rows l, l+32, .. of the slice: S[JP][RE] doubles in registers (RE = R rounded up to 4 / 8 / 16,
+//     the padding columns are zero and never rotate), and row l of the rotation matrix V;
+//   * the RE/2 column pairs of a round sit in FIXED register positions (2q, 2q+1); between rounds the columns move one
+//     step around the ring of the round-robin tournament (Brent-Luk: position 0 stays, the other RE-1 rotate), a static
+//     register permutation, so every register index is a compile-time constant and after a full sweep of RE-1 rounds
+//     the columns are back in their own positions;
+//   * the RE/2 dot products of a round are reduced with ONE transposing butterfly (RE/2-1 + 5-log2(RE/2) shuffles
+//     instead of 5 per pair), which leaves the total of pair q in the lanes of group q; those lanes compute the
+//     rotation of their pair - the scalar chain runs once per round - and broadcast (cos, sin) through shared memory;
+//   * the rotations of a round are branch-free (cos = 1, sin = 0 is exact) and independent: full ILP, warp barriers only.
+// Same rotation formula, tolerance and tracked column norms as the CTA kernel; the pair ORDER within a sweep differs
+// (any cyclic ordering converges to the same polar factor).
+// ---------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void reduce_transpose(double (&v)[N], int lane) {
+  // sums v[i] over the 32 lanes for all i at once; afterwards v[0] of lane l is the total of index transpose_index<N>(l)
+  int off = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int N>
+__device__ __forceinline__ int transpose_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1, off >>= 1) idx |= (lane & off) ? half : 0;
+  return idx;
+}
+// one step of the tournament ring: t_0 stays, b_0 -> t_1, t_q -> t_{q+1}, t_{n-1} -> b_{n-1}, b_q -> b_{q-1}
+// (t_q = position 2q, b_q = position 2q+1)
+template <int RE>
+__device__ __forceinline__ void ring_step(double (&c)[RE]) {
+  constexpr int n = RE / 2;
+  double nt[n], nb[n];
+  nt[0] = c[0];
+  nt[1] = c[1];
+#pragma unroll
+  for (int q = 2; q < n; ++q) nt[q] = c[2 * (q - 1)];
+#pragma unroll
+  for (int q = 0; q < n - 1; ++q) nb[q] = c[2 * (q + 1) + 1];
+  nb[n - 1] = c[2 * (n - 1)];
+#pragma unroll
+  for (int q = 0; q < n; ++q) {
+    c[2 * q] = nt[q];
+    c[2 * q + 1] = nb[q];
+  }
+}
+template <int RE>
+__device__ __forceinline__ int ring_newpos(int pos) {
+  constexpr int n = RE / 2;
+  const int q = pos >> 1;
+  if ((pos & 1) == 0) return (q == 0) ? 0 : ((q == n - 1) ? 2 * (n - 1) + 1 : 2 * (q + 1));
+  return (q == 0) ? 2 : 2 * (q - 1) + 1;
+}
+
+template <int RE>
+__host__ __device__ inline size_t par2_step1_reg_doubles(long long Jmax) {
+  const long long pitch = Jmax | 1;
+  return (size_t)4 * RE * RE + (size_t)2 * pitch * RE + 2 * (RE / 2) + 2 * RE + RE;
+}
+
+template <int RE, int JP>
+__global__ void __launch_bounds__(32) par2_B_step1_reg_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl, int warm) {
+  constexpr int NP = RE / 2;
+  if (ctl != nullptr && ctl->done != 0) return;
+  extern __shared__ __align__(16) double sm[];
+  const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, lane = threadIdx.x;
+  const long long j0 = L.joff[k], ld = L.Jtot;
+  const int Jk = (int)(L.joff[k + 1] - j0);
+  const int pitch = (int)(L.Jmax | 1);
+  double* dB = sm;                       // RE x RE, zero padded, element (r, c) at r + c*RE
+  double* Bi = dB + RE * RE;
+  double* Wm = Bi + RE * RE;             // DeltaB' W; after the iteration: V
+  double* V0 = Wm + RE * RE;             // rotations of the previous inner iteration (warm) or I
+  double* Ms = V0 + RE * RE;             // B_k + mu_k           (pitch x RE)
+  double* Ts = Ms + (size_t)pitch * RE;  // P_k                  (pitch x RE)
+  double* par = Ts + (size_t)pitch * RE; // (cos, sin) of the pairs of a round
+  double* nrm = par + 2 * NP;            // tracked squared column norms by position, double buffered
+  double* isg = nrm + 2 * RE;            // 1 / sigma
+  const double rho = a.rho_k[k], half = rho / 2.0;
+
+  for (int e = lane; e < RE * RE; e += 32) {
+    const int r = e % RE, c = e / RE;
+    const bool in = r < R && c < R;
+    dB[e] = in ? a.DeltaB[r + c * R] : 0.0;
+    Bi[e] = in ? a.Binv[(size_t)k * RR + r + c * R] : 0.0;
+    V0[e] = (in && warm) ? a.Vprev[(size_t)k * RR + r + c * R] : ((r == c) ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  for (int e = lane; e < RE * RE; e += 32) {   // Wm = DeltaB' V0
+    const int r = e % RE, c = e / RE;
+    double x = 0.0;
+    if (warm) {
+      for (int q = 0; q < R; ++q) x = fma(dB[q + r * RE], V0[q + c * RE], x);
+    } else {
+      x = dB[c + r * RE];
+    }
+    Wm[e] = x;
+  }
+  __syncwarp();
+
+  double S[JP][RE];
+#pragma unroll
+  for (int jp = 0; jp < JP; ++jp) {
+    const int j = lane + 32 * jp;
+    const bool ok = j < Jk;
+    const long long g0 = j0 + j;
+    double p[RE], mu[RE], s[RE];
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      const bool in = ok && c < R;
+      p[c] = in ? a.P[g0 + (long long)c * ld] : 0.0;
+      mu[c] = in ? a.mu[g0 + (long long)c * ld] : 0.0;
+    }
+    // A_inner = A_k + rho_k/2 (P_k DeltaB - mu_k) [+ rho_k/2 (Z_k - muZ_k)]          (:526-529)
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      double pd = 0.0;
+#pragma unroll
+      for (int r = 0; r < RE; ++r) pd = fma(p[r], dB[r + c * RE], pd);
+      double v = 0.0;
+      if (ok && c < R) {
+        const long long g = g0 + (long long)c * ld;
+        a.PDold[g] = pd;
+        v = a.A[g] + half * (pd - mu[c]);
+        if (a.con_active) v += half * (a.Z[g] - a.muZ[g]);
+      }
+      s[c] = v;
+    }
+    // B_k = A_inner inv(Bsys_k)   (:530) ;  M = B_k + mu_k ;  S = M DeltaB' W   (:532)
+    double m[RE];
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      double x = 0.0;
+#pragma unroll
+      for (int r = 0; r < RE; ++r) x = fma(s[r], Bi[r + c * RE], x);
+      m[c] = 0.0;
+      if (ok && c < R) {
+        a.B[g0 + (long long)c * ld] = x;
+        m[c] = x + mu[c];
+        Ms[j + c * pitch] = m[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      double x = 0.0;
+#pragma unroll
+      for (int r = 0; r < RE; ++r) x = fma(m[r], Wm[r + c * RE], x);
+      S[jp][c] = x;
+    }
+  }
+  // ---- one-sided Jacobi: S <- S V with orthogonal columns
+  double v[RE];   // row `lane` of V
+#pragma unroll
+  for (int c = 0; c < RE; ++c) v[c] = (lane < RE) ? V0[lane + c * RE] : 0.0;
+  const int myq = transpose_index<NP>(lane);
+  const bool pair_writer = (lane & (32 / NP - 1)) == 0;
+  const int myc = transpose_index<RE>(lane);
+  const bool col_writer = (lane & (32 / RE - 1)) == 0;
+  const int np_t = ring_newpos<RE>(2 * myq), np_b = ring_newpos<RE>(2 * myq + 1);
+  const double tol2 = 2.220446049250313e-16 * 2.220446049250313e-16 * (double)Jk;
+  int buf = 0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    {  // exact squared column norms at the start of every sweep
+      double n2[RE];
+#pragma unroll
+      for (int c = 0; c < RE; ++c) {
+        double x = 0.0;
+#pragma unroll
+        for (int jp = 0; jp < JP; ++jp) x = fma(S[jp][c], S[jp][c], x);
+        n2[c] = x;
+      }
+      reduce_transpose<RE>(n2, lane);
+      if (col_writer) nrm[buf * RE + myc] = n2[0];
+    }
+    __syncwarp();
+    int rot = 0;
+    for (int rd = 0; rd < RE - 1; ++rd) {
+      double ga[NP];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        double x = 0.0;
+#pragma unroll
+        for (int jp = 0; jp < JP; ++jp) x = fma(S[jp][2 * q], S[jp][2 * q + 1], x);
+        ga[q] = x;
+      }
+      reduce_transpose<NP>(ga, lane);
+      const double g = ga[0];
+      const double al = nrm[buf * RE + 2 * myq], be = nrm[buf * RE + 2 * myq + 1];
+      double cs = 1.0, sn = 0.0, nal = al, nbe = be;
+      int r1 = 0;
+      if (g * g > tol2 * (al * be)) {
+        const double tau = be - al, g2 = 2.0 * g;
+        const double t = g2 / (tau + copysign(sqrt(fma(tau, tau, g2 * g2)), tau));
+        cs = rsqrt(fma(t, t, 1.0));
+        sn = cs * t;
+        nal = al - t * g;
+        nbe = be + t * g;
+        r1 = 1;
+      }
+      if (pair_writer) {
+        *reinterpret_cast<double2*>(par + 2 * myq) = make_double2(cs, sn);
+        nrm[(buf ^ 1) * RE + np_t] = nal;   // the columns move to their next positions below
+        nrm[(buf ^ 1) * RE + np_b] = nbe;
+      }
+      __syncwarp();   // par / nrm written, visible to every lane
+      const int any = __any_sync(0xffffffffu, r1);
+      rot |= any;
+      if (any) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const double2 cssn = *reinterpret_cast<const double2*>(par + 2 * q);
+#pragma unroll
+          for (int jp = 0; jp < JP; ++jp) {
+            const double xv = S[jp][2 * q], yv = S[jp][2 * q + 1];
+            S[jp][2 * q] = cssn.x * xv - cssn.y * yv;
+            S[jp][2 * q + 1] = cssn.y * xv + cssn.x * yv;
+          }
+          const double xv = v[2 * q], yv = v[2 * q + 1];
+          v[2 * q] = cssn.x * xv - cssn.y * yv;
+          v[2 * q + 1] = cssn.y * xv + cssn.x * yv;
+        }
+      }
+      __syncwarp();   // par is rewritten in the next round
+#pragma unroll
+      for (int jp = 0; jp < JP; ++jp) ring_step<RE>(S[jp]);
+      ring_step<RE>(v);
+      buf ^= 1;
+    }
+    if (rot == 0) break;
+  }
+  // after whole sweeps every column is back in its own position
+  if (lane < RE) {
+#pragma unroll
+    for (int c = 0; c < RE; ++c) Wm[lane + c * RE] = v[c];   // V (element (i, c) at i + c*RE)
+    if (lane < R) {
+#pragma unroll
+      for (int c = 0; c < RE; ++c)
+        if (c < R) a.Vprev[(size_t)k * RR + lane + c * R] = v[c];
+    }
+  }
+  {  // 1 / sigma
+    double n2[RE];
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      double x = 0.0;
+#pragma unroll
+      for (int jp = 0; jp < JP; ++jp) x = fma(S[jp][c], S[jp][c], x);
+      n2[c] = x;
+    }
+    reduce_transpose<RE>(n2, lane);
+    if (col_writer) isg[myc] = (n2[0] > 0.0) ? 1.0 / sqrt(n2[0]) : 0.0;
+  }
+  __syncwarp();
+  // P_k = U V'   (:534)
+#pragma unroll
+  for (int jp = 0; jp < JP; ++jp) {
+    const int j = lane + 32 * jp;
+    const bool ok = j < Jk;
+    double u[RE];
+#pragma unroll
+    for (int r = 0; r < RE; ++r) u[r] = S[jp][r] * isg[r];
+#pragma unroll
+    for (int c = 0; c < RE; ++c) {
+      double x = 0.0;
+#pragma unroll
+      for (int r = 0; r < RE; ++r) x = fma(u[r], Wm[c + r * RE], x);
+      if (ok && c < R) {
+        a.P[j0 + j + (long long)c * ld] = x;
+        Ts[j + c * pitch] = x;
+      }
+    }
+  }
+  __syncwarp();
+  // contribution to DeltaB: rho_k P_k' (B_k + mu_k)   (:541)
+  for (int e = lane; e < RR; e += 32) {
+    const int ra = e % R, cb = e / R;
+    const double* pc = Ts + ra * pitch;
+    const double* mc = Ms + cb * pitch;
+    double acc = 0.0;
+    for (int j = 0; j < Jk; ++j) acc = fma(pc[j], mc[j], acc);
+    a.contrib[(size_t)k * RR + e] = rho * acc;
+  }
+}
+
 // one warp per element of DeltaB (see par2_modeA_had_kernel): 8 elements per CTA
 __global__ void __launch_bounds__(256) par2_B_deltaB_kernel(Par2Layout L, Par2BArgs a, const InnerCtl* ctl,
                                                             double* __restrict__ sums_out) {
@@ -982,6 +1281,29 @@ int par2_rho_max(const double* rho_k, int K, double* out, cudaStream_t st) {
 }
 
 int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, int warm, cudaStream_t st) {
+  // small slices: one warp per slice with the slice in registers
+  if (L.R <= 16 && L.Jmax <= 128) {
+    const int nsl = L.k1 - L.k0;
+    const int jp = (L.Jmax <= 32) ? 1 : (L.Jmax <= 64 ? 2 : 4);
+    auto go = [&](auto kern, size_t doubles) {
+      const size_t bytes = doubles * sizeof(double);
+      opt_in_smem(kern, bytes);
+      kern<<<nsl, 32, bytes, st>>>(L, a, ctl, warm);
+    };
+#define AO_P2_REG(RE_)                                                                                   \
+  do {                                                                                                   \
+    const size_t d = par2_step1_reg_doubles<RE_>(L.Jmax);                                                \
+    if (jp == 1) go(par2_B_step1_reg_kernel<RE_, 1>, d);                                                 \
+    else if (jp == 2) go(par2_B_step1_reg_kernel<RE_, 2>, d);                                            \
+    else go(par2_B_step1_reg_kernel<RE_, 4>, d);                                                         \
+  } while (0)
+    if (L.R <= 4) AO_P2_REG(4);
+    else if (L.R <= 8) AO_P2_REG(8);
+    else AO_P2_REG(16);
+#undef AO_P2_REG
+    AO_CHECK_LAUNCH();
+    return 1;
+  }
   const size_t smem = par2_step1_smem_bytes(L.Jmax, L.R);
   const int use_gmem = (smem == (size_t)3 * L.R * L.R * sizeof(double)) ? 1 : 0;
   opt_in_smem(par2_B_step1_kernel, smem);
