@@ -1,5 +1,6 @@
 // nvecs.cu - see nvecs.cuh
 #include "nvecs.cuh"
+#include "mttkrp.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -145,6 +146,188 @@ __global__ void __launch_bounds__(256) unfold_gram_kernel(GramArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Long modes (n > 256): the same 128 x 128 tiles, fed by TMA.  A producer warp (one elected lane) streams the two
+// operand tiles of every 32-deep reduction chunk into a 3-stage ring of 128-byte-swizzled shared-memory tiles
+// (cp.async.bulk.tensor, zero fill outside the object, completion on an mbarrier); the eight consumer warps (2 x 4,
+// warp tile 64 x 32 = 8 x 4 DMMA blocks) never issue a copy or a CTA barrier - they wait on the stage's `full`
+// barrier, read fragments and release the stage through its `empty` barrier, as the MTTKRP kernels do.
+//   layout 0 (mode contiguous):   tile = 8 boxes of [32 reduction rows][16 a]  (box 16 x 32 of the n x ncols view)
+//   layout 1 (reduction contiguous): tile = 2 boxes of [128 a][16 i]            (box 16 x 128 x 1 or 16 x 1 x 128)
+// Fragment index maps (which 8 of a box's indices form one DMMA block) are those of mttkrp.cu: every 64-bit
+// fragment load of a half-warp covers 16 distinct 8-byte slots of the swizzled rows.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGT = 128;                         // tile edge
+constexpr int kGStages = 3;
+constexpr int kGTileBytes = kGT * kBK * 8;       // 32 KB per operand tile
+constexpr int kGConsumers = 8;
+constexpr int kGThreads = (kGConsumers + 1) * 32;
+constexpr int kGSmem = kGStages * 2 * kGTileBytes + 2 * kGStages * 8 + 1024;
+
+struct GramTmaArgs {
+  long long n, nchunks, cps, cpi;
+  int a_dim;      // layout 1: which map dimension (1 or 2) carries the mode index a
+  double* P;
+};
+
+template <int L>
+__global__ void __launch_bounds__(kGThreads, 1) unfold_gram_tma_kernel(const __grid_constant__ CUtensorMap tmap, GramTmaArgs g) {
+  const int ta = blockIdx.x, tb = blockIdx.y;
+  if (tb < ta) return;
+  extern __shared__ uint8_t gsm_raw[];
+  const uint32_t sbase = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = sbase + kGStages * 2 * kGTileBytes;   // full[kGStages], empty[kGStages]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool diag = (ta == tb);
+  const int a0 = ta * kGT, b0 = tb * kGT;
+  const long long c_begin = (long long)blockIdx.z * g.cps, c_end = min(g.nchunks, c_begin + g.cps);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      mbar_init(sBar + s * 8, 1);
+      mbar_init(sBar + (kGStages + s) * 8, kGConsumers);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kGConsumers) {
+    if (lane == 0) {
+      prefetch_tensormap(&tmap);
+      for (long long c = c_begin; c < c_end; ++c) {
+        const long long cl = c - c_begin;
+        const int s = (int)(cl % kGStages);
+        const uint32_t ph = (uint32_t)((cl / kGStages) & 1);
+        mbar_wait(sBar + (kGStages + s) * 8, ph ^ 1u);
+        const uint32_t full = sBar + s * 8;
+        const uint32_t sA = sbase + s * 2 * kGTileBytes, sB = sA + kGTileBytes;
+        mbar_expect_tx(full, diag ? kGTileBytes : 2 * kGTileBytes);
+        if (L == 0) {
+          const int c0 = (int)(c * kBK);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) tma_load_3d(sA + b * 4096, &tmap, a0 + 16 * b, c0, 0, full);
+          if (!diag) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) tma_load_3d(sB + b * 4096, &tmap, b0 + 16 * b, c0, 0, full);
+          }
+        } else {
+          const int bidx = (int)(c / g.cpi), i0 = (int)((c % g.cpi) * kBK);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (g.a_dim == 1) tma_load_3d(sA + h * 16384, &tmap, i0 + 16 * h, a0, bidx, full);
+            else tma_load_3d(sA + h * 16384, &tmap, i0 + 16 * h, bidx, a0, full);
+          }
+          if (!diag) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (g.a_dim == 1) tma_load_3d(sB + h * 16384, &tmap, i0 + 16 * h, b0, bidx, full);
+              else tma_load_3d(sB + h * 16384, &tmap, i0 + 16 * h, bidx, b0, full);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: 2 (rows) x 4 (columns) warps =====
+  const int wm = warp & 1, wn = warp >> 1;
+  const int m = lane >> 2, kk = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  // per-fragment byte offsets inside an operand tile (without the k4-step part)
+  uint32_t aoff[8], axr[8], boff[4], bxr[4];
+  if (L == 0) {
+    const int cbase = ((m >> 1) & 1) * 4 + (m >> 2), off = m & 1;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      aoff[mi] = (uint32_t)((4 * wm + (mi >> 1)) * 4096 + kk * 128 + off * 8);
+      axr[mi] = (uint32_t)(((cbase + 2 * (mi & 1)) ^ kk) << 4);
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      boff[ni] = (uint32_t)((2 * wn + (ni >> 1)) * 4096 + kk * 128 + off * 8);
+      bxr[ni] = (uint32_t)(((cbase + 2 * (ni & 1)) ^ kk) << 4);
+    }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int row = 16 * (4 * wm + (mi >> 1)) + 2 * m + (mi & 1);
+      aoff[mi] = (uint32_t)(row * 128 + (kk & 1) * 8);
+      axr[mi] = (uint32_t)(row & 7);
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int row = 16 * (2 * wn + (ni >> 1)) + 2 * m + (ni & 1);
+      boff[ni] = (uint32_t)(row * 128 + (kk & 1) * 8);
+      bxr[ni] = (uint32_t)(row & 7);
+    }
+  }
+
+  for (long long c = c_begin; c < c_end; ++c) {
+    const long long cl = c - c_begin;
+    const int s = (int)(cl % kGStages);
+    const uint32_t ph = (uint32_t)((cl / kGStages) & 1);
+    mbar_wait(sBar + s * 8, ph);
+    const uint32_t sA = sbase + s * 2 * kGTileBytes, sB = diag ? sA : sA + kGTileBytes;
+#pragma unroll
+    for (int t = 0; t < kBK / 4; ++t) {
+      double a[8], b[4];
+      if (L == 0) {
+        const uint32_t rowoff = (uint32_t)(t * 512), flip = (uint32_t)((t & 1) << 6);
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = lds_f64(sA + aoff[mi] + rowoff + (axr[mi] ^ flip));
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(sB + boff[ni] + rowoff + (bxr[ni] ^ flip));
+      } else {
+        const uint32_t hoff = (uint32_t)((t >> 2) * 16384);
+        const uint32_t chunk = (uint32_t)((t & 3) * 2 + (kk >> 1));
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = lds_f64(sA + hoff + aoff[mi] + ((chunk ^ axr[mi]) << 4));
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(sB + hoff + boff[ni] + ((chunk ^ bxr[ni]) << 4));
+      }
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sBar + (kGStages + s) * 8);
+  }
+
+  double* P = g.P + (long long)blockIdx.z * g.n * g.n;
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    long long row;
+    if (L == 0) {
+      const int cbase = ((m >> 1) & 1) * 4 + (m >> 2);
+      row = a0 + 16 * (4 * wm + (mi >> 1)) + 2 * (cbase + 2 * (mi & 1)) + (m & 1);
+    } else {
+      row = a0 + 16 * (4 * wm + (mi >> 1)) + 2 * m + (mi & 1);
+    }
+    if (row >= g.n) continue;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nn = 2 * kk + e;   // column index inside the DMMA block
+        long long col;
+        if (L == 0) {
+          const int cb = ((nn >> 1) & 1) * 4 + (nn >> 2);
+          col = b0 + 16 * (2 * wn + (ni >> 1)) + 2 * (cb + 2 * (ni & 1)) + (nn & 1);
+        } else {
+          col = b0 + 16 * (2 * wn + (ni >> 1)) + 2 * nn + (ni & 1);
+        }
+        if (col < g.n) P[row + g.n * col] = acc[mi][ni][e];
+      }
+  }
+}
+
 // Y(a,b) = Y(b,a) = sum over splits (fixed order) of the upper-triangle partials
 __global__ void gram_reduce_mirror_kernel(const double* __restrict__ P, int splits, long long n, double* __restrict__ Y,
                                           int accumulate) {
@@ -180,8 +363,26 @@ GramPlan plan_gram(const UnfoldSpec& s) {
   p.nchunks = std::max<long long>(p.nchunks, 1);
   const long long active = p.T * (p.T + 1) / 2;
   long long splits = std::max<long long>(1, ceil_div(2 * 148, active));
-  splits = std::min(splits, std::max<long long>(1, p.nchunks / 8));         // at least 8 chunks per split
   const long long cap = std::max<long long>(1, (1LL << 28) / std::max<long long>(s.n * s.n, 1));  // <= 2 GB of partials
+  if (p.bmt == 128) {
+    // TMA kernel: one CTA per SM, so the pass lasts ceil(active * splits / 148) / splits tile-times.  Take the smallest
+    // split count whose last wave is (nearly) as full as the best one's (n = 4096: 528 tiles -> 3.57 waves rounded up
+    // to 4 with one split, 17.8 -> 18 with five).
+    const long long smax = std::max<long long>(1, std::min<long long>({p.nchunks / 8, cap, 64LL}));
+    double best = 0.0;
+    for (long long q = 1; q <= smax; ++q) {
+      const double w = (double)(active * q) / 148.0;
+      best = std::max(best, w / std::ceil(w));
+    }
+    for (long long q = 1; q <= smax; ++q) {
+      const double w = (double)(active * q) / 148.0;
+      if (w / std::ceil(w) >= best - 0.01) {
+        splits = q;
+        break;
+      }
+    }
+  }
+  splits = std::min(splits, std::max<long long>(1, p.nchunks / 8));         // at least 8 chunks per split
   splits = std::min({splits, cap, (long long)65535});
   p.cps = ceil_div(p.nchunks, splits);
   p.splits = (int)ceil_div(p.nchunks, p.cps);
@@ -301,7 +502,37 @@ int unfold_gram(const UnfoldSpec& s, double* Y, double* work, cudaStream_t st, b
   g.cpi = std::max<long long>(p.cpi, 1);
   g.P = work;
   if (p.T > 65535) throw CudaError(2, "nvecs: mode too long for an explicit Gram matrix");
-  if (s.layout == 0) {
+  if (p.bmt == 128) {
+    // TMA-fed kernel: tensor map of the unfolding view
+    CUtensorMap map;
+    GramTmaArgs ga{};
+    ga.n = s.n;
+    ga.nchunks = p.nchunks;
+    ga.cps = p.cps;
+    ga.cpi = std::max<long long>(p.cpi, 1);
+    ga.P = work;
+    ga.a_dim = 1;
+    dim3 grid((unsigned)p.T, (unsigned)p.T, (unsigned)p.splits);
+    if (s.layout == 0) {
+      const uint64_t dims[3] = {(uint64_t)s.n, (uint64_t)s.ncols, 1};
+      const uint64_t str[2] = {(uint64_t)s.ld * 8, (uint64_t)s.ld * 8 * (uint64_t)s.ncols};
+      const uint32_t box[3] = {16, 32, 1};
+      encode_map3(&map, s.X, dims, str, box);
+      ensure_dynamic_smem(reinterpret_cast<const void*>(unfold_gram_tma_kernel<0>), kGSmem, 0);
+      unfold_gram_tma_kernel<0><<<grid, kGThreads, kGSmem, st>>>(map, ga);
+    } else {
+      // dimensions in storage order: the smaller stride first
+      const bool a_first = (s.nb <= 1) || (s.cs <= s.bs);
+      ga.a_dim = a_first ? 1 : 2;
+      const uint64_t dims[3] = {(uint64_t)s.I, (uint64_t)(a_first ? s.n : s.nb), (uint64_t)(a_first ? std::max<long long>(s.nb, 1) : s.n)};
+      const uint64_t str[2] = {(uint64_t)(a_first ? s.cs : s.bs) * 8, (uint64_t)(a_first ? std::max<long long>(s.bs, s.cs * s.n) : s.cs) * 8};
+      const uint32_t box[3] = {16, a_first ? 128u : 1u, a_first ? 1u : 128u};
+      encode_map3(&map, s.X, dims, str, box);
+      ensure_dynamic_smem(reinterpret_cast<const void*>(unfold_gram_tma_kernel<1>), kGSmem, 0);
+      unfold_gram_tma_kernel<1><<<grid, kGThreads, kGSmem, st>>>(map, ga);
+    }
+    AO_CHECK_LAUNCH();
+  } else if (s.layout == 0) {
     if (p.bmt == 128) launch_gram<0, 128>(g, p, st);
     else if (p.bmt == 64) launch_gram<0, 64>(g, p, st);
     else launch_gram<0, 32>(g, p, st);

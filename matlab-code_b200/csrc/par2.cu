@@ -723,8 +723,12 @@ __global__ void __launch_bounds__(32) par2_B_step1_reg_kernel(Par2Layout L, Par2
       double cs = 1.0, sn = 0.0, nal = al, nbe = be;
       int r1 = 0;
       if (g * g > tol2 * (al * be)) {
+        // tan(theta) = 2g / (tau + sign(tau) sqrt(tau^2 + 4g^2)); this chain is the critical path of a round, so the
+        // square root is x * rsqrt(x) and the division a reciprocal (a rotation only has to be orthogonal to rounding,
+        // which cos = rsqrt(1 + tan^2), sin = cos * tan is for any tan)
         const double tau = be - al, g2 = 2.0 * g;
-        const double t = g2 / (tau + copysign(sqrt(fma(tau, tau, g2 * g2)), tau));
+        const double x2 = fma(tau, tau, g2 * g2);
+        const double t = g2 * __drcp_rn(tau + copysign(x2 * rsqrt(x2), tau));
         cs = rsqrt(fma(t, t, 1.0));
         sn = cs * t;
         nal = al - t * g;

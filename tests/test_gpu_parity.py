@@ -699,7 +699,10 @@ def _nvecs_close(Ud, Uo, Z=None, n=None, tol=1e-8):
 
 @pytest.mark.parametrize('shape,R', [((30, 20, 25), 3), ((33, 65, 17), 4), ((130, 90, 70), 5), ((300, 40, 9), 6),
                                      ((8, 9, 10), 8), ((7, 6, 5, 4), 2), ((20, 12, 6, 10, 5), 3), ((64, 50), 4),
-                                     ((131, 259), 7)])
+                                     ((131, 259), 7),
+                                     # long modes (n > 256) in every position: the TMA-fed Gram kernel, partial tiles,
+                                     # a contiguous extent shorter than one TMA box (10 < 16), both map orientations
+                                     ((36, 50, 300), 4), ((10, 301, 7, 9), 3), ((45, 290, 33), 5), ((257, 31, 29), 3)])
 def test_nvecs_matches_oracle_every_mode(ab, shape, R):
     """Leading eigenvectors of X_(n) X_(n)' from the resident object, every mode position of 2..5-way objects (odd
     sizes: padded leading dimension, partial tiles), against numpy eigh of the explicit unfolding."""
