@@ -13,6 +13,7 @@
 //        [4] sum_observed (x-m)^2
 // A PARAFAC2 object is the K = 1 case on the stacked I x Jtot matrix with Fj(j,:) = B(j,:) .* C(seg(j),:).
 #include "em.cuh"
+#include "mttkrp.cuh"
 
 #include <algorithm>
 
@@ -28,6 +29,21 @@ constexpr int kRC = 32;          // rank chunk staged per pass
 constexpr int kPitch = kTile + 4;  // smem row pitch: the 4 x 8 fragment footprint of a DMMA operand hits 32 distinct banks
 
 constexpr int kMP = kTile + 2;     // pitch of the model tile: C-fragment stores and 16-byte row reads are conflict-free
+
+// running sums of one element: observed -> [2] += x m, [3] += m^2 (, [4] += (x-m)^2);  missing -> [0] += (m-x)^2,
+// [1] += x^2.  Written as two predicated groups (no selects: the FP64 pipe is shared with the DMMAs, and every select
+// of a double is two more instructions on an issue-bound path).
+__device__ __forceinline__ void em_accumulate4(double x, double m, bool observed, double& s0, double& s1, double& s2,
+                                               double& s3) {
+  const double d = m - x;
+  if (observed) {
+    s2 = fma(x, m, s2);
+    s3 = fma(m, m, s3);
+  } else {
+    s0 = fma(d, d, s0);
+    s1 = fma(x, x, s1);
+  }
+}
 
 // The model of slab k is a rank-R GEMM, M_k = (Fi diag(Fk(k,:))) * Fj': it runs on the FP64 tensor cores like the
 // MTTKRP (mma.m8n8k4, SASS DMMA.8x8x4).  CTA tile 64 (i) x 32 (j), 4 warps along i, warp tile 16 x 32 =
@@ -64,7 +80,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     double x0[8], x1[8];
-    unsigned mk[8];   // bit 0 / bit 8: element 0 / 1 observed; 0xFFFF0000: column outside the object
+    unsigned mk[8];   // byte 0 / byte 1: rows 2l / 2l+1 observed (non-zero); outside the object: "observed", data 0
     {
       const long long colbase = ie + a.ldI * (j0 + 8 * warp + (long long)a.J * k);
 #pragma unroll
@@ -72,7 +88,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
         const long long idx = colbase + a.ldI * c;
         const bool col_ok = (j0 + 8 * warp + c < a.J);
         x0[c] = x1[c] = 0.0;
-        mk[c] = 0xFFFF0000u;
+        mk[c] = 0x0101u;
         if (col_ok && nrow == 2) {   // idx is even (ldI and ie are): 16-byte / 2-byte aligned vector loads
           const double2 xv = *reinterpret_cast<const double2*>(a.X + idx);
           const unsigned short mv = *reinterpret_cast<const unsigned short*>(a.mask + idx);
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
           mk[c] = mv;
         } else if (col_ok && nrow == 1) {
           x0[c] = a.X[idx];
-          mk[c] = 0x0000FF00u | a.mask[idx];   // second row outside: marked neither observed nor missing below
+          mk[c] = 0x0100u | a.mask[idx];   // second row outside
         }
       }
     }
@@ -130,29 +146,19 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const double2 mv = *reinterpret_cast<const double2*>(&Ms[(8 * warp + c) * kMP + 2 * lane]);
-        const unsigned m16 = mk[c];
-        const bool in0 = (m16 >> 16) == 0, in1 = in0 && ((m16 & 0xFF00u) != 0xFF00u || nrow == 2);
-        // branch-free sums; only the store of an imputed value is predicated
-        const bool ob0 = in0 && (m16 & 0xFFu) != 0, ob1 = in1 && (m16 & 0xFF00u) != 0;
-        const bool mi0 = in0 && !ob0, mi1 = in1 && !ob1;
-        const double xo0 = ob0 ? x0[c] : 0.0, mo0 = ob0 ? mv.x : 0.0, xo1 = ob1 ? x1[c] : 0.0, mo1 = ob1 ? mv.y : 0.0;
-        const double xm0 = mi0 ? x0[c] : 0.0, mm0 = mi0 ? mv.x : 0.0, xm1 = mi1 ? x1[c] : 0.0, mm1 = mi1 ? mv.y : 0.0;
-        s[2] = fma(xo0, mo0, s[2]);
-        s[2] = fma(xo1, mo1, s[2]);
-        s[3] = fma(mo0, mo0, s[3]);
-        s[3] = fma(mo1, mo1, s[3]);
-        const double do0 = xo0 - mo0, do1 = xo1 - mo1;
-        s[4] = fma(do0, do0, s[4]);
-        s[4] = fma(do1, do1, s[4]);
-        const double dm0 = mm0 - xm0, dm1 = mm1 - xm1;
-        s[0] = fma(dm0, dm0, s[0]);
-        s[0] = fma(dm1, dm1, s[0]);
-        s[1] = fma(xm0, xm0, s[1]);
-        s[1] = fma(xm1, xm1, s[1]);
+        // outside the object data and model are both 0 (zero-padded factor tiles): no special case in the sums
+        const bool ob0 = (mk[c] & 0xFFu) != 0, ob1 = (mk[c] & 0xFF00u) != 0;
+        em_accumulate4(x0[c], mv.x, ob0, s[0], s[1], s[2], s[3]);
+        em_accumulate4(x1[c], mv.y, ob1, s[0], s[1], s[2], s[3]);
+        if (a.Fk == nullptr) {   // PARAFAC2 / matrix objects: the direct residual of :1249-1252
+          const double d0 = x0[c] - mv.x, d1 = x1[c] - mv.y;
+          if (ob0) s[4] = fma(d0, d0, s[4]);
+          if (ob1) s[4] = fma(d1, d1, s[4]);
+        }
         if (a.impute) {
           const long long idx = colbase + a.ldI * c;
-          if (mi0) a.X[idx] = mv.x;
-          if (mi1) a.X[idx + 1] = mv.y;
+          if (!ob0) a.X[idx] = mv.x;
+          if (!ob1) a.X[idx + 1] = mv.y;
         }
       }
     }
@@ -162,6 +168,260 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_kernel(EmArgs a, int kper) {
   for (int t = 0; t < 5; ++t) {
     const double v = block_sum(s[t], red);
     if (tid == 0) a.partials[cta * 5 + t] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined version for objects with many slabs (K >= 8, R <= 128): one persistent-style CTA per SM walks the slabs
+// k of its (i-tile, j-tile) column, with the three phases of a slab on different warps so that they overlap ACROSS
+// slabs instead of alternating inside a CTA (the kernel above keeps the FP64 pipe - DMMA and the epilogue's DFMAs
+// share it - busy only 52 % of the time: profiles/r02_ncu_em_v4_summary.md):
+//   warp 16     producer: TMA box load of the 64 x 32 data tile of slab k (dense, zero fill outside) and a bulk copy
+//               of row k of the transposed third factor into a 4-stage ring;
+//   warps 0-7   model GEMM of slab k on DMMA (16 x 16 each; two such warps per scheduler, one warp alone issues a
+//               DMMA only every ~32 cycles: profiles/r02_ncu_em_v4_summary.md) from the factor tiles staged once per
+//               CTA - for R <= 32 held as register fragments for the whole slab range - scaled by the ring's Fk row,
+//               written to one of two model tiles in shared memory;
+//   warps 8-15  comparison of model tile and data tile in the data layout (4 columns each, lane l rows 2l, 2l+1),
+//               mask bytes prefetched one slab ahead from global memory (the mask's row stride is not TMA-aligned),
+//               imputed values stored straight to global memory, four running sums.
+// mbarriers: xfull / xempty per ring stage (expect_tx; 16 consumer-warp arrivals), mfull / mempty per model tile.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPStages = 4;
+constexpr int kPXBytes = kTile * kTJ * 8;      // 16 KB data tile
+constexpr int kPBPitch = kTJ + 4;              // Fj tile pitch
+constexpr int kPMmaWarps = 8, kPEpiWarps = 8;
+constexpr int kPEC = kTJ / kPEpiWarps;         // columns of a comparison warp
+constexpr int kPThreads = (kPMmaWarps + kPEpiWarps + 1) * 32;
+constexpr int kPRegKs = 8;                     // R <= 32: the GEMM warps keep their operand fragments in registers
+constexpr int kPMaxR = 128;
+
+struct EmPipeLayout {
+  int Rp, offA, offB, offX, offC, offM, offBar, bytes;
+};
+__host__ __device__ inline EmPipeLayout em_pipe_layout(int R) {
+  EmPipeLayout l;
+  l.Rp = (R + 3) / 4 * 4;
+  l.offX = 0;                                         // 1024-aligned: TMA destinations
+  l.offC = l.offX + kPStages * kPXBytes;
+  l.offA = l.offC + kPStages * l.Rp * 8;
+  l.offB = l.offA + l.Rp * kPitch * 8;
+  l.offM = l.offB + l.Rp * kPBPitch * 8;
+  l.offBar = l.offM + 2 * kTJ * kMP * 8;
+  l.bytes = l.offBar + (2 * kPStages + 4) * 8 + 1024;
+  return l;
+}
+
+template <bool REGS>
+__global__ void __launch_bounds__(kPThreads, 1) em_pipe_kernel(const __grid_constant__ CUtensorMap xmap, EmArgs a, int kper) {
+  extern __shared__ uint8_t em_raw[];
+  const EmPipeLayout L = em_pipe_layout(a.R);
+  const uint32_t sbase = (smem_u32(em_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = em_raw + (sbase - smem_u32(em_raw));
+  const uint32_t sX = sbase + L.offX, sC = sbase + L.offC, sBar = sbase + L.offBar;
+  double* As = reinterpret_cast<double*>(gbase + L.offA);   // [Rp][kPitch]
+  double* Bs = reinterpret_cast<double*>(gbase + L.offB);   // [Rp][kPBPitch]
+  double* Ms = reinterpret_cast<double*>(gbase + L.offM);   // 2 x [kTJ][kMP]
+  const double* Xs = reinterpret_cast<const double*>(gbase + L.offX);
+  const double* Cs = reinterpret_cast<const double*>(gbase + L.offC);
+  __shared__ double red[kPEpiWarps][4];
+  const uint32_t xfull = sBar, xempty = sBar + kPStages * 8, mfull = sBar + 2 * kPStages * 8, mempty = mfull + 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long i0 = (long long)blockIdx.x * kTile, j0 = (long long)blockIdx.y * kTJ;
+  const int k0 = blockIdx.z * kper, k1 = min(a.K, k0 + kper);
+  const int Rp = L.Rp;
+
+  if (tid == 0) {
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(xfull + s * 8, 1);
+      mbar_init(xempty + s * 8, kPMmaWarps + kPEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(mfull + b * 8, kPMmaWarps);
+      mbar_init(mempty + b * 8, kPEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  for (int e = tid; e < Rp * kTile; e += kPThreads) {
+    const int ii = e % kTile, r = e / kTile;
+    As[r * kPitch + ii] = (r < a.R && i0 + ii < a.I) ? a.Fi[i0 + ii + (long long)r * a.ldFi] : 0.0;
+    if (ii < kTJ) Bs[r * kPBPitch + ii] = (r < a.R && j0 + ii < a.J) ? a.Fj[j0 + ii + (long long)r * a.ldFj] : 0.0;
+  }
+  __syncthreads();
+
+  if (warp == kPMmaWarps + kPEpiWarps) {
+    if (lane == 0) {
+      prefetch_tensormap(&xmap);
+      for (int k = k0; k < k1; ++k) {
+        const int kl = k - k0, s = kl % kPStages;
+        mbar_wait(xempty + s * 8, (uint32_t)(((kl / kPStages) & 1) ^ 1));
+        mbar_expect_tx(xfull + s * 8, kPXBytes + Rp * 8);
+        tma_load_3d(sX + s * kPXBytes, &xmap, (int)i0, (int)j0, k, xfull + s * 8);
+        bulk_load_1d(sC + s * Rp * 8, a.fkT + (long long)k * Rp, Rp * 8, xfull + s * 8);
+      }
+    }
+    return;
+  }
+
+  if (warp < kPMmaWarps) {
+    // ===== model GEMM: 16 x 16 block (rows 16*wr, columns 16*wc) of the tile per warp.  One warp issues a DMMA only
+    // every ~32 cycles, the pipe takes one every 16 per scheduler: two GEMM warps per scheduler.  (Measured variants,
+    // 512^3 R = 32: 4 warps of 16 x 32: 0.51 ms; 8 of 16 x 16: 0.45; 16 of 8 x 16: 0.48; 8 of 8 x 32 with the producer
+    // folded into a comparison warp: 0.50.) =====
+    const int q = lane & 3, p = lane >> 2, wr = warp & 3, wc = warp >> 2;
+    const double* Ap = As + q * kPitch + 16 * wr + p;
+    const double* Bp = Bs + q * kPBPitch + 16 * wc + p;
+    const int nks = Rp / 4;
+    double afr[2][kPRegKs], bfr[2][kPRegKs];
+    if (REGS) {
+      // both operand tiles are the same for every slab: the fragments stay in registers, a slab costs one
+      // shared-memory load (its Fk entry) and two multiplies per rank step
+#pragma unroll
+      for (int ks = 0; ks < kPRegKs; ++ks) {
+        const bool in = ks < nks;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          afr[t][ks] = in ? Ap[4 * ks * kPitch + 8 * t] : 0.0;
+          bfr[t][ks] = in ? Bp[4 * ks * kPBPitch + 8 * t] : 0.0;
+        }
+      }
+    }
+    for (int k = k0; k < k1; ++k) {
+      const int kl = k - k0, s = kl % kPStages, b = kl & 1;
+      double acc[2][2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      mbar_wait(xfull + s * 8, (uint32_t)((kl / kPStages) & 1));
+      const double* cs = Cs + s * Rp + q;
+      if (REGS) {
+#pragma unroll
+        for (int ks = 0; ks < kPRegKs; ++ks) {
+          const double ck = (ks < nks) ? cs[4 * ks] : 0.0;
+          const double a0 = afr[0][ks] * ck, a1 = afr[1][ks] * ck;
+          dmma884(acc[0][0][0], acc[0][0][1], a0, bfr[0][ks]);
+          dmma884(acc[0][1][0], acc[0][1][1], a0, bfr[1][ks]);
+          dmma884(acc[1][0][0], acc[1][0][1], a1, bfr[0][ks]);
+          dmma884(acc[1][1][0], acc[1][1][1], a1, bfr[1][ks]);
+        }
+      } else {
+#pragma unroll 4
+        for (int ks = 0; ks < nks; ++ks) {
+          const double ck = cs[4 * ks];
+          const double a0 = Ap[4 * ks * kPitch] * ck, a1 = Ap[4 * ks * kPitch + 8] * ck;
+          const double b0 = Bp[4 * ks * kPBPitch], b1 = Bp[4 * ks * kPBPitch + 8];
+          dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+          dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+          dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+          dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+      }
+      mbar_wait(mempty + b * 8, (uint32_t)(((kl >> 1) & 1) ^ 1));
+      // accumulator (mt, nt, e) of this lane is model element (i = 16 wr + 8 mt + p, j = 16 wc + 8 nt + 2 q + e)
+      double* M = Ms + b * kTJ * kMP + (16 * wc + 2 * q) * kMP + 16 * wr + p;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          M[(8 * nt) * kMP + 8 * mt] = acc[mt][nt][0];
+          M[(8 * nt + 1) * kMP + 8 * mt] = acc[mt][nt][1];
+        }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(mfull + b * 8);
+        mbar_arrive(xempty + s * 8);
+      }
+    }
+    return;
+  }
+
+  // ===== comparison: columns kPEC*ew .. +kPEC-1, lane l rows 2l, 2l+1 =====
+  // The FP64 pipe is shared with the DMMAs of the two GEMM warps on the same scheduler and serves the ready warps in
+  // turn, so a comparison warp gets roughly one FP64 instruction per ~35 cycles: the sums are spread over eight warps
+  // (two per scheduler) to keep the per-slab time of a comparison warp below that of the GEMM.
+  const int ew = warp - kPMmaWarps;
+  const long long ie = i0 + 2 * lane;
+  const int nrow = (ie + 1 < a.I) ? 2 : ((ie < a.I) ? 1 : 0);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  // Elements outside the object need no special case in the sums: TMA zero-fills the data tile and the zero-padded
+  // factor tiles make the model 0 there, so every product is 0; their mask word is "observed", which suppresses the
+  // store.  Mask word of a column: byte 0 / byte 1 = rows 2l / 2l+1 (non-zero = observed).
+  unsigned mk[kPEC], mkn[kPEC];
+  const int ncol = (int)max(0LL, min((long long)kPEC, a.J - (j0 + kPEC * ew)));   // columns of this warp inside the object
+  auto load_mask = [&](int k, unsigned (&m)[kPEC]) {
+    const uint8_t* mp = a.mask + (ie + a.ldI * (j0 + kPEC * ew + (long long)a.J * k));
+#pragma unroll
+    for (int c = 0; c < kPEC; ++c) {
+      unsigned v = 0x0101u;
+      if (c < ncol) {
+        if (nrow == 2) v = *reinterpret_cast<const unsigned short*>(mp);   // ie and ldI are even: 2-byte aligned
+        else if (nrow == 1) v = 0x0100u | *mp;
+      }
+      m[c] = v;
+      mp += a.ldI;
+    }
+  };
+  if (k0 < k1) load_mask(k0, mkn);
+  for (int k = k0; k < k1; ++k) {
+    const int kl = k - k0, s = kl % kPStages, b = kl & 1;
+#pragma unroll
+    for (int c = 0; c < kPEC; ++c) mk[c] = mkn[c];
+    if (k + 1 < k1) load_mask(k + 1, mkn);
+    mbar_wait(xfull + s * 8, (uint32_t)((kl / kPStages) & 1));
+    mbar_wait(mfull + b * 8, (uint32_t)((kl >> 1) & 1));
+    const double* M = Ms + b * kTJ * kMP + kPEC * ew * kMP + 2 * lane;
+    const double* X = Xs + s * (kPXBytes / 8) + kPEC * ew * kTile + 2 * lane;
+    double* xp = a.X + (ie + a.ldI * (j0 + kPEC * ew + (long long)a.J * k));
+#pragma unroll
+    for (int c = 0; c < kPEC; ++c) {
+      const double2 mv = *reinterpret_cast<const double2*>(M + c * kMP);
+      const double2 xv = *reinterpret_cast<const double2*>(X + c * kTile);
+      const bool ob0 = (mk[c] & 0xFFu) != 0, ob1 = (mk[c] & 0xFF00u) != 0;
+      em_accumulate4(xv.x, mv.x, ob0, s0, s1, s2, s3);
+      em_accumulate4(xv.y, mv.y, ob1, s0, s1, s2, s3);
+      if (a.impute) {
+        if (!ob0) xp[0] = mv.x;
+        if (!ob1) xp[1] = mv.y;
+      }
+      xp += a.ldI;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(mempty + b * 8);
+      mbar_arrive(xempty + s * 8);
+    }
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  s3 = warp_sum(s3);
+  if (lane == 0) {
+    red[ew][0] = s0;
+    red[ew][1] = s1;
+    red[ew][2] = s2;
+    red[ew][3] = s3;
+  }
+  named_bar_sync(1, kPEpiWarps * 32);   // the comparison warps
+  if (ew == 0 && lane < 5) {
+    const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    double v = 0.0;
+    if (lane < 4) {
+#pragma unroll
+      for (int w = 0; w < kPEpiWarps; ++w) v += red[w][lane];   // fixed order
+    }
+    a.partials[cta * 5 + lane] = v;
+  }
+}
+
+// fkT[r + Rp*k] = Fk(k, r), zero for R <= r < Rp: row k of the third factor as one aligned bulk copy
+__global__ void em_transpose_fk_kernel(const double* __restrict__ Fk, long long ldFk, int K, int R, int Rp,
+                                       double* __restrict__ out) {
+  const long long n = (long long)K * Rp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % Rp);
+    const long long k = idx / Rp;
+    out[idx] = (r < R) ? Fk[k + (long long)r * ldFk] : 0.0;
   }
 }
 
@@ -233,19 +493,71 @@ void em_grid(const EmArgs& a, dim3& grid, int& kper) {
   grid = dim3((unsigned)ti, (unsigned)tj, (unsigned)kz);
 }
 
+// pipelined kernel: one CTA per SM, a CTA's work is kper slabs (+ about two slab-times of prologue: factor tiles, ring
+// fill) - pick the slab split whose waves of 148 CTAs finish first
+void em_pipe_grid(const EmArgs& a, dim3& grid, int& kper) {
+  const long long ti = ceil_div(a.I, kTile), tj = ceil_div(a.J, kTJ), tiles = ti * tj;
+  long long best_kz = 1;
+  double best_cost = 1e300;
+  for (long long kz = 1; kz <= std::min<long long>(a.K, 65535); ++kz) {
+    const long long kp = ceil_div(a.K, kz), kzz = ceil_div(a.K, kp);
+    if (kzz != kz) continue;
+    const double cost = (double)ceil_div(tiles * kz, 148) * ((double)kp + 2.0);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best_kz = kz;
+    }
+  }
+  kper = (int)ceil_div(a.K, best_kz);
+  grid = dim3((unsigned)ti, (unsigned)tj, (unsigned)ceil_div(a.K, kper));
+}
+
+bool em_use_pipe(const EmArgs& a) {
+  return a.Fk != nullptr && a.fkT != nullptr && a.K >= 8 && a.R <= kPMaxR && (a.ldI & 1) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.X) & 15) == 0 && ceil_div(a.J, kTJ) <= 65535;
+}
+
 }  // namespace
 
 size_t em_partials_doubles(const EmArgs& a) {
   dim3 g;
   int kper;
   em_grid(a, g, kper);
-  return (size_t)g.x * g.y * g.z * 5;
+  size_t n = (size_t)g.x * g.y * g.z * 5;
+  if (a.K >= 8) {
+    em_pipe_grid(a, g, kper);
+    n = std::max(n, (size_t)g.x * g.y * g.z * 5);
+  }
+  return n;
 }
 
 int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st) {
   if (a.I <= 0 || a.J <= 0 || a.K <= 0) return 0;
   dim3 g;
   int kper;
+  if (em_use_pipe(a)) {
+    em_pipe_grid(a, g, kper);
+    const EmPipeLayout L = em_pipe_layout(a.R);
+    CUtensorMap xmap;
+    const uint64_t dims[3] = {(uint64_t)a.I, (uint64_t)a.J, (uint64_t)a.K};
+    const uint64_t str[2] = {(uint64_t)a.ldI * 8, (uint64_t)a.ldI * (uint64_t)a.J * 8};
+    const uint32_t box[3] = {(uint32_t)kTile, (uint32_t)kTJ, 1};
+    encode_map3(&xmap, a.X, dims, str, box, false);
+    const unsigned tb = (unsigned)std::min<long long>(ceil_div((long long)a.K * L.Rp, 256), 148 * 8);
+    em_transpose_fk_kernel<<<tb, 256, 0, st>>>(a.Fk, a.ldFk, a.K, a.R, L.Rp, a.fkT);
+    AO_CHECK_LAUNCH();
+    if (L.Rp <= 4 * kPRegKs) {
+      ensure_dynamic_smem(reinterpret_cast<const void*>(em_pipe_kernel<true>), (size_t)L.bytes, 0);
+      em_pipe_kernel<true><<<g, kPThreads, (size_t)L.bytes, st>>>(xmap, a, kper);
+    } else {
+      ensure_dynamic_smem(reinterpret_cast<const void*>(em_pipe_kernel<false>), (size_t)L.bytes, 0);
+      em_pipe_kernel<false><<<g, kPThreads, (size_t)L.bytes, st>>>(xmap, a, kper);
+    }
+    AO_CHECK_LAUNCH();
+    em_reduce_kernel<<<1, 256, 0, st>>>(a.partials, (long long)g.x * g.y * g.z, sums_out);
+    AO_CHECK_LAUNCH();
+    return 3;
+  }
   em_grid(a, g, kper);
   if (g.y > 65535) throw CudaError(2, "EM imputation: object too wide");
   constexpr size_t kEmSmem = (size_t)(kTJ * kMP + 2 * kRC * kPitch + kRC) * sizeof(double);

@@ -19,7 +19,9 @@ struct EmArgs {
   int R;
   int impute;              // 0: only the sums (iteration-0 objective)
   double* partials;        // >= em_partials_doubles(args)
+  double* fkT = nullptr;   // optional scratch, >= em_fkT_doubles(K, R): enables the pipelined kernel for K >= 8
 };
+inline size_t em_fkT_doubles(long long K, int R) { return (size_t)K * (size_t)((R + 3) / 4 * 4); }
 
 // Khatri-Rao product of the trailing factors of an N-way (N > 3) object, first factor fastest:
 //   out(k, r) = prod_q F_q(k_q, r),  k = k_0 + d_0*(k_1 + d_1*(...)),  out: K x R (ld = K), K = prod d_q
@@ -34,6 +36,8 @@ int em_khatri_rao(const KrArgs& a, double* out, long long K, int R, cudaStream_t
 
 size_t em_partials_doubles(const EmArgs& a);
 // sums_out[0..4] = sum_missing (m-x)^2, sum_missing x^2, sum_observed x*m, sum_observed m^2, sum_observed (x-m)^2
+// ([4] is the PARAFAC2 objective (:1249-1252) and is only evaluated for objects without a third factor, Fk == nullptr;
+// objects with a third factor report 0 there - their objective uses [2] and [3], :1224-1226)
 int em_pass(const EmArgs& a, double* sums_out, cudaStream_t st);
 
 // *out = sum of squares of the elements (i < I of every column of length ld, `slab` columns) with mask != 0

@@ -773,6 +773,7 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
         if (kk > 0x7fffffffLL) throw CudaError(2, "missing data: trailing extent too large");
         a.K = (int)kk;
         if (o.order > 3) AO_CUDA(cudaMalloc(&o.em_kr, std::max<size_t>((size_t)kk * a.R * sizeof(double), 256)));
+        if (o.order >= 3) AO_CUDA(cudaMalloc(&o.em_fkT, std::max<size_t>(em_fkT_doubles(kk, a.R) * sizeof(double), 256)));
       }
       need = std::max(need, em_partials_doubles(a));
     }
@@ -820,6 +821,7 @@ void Engine::release() {
     dfree(o.Tbuf);
     dfree(o.mask);
     dfree(o.em_kr);
+    dfree(o.em_fkT);
     for (auto& v : o.views) {
       if (v.f0_own) packed_factor_free(v.f0);
       if (v.f1_own) packed_factor_free(v.f1);
@@ -1622,6 +1624,7 @@ void Engine::em_step(bool impute) {
         a.K = 1;
         a.Fk = nullptr;
       }
+      a.fkT = o.em_fkT;
       launches_ += em_pass(a, em_sums_ + 5 * p, st_);
       if (o.sharded) allreduce(em_sums_ + 5 * p, 5);
       if (impute) o.T_version = 0;

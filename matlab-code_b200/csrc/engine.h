@@ -162,6 +162,7 @@ struct ObjectState {
   int last_m = 0;             // global id of the mode updated last in a sweep (static)
   uint8_t* mask = nullptr;    // Z.miss{p}: 1 = observed, 0 = missing, same indexing as data (nullptr: complete data)
   double* em_kr = nullptr;    // masked objects of order > 3: Khatri-Rao product of the factors of modes 3..N
+  double* em_fkT = nullptr;   // masked objects of order >= 3: transposed third factor for the pipelined EM kernel
   double* Tbuf = nullptr;     // dimension tree: T(j,k,r) = sum_i X(i,j,k) F1(i,r), emitted by the mode-2 MTTKRP
   uint64_t T_version = 0;     // version of the mode-1 factor T was computed from (0 = invalid)
 };

@@ -668,13 +668,13 @@ void encode_map(CUtensorMap* map, const double* X, int64_t I, int64_t J, int64_t
 
 // generic 3-D FP64 tensor map with 128-byte swizzle (box[0] must be 16 doubles); used by the unfolding Gram kernel
 void encode_map3(CUtensorMap* map, const double* X, const uint64_t dims[3], const uint64_t strides_bytes[2],
-                 const uint32_t box[3]) {
+                 const uint32_t box[3], bool swizzle128) {
   cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
   cuuint64_t sb[2] = {strides_bytes[0], strides_bytes[1]};
   cuuint32_t bx[3] = {box[0], box[1], box[2]};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), d, sb, bx, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw CudaError(5, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " for a " +

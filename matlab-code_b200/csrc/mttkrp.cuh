@@ -39,9 +39,10 @@ struct MttkrpWorkspace {
 };
 
 void make_tensor3(Tensor3& t, const double* X, int64_t I, int64_t J, int64_t K, int64_t ldI);
-// generic 3-D FP64 tensor map, 128-byte swizzle: dims (dims[0] contiguous), byte strides of dims 1 and 2, box (box[0] = 16)
+// generic 3-D FP64 tensor map: dims (dims[0] contiguous), byte strides of dims 1 and 2, box; with the 128-byte swizzle
+// (box[0] = 16 doubles) or as a plain dense box
 void encode_map3(CUtensorMap* map, const double* X, const uint64_t dims[3], const uint64_t strides_bytes[2],
-                 const uint32_t box[3]);
+                 const uint32_t box[3], bool swizzle128 = true);
 
 // allocate + describe (rows_pad = rows rounded up to 128, plus one extra tile)
 void packed_factor_alloc(PackedFactor& p, int64_t rows, int R);

@@ -477,6 +477,19 @@ def test_em_imputation_large_ranks_and_front_end(ab):
     assert abs(out['f_tensors'] - oo['f_tensors']) < FIT_TOL       # the front end computes the masked Znorm_const
 
 
+@pytest.mark.parametrize('shape,R', [((50, 41, 6), 5), ((72, 70, 12), 70), ((130, 35, 9), 6)])
+def test_em_imputation_kernel_variants(ab, shape, R):
+    """Both EM kernels: fewer than 8 slabs (one CTA per tile and slab range, rank chunks of 32) and the pipelined kernel
+    (TMA data ring + GEMM warps + comparison warps) with a rank that is neither a multiple of 4 nor below 64, partial
+    tiles in both directions."""
+    Z, G, _ = pg.config_cp_matrix(shape[0], shape[1], shape[2], 60, R, seed=12, noise=0.1)
+    Zm = pg.add_missing(Z, 0.35, seed=6, objects=[0])
+    Go, oo, Gd, od = _both(ab, Zm, G, pg.default_options(MaxOuterIters=6, **ZERO_TOL))
+    _assert_out_close(od, oo)
+    _assert_missing_close(od, oo)
+    assert_state_close(Gd, Go)
+
+
 def test_znorm_const_computed_on_device(ab):
     """Znorm_const = NaN asks the engine for ||X_p||^2 (observed entries with Z.miss), cmtf_AOADMM.m:124-156."""
     Z, G, _ = pg.config_cp_par2(I=21, J=17, K=13, Jk=11, Kp=6, R=3, seed=6, noise=0.1)
