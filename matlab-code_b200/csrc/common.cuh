@@ -155,6 +155,24 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /* >= 32 d
   }
   return r;
 }
+// Final step of a two-level deterministic reduction, executed by ONE WARP of the last CTA: sum of the n per-CTA
+// partials p[0], p[stride], p[2*stride], ... in a fixed order (lane l takes l, l+32, ...; then the shuffle tree).  A
+// single thread walking the partials pays one L2 round trip per handful of loads - 20 us for 256 CTAs, which was most of
+// an inner ADMM iteration; a warp issues all its loads at once.  Result valid in every lane.
+__device__ __forceinline__ double warp_sum_partials(const double* p, unsigned n, unsigned stride) {
+  const unsigned lane = threadIdx.x & 31;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  unsigned b = lane;
+  // __ldcg: the partials were written by other SMs (and this SM may hold last iteration's lines in L1)
+  for (; b + 96 < n; b += 128) {
+    v0 += __ldcg(p + (size_t)b * stride);
+    v1 += __ldcg(p + (size_t)(b + 32) * stride);
+    v2 += __ldcg(p + (size_t)(b + 64) * stride);
+    v3 += __ldcg(p + (size_t)(b + 96) * stride);
+  }
+  for (; b < n; b += 32) v0 += __ldcg(p + (size_t)b * stride);
+  return warp_sum((v0 + v1) + (v2 + v3));
+}
 #endif
 
 }  // namespace aoadmm

@@ -667,8 +667,8 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
   AO_CUDA(cudaMalloc(&admm_partials_, admm_ws * sizeof(double)));
   AO_CUDA(cudaMalloc(&admm_sums_, (6 * kMaxGroup + 1) * sizeof(double)));
   AO_CUDA(cudaMemset(admm_sums_, 0, (6 * kMaxGroup + 1) * sizeof(double)));
-  AO_CUDA(cudaMalloc(&admm_counter_, sizeof(unsigned)));
-  AO_CUDA(cudaMemset(admm_counter_, 0, sizeof(unsigned)));
+  AO_CUDA(cudaMalloc(&admm_counter_, 2 * sizeof(unsigned)));   // [0] arrival counter, [1] generation of the inner-loop barrier
+  AO_CUDA(cudaMemset(admm_counter_, 0, 2 * sizeof(unsigned)));
   if (prox_bytes > 0) AO_CUDA(cudaMalloc(&prox_scratch_, prox_bytes));
 
   // control blocks: one per mode (a coupled group uses the block of its first mode)

@@ -1158,12 +1158,13 @@ __global__ void __launch_bounds__(256) par2_residual_kernel(Par2Layout L, const 
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && threadIdx.x < 32) {
     __threadfence();
-    double v = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) v += partials[b];
-    *res = v;
-    *counter = 0u;
+    const double v = warp_sum_partials(partials, gridDim.x, 1u);
+    if (threadIdx.x == 0) {
+      *res = v;
+      *counter = 0u;
+    }
   }
 }
 

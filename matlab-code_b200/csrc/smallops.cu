@@ -79,7 +79,7 @@ __global__ void gram_reduce_kernel(const double* __restrict__ ws, int nchunks, i
 // =====================================================================================================
 __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const int* __restrict__ skip) {
   if (skip != nullptr && *skip != 0) return;
-  extern __shared__ double S[];  // R*R when R <= 64, else unused (factorisation runs in global memory)
+  extern __shared__ double S[];  // R*R + R*(R+1) when R <= 64, else unused (factorisation runs in global memory)
   __shared__ double red[32];
   __shared__ double s_rho;
   __shared__ int s_err;
@@ -115,24 +115,47 @@ __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const i
   }
   __syncthreads();
   if (a.do_chol) {
-    // right-looking Cholesky on the lower triangle of W (column-major, ld = R)
+    // Right-looking Cholesky on the lower triangle of W (column-major, ld = R).  The kernel is one CTA walking R
+    // dependent steps, so a step is kept to ONE barrier and no division or square root: 1/sqrt(d) comes from rsqrt
+    // (every thread computes it from the pivot it reads), the trailing update multiplies the still unscaled column by
+    // it on the fly, and the column itself is scaled after the barrier - nothing reads column j again before the
+    // substitution below.  L(i,j) = W(i,j) * rsqrt(d) in both places, so the factor is consistent to the bit.
     for (int j = 0; j < R; ++j) {
       const double d = W[j * R + j];
       if (!(d > 0.0) || !isfinite(d)) {
         if (tid == 0) s_err = 3;
         break;  // uniform: every thread read the same d
       }
-      const double s = sqrt(d);
-      __syncthreads();
-      for (int i = j + 1 + tid; i < R; i += nt) W[j * R + i] = W[j * R + i] / s;
-      if (tid == 0) W[j * R + j] = s;
-      __syncthreads();
+      const double is = rsqrt(d);
       const int n = R - j - 1;
-      for (int e = tid; e < n * n; e += nt) {
-        const int ci = e / n, ri = e % n;  // trailing block column ci, row ri (0-based inside the block)
-        if (ri >= ci) W[(j + 1 + ci) * R + (j + 1 + ri)] -= W[j * R + (j + 1 + ri)] * W[j * R + (j + 1 + ci)];
+      const double* col = W + j * R + j + 1;
+      // trailing block: 64 rows x (nt / 64) columns per pass (shifts and masks only - an integer division per entry
+      // was most of a step)
+      // The entries of a thread are loaded in batches of eight before any is stored: the compiler cannot move a
+      // load above a possibly aliasing store, and one dependent shared-memory round trip per entry was the step time.
+      const int cstep = nt >> 6;
+      for (int ri = tid & 63; ri < n; ri += 64) {
+        const double lr = col[ri] * is;
+        double* wrow = W + (j + 1) * R + (j + 1 + ri);
+        for (int c0 = tid >> 6; c0 <= ri; c0 += 8 * cstep) {
+          double w8[8], l8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ci = c0 + u * cstep;
+            const bool ok = ci <= ri;
+            w8[u] = ok ? wrow[ci * R] : 0.0;
+            l8[u] = ok ? col[ci] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ci = c0 + u * cstep;
+            if (ci <= ri) wrow[ci * R] = w8[u] - lr * (l8[u] * is);
+          }
+        }
       }
       __syncthreads();
+      for (int i = j + 1 + tid; i < R; i += nt) W[j * R + i] *= is;
+      if (tid == 0) W[j * R + j] = d * is;
     }
     __syncthreads();
     for (int e = tid; e < RR; e += nt) {
@@ -143,31 +166,49 @@ __global__ void __launch_bounds__(256, 1) prep_system_kernel(PrepArgs a, const i
     }
     if (a.Binv != nullptr && s_err == 0) {
       // inv(L) by forward substitution on all columns at once: V = I; for every pivot j, row j is divided by L(j,j) and
-      // L(i,j) * row j is subtracted from the rows below.  Each entry sees the same FMAs in the same order as a
-      // column-by-column substitution (bitwise the same result), but a step updates (R-j-1) x (j+1) entries across the
-      // whole CTA instead of R threads walking R^2/2 dependent FMAs.  V(i,c) lives at V[i*R + c] (zeros above the diagonal).
+      // L(i,j) * row j is subtracted from the rows below - again one barrier per step: the rows below use the scaled
+      // row j on the fly (V(j,c) * 1/L(j,j)), row j is scaled in place after the barrier (zeros above the diagonal).
+      // In shared memory V is stored transposed with an odd pitch, V(i,c) at V[c*(R+1) + i]: the substitution runs
+      // with lanes over the rows i, the product below with lanes over the columns - both conflict-free.
       double* V = use_smem ? (S + RR) : a.Binv;
+      const int vi = use_smem ? 1 : R, vc = use_smem ? R + 1 : 1;   // strides of the row / column index
       __syncthreads();
-      for (int e = tid; e < RR; e += nt) V[e] = (e / R == e % R) ? 1.0 : 0.0;
+      for (int e = tid; e < RR; e += nt) V[(e / R) * vi + (e % R) * vc] = (e / R == e % R) ? 1.0 : 0.0;
       __syncthreads();
       for (int j = 0; j < R; ++j) {
-        const double d = W[j * R + j];
-        for (int c = tid; c <= j; c += nt) V[j * R + c] = V[j * R + c] / d;
-        __syncthreads();
-        const int ncol = j + 1, nent = (R - j - 1) * ncol;
-        for (int e = tid; e < nent; e += nt) {
-          const int i2 = j + 1 + e / ncol, c = e % ncol;
-          V[i2 * R + c] = fma(-W[j * R + i2], V[j * R + c], V[i2 * R + c]);
+        const double id = a.invdiag[j];   // 1 / L(j,j), stored above (visible after the barrier): no division on the chain
+        const int cstep = nt >> 6;
+        for (int i2 = j + 1 + (tid & 63); i2 < R; i2 += 64) {
+          const double lij = -W[j * R + i2];
+          for (int c0 = tid >> 6; c0 <= j; c0 += 8 * cstep) {   // batches of eight loads before the stores (see above)
+            double v8[8], r8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c = c0 + u * cstep;
+              const bool ok = c <= j;
+              v8[u] = ok ? V[i2 * vi + c * vc] : 0.0;
+              r8[u] = ok ? V[j * vi + c * vc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c = c0 + u * cstep;
+              if (c <= j) V[i2 * vi + c * vc] = fma(lij, r8[u] * id, v8[u]);
+            }
+          }
         }
         __syncthreads();
+        for (int c = tid; c <= j; c += nt) V[j * vi + c * vc] *= id;
       }
+      __syncthreads();
       // inv(B) = inv(L)' * inv(L)
       if (use_smem) {
         for (int e = tid; e < RR; e += nt) {
           const int ca = e / R, cb = e % R;
           const int lo = ca > cb ? ca : cb;
+          const double* va = V + ca * vc;
+          const double* vb = V + cb * vc;
           double acc = 0.0;
-          for (int i2 = lo; i2 < R; ++i2) acc = fma(V[i2 * R + ca], V[i2 * R + cb], acc);
+          for (int i2 = lo; i2 < R; ++i2) acc = fma(va[i2], vb[i2], acc);
           a.Binv[e] = acc;
         }
       } else {
@@ -272,9 +313,14 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
   // max_iters > 1 (cooperative launch, every CTA resident): the whole inner ADMM loop of :600 / :633 runs inside one
   // launch, with a grid-wide barrier after every iteration so that all CTAs see the exit test of the last CTA.
   extern __shared__ double sm[];
-  __shared__ double red[32];
+  __shared__ double redm[32 * (6 * kMaxGroup + 1)];   // per-warp values of the NS running sums
   __shared__ bool s_last;
   const int R = g.R, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthreads = blockDim.x;
+  // max_iters > 1: the grid-wide barrier between inner iterations is the "last CTA has evaluated the exit test" event
+  // itself - counter[1] is a generation number the last CTA bumps after finalize_ctl, everybody else spins on it (all
+  // CTAs are resident: cooperative launch).  One global round trip per inner iteration instead of the arrival counter
+  // plus a separate grid.sync(); these loops are pure latency (107 us for 5 iterations on 4 CTAs as on 256).
+  unsigned gen = (max_iters > 1) ? *reinterpret_cast<volatile unsigned*>(counter + 1) : 0u;
   double* a_s = sm;                      // [R][32]
   double* Binv_s = sm + (size_t)R * 32;  // [R*R] when BSMEM
   const long long i = (long long)blockIdx.x * 32 + lane;
@@ -283,7 +329,6 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
   const int NS = 6 * g.nmodes + 1;
   const bool coupled = g.Delta != nullptr;
   for (int inner = 0; inner < max_iters; ++inner) {
-  if (inner > 0) cooperative_groups::this_grid().sync();
   if (*reinterpret_cast<volatile int*>(&ctl->done) != 0) return;  // uniform over the grid
   double lsum[6 * kMaxGroup + 1];
   for (int s = 0; s < NS; ++s) lsum[s] = 0.0;
@@ -443,12 +488,20 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     }
   }
 
-  // deterministic two-level reduction: per-CTA partials, then the last CTA sums them in CTA order
+  // deterministic two-level reduction: per-CTA partials (all NS sums at once: shuffles, one barrier, the warps' values
+  // added in warp order), then the last CTA sums the partials in a fixed order
   for (int s = 0; s < NS; ++s) {
-    const double v = block_sum(lsum[s], red);
-    if (tid == 0) partials[(long long)blockIdx.x * NS + s] = v;
+    const double v = warp_sum(lsum[s]);
+    if (lane == 0) redm[w * (6 * kMaxGroup + 1) + s] = v;
   }
-  __threadfence();
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+    for (int ww = 0; ww < (nthreads >> 5); ++ww) v += redm[ww * (6 * kMaxGroup + 1) + tid];
+    partials[(long long)blockIdx.x * NS + tid] = v;
+    __threadfence();
+  }
+  __syncthreads();
   if (tid == 0) {
     const unsigned t = atomicAdd(counter, 1u);
     s_last = (t == gridDim.x - 1);
@@ -456,24 +509,32 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int s = tid; s < NS; s += nthreads) {
+    for (int s = w; s < NS; s += (nthreads >> 5)) {   // one warp per sum
       const int mi = s / 6, ww = s % 6;
       // sums owned by a deferred (non element-wise) constraint update are left untouched
       const bool deferred = (s < 6 * g.nmodes) && (ww >= 3) && g.m[mi].constrained &&
                             !prox_is_elementwise(g.m[mi].prox_kind);
       if (deferred) continue;
-      double v = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) v += partials[(long long)b * NS + s];
-      sums[s] = v;
+      const double v = warp_sum_partials(partials + s, gridDim.x, (unsigned)NS);
+      if (lane == 0) sums[s] = v;
     }
     __syncthreads();
     if (tid == 0) {
       *counter = 0u;
       if (finalize) finalize_ctl(sums, fin, tol, ctl);
       __threadfence();
+      if (max_iters > 1) atomicAdd(counter + 1, 1u);   // releases the other CTAs into the next inner iteration
     }
   }
-  __syncthreads();
+  if (max_iters > 1 && inner + 1 < max_iters) {
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile unsigned*>(counter + 1) == gen) {
+      }
+      __threadfence();
+    }
+    gen += 1u;
+    __syncthreads();
+  }
   }  // inner iterations
 }
 
@@ -516,10 +577,10 @@ __global__ void admm_constraint_update_kernel(AdmmGroup g, int which, const doub
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (threadIdx.x < 3) {
-      double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) t += partials[b * 3 + threadIdx.x];
-      sums[6 * which + 3 + threadIdx.x] = t;
+    if ((threadIdx.x >> 5) < 3) {   // one warp per sum
+      const int q = threadIdx.x >> 5;
+      const double t = warp_sum_partials(partials + q, gridDim.x, 3u);
+      if ((threadIdx.x & 31) == 0) sums[6 * which + 3 + q] = t;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -682,8 +743,8 @@ int gram(const double* F, int64_t rows, int64_t ld, int R, double* G, double* ws
 }
 
 int prep_system(const PrepArgs& a, cudaStream_t st, const int* skip) {
-  const size_t smem = (a.R <= 64) ? (size_t)2 * a.R * a.R * sizeof(double) : 0;
-  if (smem > 40 * 1024) ensure_dynamic_smem(reinterpret_cast<const void*>(prep_system_kernel), 2 * 64 * 64 * 8, 40 * 1024);
+  const size_t smem = (a.R <= 64) ? ((size_t)2 * a.R * a.R + a.R) * sizeof(double) : 0;
+  if (smem > 40 * 1024) ensure_dynamic_smem(reinterpret_cast<const void*>(prep_system_kernel), (2 * 64 * 64 + 64) * 8, 40 * 1024);
   if (a.Binv != nullptr && a.R > 64 && a.Btmp == nullptr) throw CudaError(1, "prep_system: Btmp scratch required for R > 64");
   prep_system_kernel<<<1, 256, smem, st>>>(a, skip);
   AO_CHECK_LAUNCH();
