@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
   const int e0 = w * 8;
   const int NS = 6 * g.nmodes + 1;
   const bool coupled = g.Delta != nullptr;
+  const bool binv_once = BSMEM && g.nmodes == 1;
   for (int inner = 0; inner < max_iters; ++inner) {
   if (*reinterpret_cast<volatile int*>(&ctl->done) != 0) return;  // uniform over the grid
   double lsum[6 * kMaxGroup + 1];
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(BSMEM ? 256 : 1024) admm_tile_kernel(AdmmGroup
     const double half = rho / 2.0;
     sum_rho += rho;
     __syncthreads();  // previous mode's GEMM has finished reading a_s / Binv_s
-    if (BSMEM && !rowsys)
+    if (BSMEM && !rowsys && !(binv_once && inner > 0))   // a single-mode group stages its inverse once for the whole loop
       for (int e = tid; e < R * R; e += nthreads) Binv_s[e] = md.Binv[e];
     if (active) {
 #pragma unroll
@@ -642,6 +643,7 @@ __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __re
   const RedJob jb = jobs[blockIdx.x];
   const int tid = threadIdx.x, nt = blockDim.x;
   double total = 0.0;  // valid in thread 0
+  double carry = 0.0;  // per-thread running sum over the columns of this CTA
   for (int c = blockIdx.y; c < jb.cols; c += kRedSplit) {
     const double* a = jb.a + (long long)c * jb.lda;
     const double* b = (jb.b != nullptr) ? jb.b + (long long)c * jb.ldb : nullptr;
@@ -703,8 +705,16 @@ __global__ void reduce_jobs_kernel(const RedJob* __restrict__ jobs, double* __re
         default: break;
       }
     }
-    acc = block_sum(acc, red);
-    if (tid == 0) total += (jb.kind == RED_COLNORM) ? sqrt(acc) : acc;
+    if (jb.kind == RED_COLNORM) {   // needs the square root of every column's sum
+      acc = block_sum(acc, red);
+      if (tid == 0) total += sqrt(acc);
+    } else {
+      carry += acc;                 // one block reduction for all columns of this CTA (two barriers per column were most
+    }                               // of the kernel on factor-sized jobs)
+  }
+  if (jb.kind != RED_COLNORM) {
+    carry = block_sum(carry, red);
+    if (tid == 0) total = carry;
   }
   if (tid == 0) partials[blockIdx.x * kRedSplit + blockIdx.y] = total;
   __threadfence();
