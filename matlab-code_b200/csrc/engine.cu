@@ -836,7 +836,7 @@ void Engine::release() {
   for (auto& s : par2_) {
     for (DevMat* d : {&s.W, &s.T, &s.P, &s.muDB, &s.DeltaB, &s.PDold, &s.gM, &s.gS}) dev_free(*d);
     for (void* q : {(void*)s.joff_dev, (void*)s.seg_dev, (void*)s.X_alloc, (void*)s.mask_alloc, (void*)s.redbuf, (void*)s.G2, (void*)s.Binv2, (void*)s.Binv3,
-                    (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.Vprev, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
+                    (void*)s.rho2, (void*)s.rho3, (void*)s.tdiag, (void*)s.contrib, (void*)s.Vprev, (void*)s.sysws, (void*)s.norms, (void*)s.Csum, (void*)s.segn,
                     (void*)s.res_partials})
       if (q) cudaFree(q);
     if (s.segn_host) cudaFreeHost(s.segn_host);
@@ -1128,7 +1128,7 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   ModeState &ma = mode(s.m1), &mb = mode(s.m2), &mc = mode(s.m3);
   s.R = ma.R;
   if (mb.R != s.R || mc.R != s.R) throw CudaError(1, "all modes of a PARAFAC2 object need the same rank");
-  if (s.R > 64) throw CudaError(2, "PARAFAC2 objects support at most 64 components on device");
+  if (s.R > 128) throw CudaError(2, "PARAFAC2 objects support at most 128 components on device");
   s.K = (prob->n_slices != nullptr) ? prob->n_slices[s.m2 - 1] : 0;
   const int64_t* jk = (prob->slice_rows != nullptr) ? prob->slice_rows[s.m2 - 1] : nullptr;
   if (s.K <= 0 || jk == nullptr || src.n_slices != s.K || src.slices == nullptr)
@@ -1227,6 +1227,7 @@ void Engine::setup_par2(const aoadmm_problem* prob, int p) {
   AO_CUDA(cudaMalloc(&s.Binv3, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.contrib, KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.Vprev, KRR * sizeof(double)));
+  if (s.R > 64) AO_CUDA(cudaMalloc(&s.sysws, 2 * KRR * sizeof(double)));
   AO_CUDA(cudaMalloc(&s.rho2, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.rho3, sizeof(double) * s.K));
   AO_CUDA(cudaMalloc(&s.tdiag, sizeof(double) * s.K));
@@ -1334,6 +1335,7 @@ void Engine::par2_update_B(ModeState& m, int outer_iter) {
   sa.rho_k = s.rho2;
   sa.Binv = s.Binv2;
   sa.ctl = m.ctl;
+  sa.gws = s.sysws;
   launches_ += par2_sys_prep(s.lay, sa, st_);
   const bool deferred = con_active && !prox_is_elementwise(m.con.kind);
   Par2BArgs b{};
@@ -1427,6 +1429,7 @@ void Engine::par2_precompute_C(ModeState& m, int n_rho_terms, bool ls_direct, do
   sa.no_factor = (Bsys_out != nullptr) ? 1 : 0;
   sa.HHt = HHt;
   sa.ctl = m.ctl;
+  sa.gws = s.sysws;
   launches_ += par2_sys_prep(s.lay, sa, st_);
   if (s.sharded) {
     // the third mode is updated on every rank (its K rows are few): gather the rows each rank prepared -

@@ -131,7 +131,8 @@ struct Par2State {
   uint64_t T_version = 0;                // version of A that T was computed from
   DevMat P, muDB, DeltaB, PDold, gM, gS;
   double *G2 = nullptr, *Binv2 = nullptr, *Binv3 = nullptr, *rho2 = nullptr, *rho3 = nullptr, *contrib = nullptr,
-         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr, *tdiag = nullptr, *Vprev = nullptr;
+         *norms = nullptr, *Csum = nullptr, *segn = nullptr, *res = nullptr, *res_partials = nullptr, *tdiag = nullptr, *Vprev = nullptr,
+         *sysws = nullptr;   // R > 64: factorisation workspace of the per-slice systems (2 R^2 per slice)
   double* segn_host = nullptr;           // pinned: K x 4 per-slice objective terms + 1 residual
   bool explicit_residual = false;        // objective needs ||X_k - A D_k B_k'||^2 (mode A is not updated last)
 };

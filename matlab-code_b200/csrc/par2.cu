@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(128) par2_sys_prep_kernel(Par2Layout L, Par2Sy
   __shared__ double red[32];
   __shared__ double s_rho;
   const int k = blockIdx.x + L.k0, R = L.R, RR = R * R, tid = threadIdx.x, nt = blockDim.x;
-  double* W = sm;            // system matrix / Cholesky factor
-  double* V = sm + RR;       // inverse of the factor
-  double* rhs_s = sm + 2 * RR;  // R
+  // R <= 64: everything in shared memory; larger ranks factor in the caller's global workspace (2 R^2 per slice)
+  const bool big = R > 64;
+  double* W = big ? a.gws + (size_t)k * 2 * RR : sm;   // system matrix / Cholesky factor
+  double* V = W + RR;                                   // inverse of the factor
+  double* rhs_s = big ? sm : sm + 2 * RR;               // R
   const long long j0 = L.joff[k];
   const int Jk = (int)(L.joff[k + 1] - j0);
   if (k == L.k0 && tid == 0 && a.ctl != nullptr) {  // a new inner loop starts (err is sticky)
@@ -360,16 +362,25 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const long long j0 = L.joff[k], ld = L.Jtot;
   const int Jk = (int)(L.joff[k + 1] - j0);
-  double* dB = sm;
-  double* Bi = sm + RR;
-  double* V = sm + 2 * RR;
-  double* M = use_gmem ? a.gM + j0 * R : sm + 3 * RR;
-  double* S = use_gmem ? a.gS + j0 * R : sm + 3 * RR + (size_t)L.Jmax * R;
+  // R <= 64: DeltaB, inv(Bsys_k) (later DeltaB' W and 1/sigma) and V in shared memory.  Larger ranks: DeltaB and the
+  // inverse are read from global memory, DeltaB' W / 1/sigma live in this slice's part of `contrib` (written with its
+  // result only at the very end) and V is iterated in place in `Vprev`.
+  const bool bigR = R > 64;
+  double* nrm = sm;   // squared column norms
+  double* base = sm + ((R + 1) & ~1);
+  const double* dB = bigR ? a.DeltaB : base;
+  double* Bi = bigR ? a.contrib + (size_t)k * RR : base + RR;
+  const double* Binv_ro = bigR ? a.Binv + (size_t)k * RR : Bi;
+  double* V = bigR ? a.Vprev + (size_t)k * RR : base + 2 * RR;
+  double* M = use_gmem ? a.gM + j0 * R : base + (bigR ? 0 : 3 * RR);
+  double* S = use_gmem ? a.gS + j0 * R : M + (size_t)L.Jmax * R;
   const double rho = a.rho_k[k], half = rho / 2.0;
   for (int e = tid; e < RR; e += nt) {
-    dB[e] = a.DeltaB[e];
-    Bi[e] = a.Binv[(size_t)k * RR + e];
-    V[e] = (e % (R + 1) == 0) ? 1.0 : 0.0;
+    if (!bigR) {
+      base[e] = a.DeltaB[e];
+      Bi[e] = a.Binv[(size_t)k * RR + e];
+    }
+    if (!bigR || !warm) V[e] = (e % (R + 1) == 0) ? 1.0 : 0.0;
   }
   __syncthreads();
   const int nitems = Jk * R;
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
     const int c = it / Jk, j = it % Jk;
     const long long g = j0 + j + (long long)c * ld;
     double x = 0.0;
-    for (int r = 0; r < R; ++r) x = fma(S[j + r * Jk], Bi[r + c * R], x);
+    for (int r = 0; r < R; ++r) x = fma(S[j + r * Jk], Binv_ro[r + c * R], x);
     a.B[g] = x;
     M[j + c * Jk] = x + a.mu[g];
   }
@@ -400,7 +411,8 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   // instead of 6-8; the polar factor it converges to is the same).  Wm = DeltaB' W is formed in the Binv area.
   double* Wm = Bi;
   if (warm) {
-    for (int e = tid; e < RR; e += nt) V[e] = a.Vprev[(size_t)k * RR + e];
+    if (!bigR)
+      for (int e = tid; e < RR; e += nt) V[e] = a.Vprev[(size_t)k * RR + e];
     __syncthreads();
     for (int e = tid; e < RR; e += nt) {
       const int r = e % R, c = e / R;
@@ -425,7 +437,6 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
   // product and one warp reduction per pair instead of three); the round-robin partner indices use a conditional subtract
   // instead of a modulo; tan(theta) = 2ga / (tau + sign(tau) sqrt(tau^2 + 4ga^2)) needs one division and one square root.
   const int Re = (R + 1) & ~1, npairs = Re / 2;
-  __shared__ double nrm[64];   // squared column norms (R <= 64)
   const double tol2 = 2.220446049250313e-16 * 2.220446049250313e-16 * (double)Jk;
   for (int sweep = 0; sweep < 60; ++sweep) {
     if (tid == 0) s_rot = 0;
@@ -488,7 +499,8 @@ __global__ void __launch_bounds__(kP2Threads) par2_B_step1_kernel(Par2Layout L, 
     __syncthreads();
     if (rot == 0) break;
   }
-  for (int e = tid; e < RR; e += nt) a.Vprev[(size_t)k * RR + e] = V[e];
+  if (!bigR)
+    for (int e = tid; e < RR; e += nt) a.Vprev[(size_t)k * RR + e] = V[e];
   // singular values -> 1/sigma (kept in the Bi area, no longer needed)
   for (int r = warp; r < R; r += nw) {
     const double* x = S + (size_t)r * Jk;
@@ -1180,7 +1192,7 @@ constexpr size_t kSmemBudget = 200 * 1024;
 }  // namespace
 
 size_t par2_step1_smem_bytes(long long Jmax, int R) {
-  const size_t small = (size_t)3 * R * R * sizeof(double);
+  const size_t small = ((size_t)((R + 1) & ~1) + (R <= 64 ? (size_t)3 * R * R : 0)) * sizeof(double);
   const size_t big = small + (size_t)2 * Jmax * R * sizeof(double);
   return big <= kSmemBudget ? big : small;
 }
@@ -1205,7 +1217,8 @@ int par2_modeA_had(const Par2Layout& L, const double* G2, const double* C, long 
 }
 
 int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)2 * L.R * L.R + L.R) * sizeof(double);
+  if (L.R > 64 && a.gws == nullptr) throw CudaError(1, "par2_sys_prep: workspace required for R > 64");
+  const size_t smem = ((L.R > 64 ? 0 : (size_t)2 * L.R * L.R) + L.R) * sizeof(double);
   opt_in_smem(par2_sys_prep_kernel, smem);
   par2_sys_prep_kernel<<<L.k1 - L.k0, 128, smem, st>>>(L, a);
   AO_CHECK_LAUNCH();
@@ -1310,7 +1323,8 @@ int par2_B_step1(const Par2Layout& L, const Par2BArgs& a, const InnerCtl* ctl, i
     return 1;
   }
   const size_t smem = par2_step1_smem_bytes(L.Jmax, L.R);
-  const int use_gmem = (smem == (size_t)3 * L.R * L.R * sizeof(double)) ? 1 : 0;
+  const size_t head = ((size_t)((L.R + 1) & ~1) + (L.R <= 64 ? (size_t)3 * L.R * L.R : 0)) * sizeof(double);
+  const int use_gmem = (smem == head) ? 1 : 0;
   opt_in_smem(par2_B_step1_kernel, smem);
   par2_B_step1_kernel<<<L.k1 - L.k0, kP2Threads, smem, st>>>(L, a, ctl, use_gmem, warm);
   AO_CHECK_LAUNCH();

@@ -61,6 +61,7 @@ struct Par2SysArgs {
   int no_factor;           // only assemble (rho_k, Bsys, rhs): the caller factors a larger system (coupling type 1)
   const double* HHt;       // optional (mode 3, coupling type 2): B_k += rho_k/2 * H*H' (:307)
   InnerCtl* ctl;           // err = 3 when a system is not positive definite
+  double* gws = nullptr;   // R > 64: global workspace, 2 R^2 doubles per slice (indexed by the global slice number)
 };
 int par2_sys_prep(const Par2Layout& L, const Par2SysArgs& a, cudaStream_t st);
 

@@ -318,6 +318,20 @@ def test_config4_family_cp_coupled_with_parafac2(ab, kw):
     assert_state_close(Gd, Go, keys=PAR2_KEYS)
 
 
+@pytest.mark.parametrize('kw', [dict(I=90, J=20, K=10, Jk=80, Kp=6, R=70),      # R > 64: per-slice systems in global memory
+                                dict(I=110, J=12, K=8, Jk=150, Kp=4, R=100),    # ... and slices that do not fit shared memory
+                                dict(I=40, J=16, K=10, Jk=128, Kp=7, R=16),     # register Jacobi, four rows per lane
+                                dict(I=30, J=16, K=10, Jk=200, Kp=5, R=12),     # long slices: CTA Jacobi
+                                dict(I=30, J=16, K=10, Jk=40, Kp=5, R=20)])     # 16 < R <= 64: CTA Jacobi
+def test_parafac2_rank_and_slice_size_variants(ab, kw):
+    """Every code path of the per-slice PARAFAC2 work: the register-resident and the CTA polar-factor kernels, and ranks
+    above 64 (reference: R <= J_k is the only limit, cmtf_AOADMM.m:55-65)."""
+    Z, G, _ = pg.config_cp_par2(seed=8, noise=0.1, **kw)
+    Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=8, **ZERO_TOL))
+    _assert_par2_out_close(od, oo)
+    assert_state_close(Gd, Go, keys=PAR2_KEYS)
+
+
 def test_config4_zero_tolerances_and_noise_free(ab):
     Z, G, _ = pg.config_cp_par2(seed=5, noise=0.0)
     Go, oo, Gd, od = _both(ab, Z, G, pg.default_options(MaxOuterIters=30, **ZERO_TOL))
