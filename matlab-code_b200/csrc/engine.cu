@@ -582,6 +582,19 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
                              cudaMemcpyHostToDevice));
       has_missing_ = true;
     }
+    if (o.order == 2 && o.mask == nullptr && o.dims[0] >= 1 && o.dims[1] >= 1 &&
+        (size_t)o.dims[0] * (size_t)o.dims[1] * 8 <= ((size_t)2 << 30)) {
+      // second copy of a (small) matrix, transposed; a failed allocation just keeps the single-copy path
+      o.ldT = round_up(o.dims[1], 2);
+      if (cudaMalloc(&o.dataT, (size_t)o.ldT * (size_t)o.dims[0] * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        o.dataT = nullptr;
+      } else {
+        AO_CUDA(cudaDeviceSynchronize());   // the upload above (null stream) before the kernel on the engine's stream
+        AO_CUDA(cudaMemsetAsync(o.dataT, 0, (size_t)o.ldT * (size_t)o.dims[0] * sizeof(double), st_));
+        refresh_transposed(o);
+      }
+    }
     AO_CUDA(cudaDeviceSynchronize());  // pageable H2D copies return before the DMA has finished
   }
   for (auto& m : modes_) {
@@ -818,6 +831,7 @@ void Engine::release() {
   modes_.clear();
   for (auto& o : objects_) {
     dfree(o.data);
+    dfree(o.dataT);
     dfree(o.Tbuf);
     dfree(o.mask);
     dfree(o.em_kr);
@@ -882,6 +896,34 @@ void Engine::release() {
   cudaGetLastError();
 }
 
+namespace {
+// out (cols x rows, leading dimension ldo) = in' (in: rows x cols, leading dimension ldi); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_ld_kernel(const double* __restrict__ in, long long rows, long long cols,
+                                                            long long ldi, double* __restrict__ out, long long ldo) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int q = ty; q < 32; q += 8) {
+    const long long r = r0 + tx, c = c0 + q;
+    tile[q][tx] = (r < rows && c < cols) ? in[r + ldi * c] : 0.0;
+  }
+  __syncthreads();
+  for (int q = ty; q < 32; q += 8) {
+    const long long c = c0 + tx, r = r0 + q;
+    if (r < rows && c < cols) out[c + ldo * r] = tile[tx][q];
+  }
+}
+}  // namespace
+
+// (re)build the transposed copy of a matrix object after its data changed
+void Engine::refresh_transposed(ObjectState& o) {
+  if (o.dataT == nullptr) return;
+  dim3 grid((unsigned)ceil_div(o.dims[0], 32), (unsigned)ceil_div(o.dims[1], 32));
+  transpose_ld_kernel<<<grid, 256, 0, st_>>>(o.data, o.dims[0], o.dims[1], o.ld0, o.dataT, o.ldT);
+  AO_CHECK_LAUNCH();
+  ++launches_;
+}
+
 void Engine::build_views(ObjectState& o) {
   const int N = o.order;
   const int R = mode(o.modes[0]).R;
@@ -894,7 +936,18 @@ void Engine::build_views(ObjectState& o) {
   for (int n = 0; n < N; ++n) {
     View3& v = o.views[n];
     int64_t I, J, K, ldI;
-    if (N == 2) {
+    const double* base = o.data;
+    if (N == 2 && n == 1 && o.dataT != nullptr) {
+      // mode 2 of a matrix from its transposed copy: out(j,:) = sum_i Yt(j,i) F1(i,:) - the contiguous-mode (LEAD) form
+      base = o.dataT;
+      I = o.dims[1];
+      J = o.dims[0];
+      K = 1;
+      ldI = o.ldT;
+      v.kernel_pos = 0;
+      v.f0_modes = {o.modes[0]};
+      v.f1_modes = {};
+    } else if (N == 2) {
       I = o.dims[0];
       J = o.dims[1];
       K = 1;
@@ -925,7 +978,7 @@ void Engine::build_views(ObjectState& o) {
       v.f0_modes.assign(o.modes.begin(), o.modes.begin() + n);
       v.f1_modes.assign(o.modes.begin() + n + 1, o.modes.end());
     }
-    make_tensor3(v.t, o.data, I, J, K, ldI);
+    make_tensor3(v.t, base, I, J, K, ldI);
     auto rows_of = [&](const std::vector<int>& ms, bool padded_first) {
       int64_t r = 1;
       for (size_t q = 0; q < ms.size(); ++q) {
@@ -2300,6 +2353,7 @@ void Engine::generate_cp_data(int object, const double* const* factors, double n
   launches_ += 5;
   o.znorm = 1.0;
   o.T_version = 0;  // cached partial contractions refer to the old data
+  refresh_transposed(o);
   for (auto p : tmp) cudaFree(p);
   cudaFree(sums);
 }

@@ -157,6 +157,8 @@ struct ObjectState {
   bool znorm_pending_allreduce = false;
   double* data = nullptr;     // device, leading dimension ld0
   int64_t ld0 = 0;
+  double* dataT = nullptr;    // matrices without a mask: transposed copy (dims[1] x dims[0], leading dimension ldT) so that
+  int64_t ldT = 0;            // the mode-2 product is a LEAD launch too (the K = 1 INNER launch cannot split inside its one slab)
   int64_t shard_offset = 0, shard_extent = 0, last_full = 0;
   bool sharded = false;
   std::vector<View3> views;   // one per mode position
@@ -210,6 +212,7 @@ class Engine {
   void construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void* shared_comm);
   void release();
   void build_views(ObjectState& o);
+  void refresh_transposed(ObjectState& o);
   void build_objective_jobs();
   // sweep pieces
   void refresh_gram(ModeState& m);
