@@ -17,14 +17,19 @@ __global__ void __launch_bounds__(256) dgemm_small_kernel(int transA, int transB
                                                            const double* __restrict__ A, long long lda,
                                                            const double* __restrict__ B, long long ldb, double beta,
                                                            double* __restrict__ C, long long ldc,
-                                                           const int* __restrict__ skip) {
+                                                           const int* __restrict__ skip, long long kchunk,
+                                                           double* __restrict__ ws) {
+  // ws != nullptr: split-K mode - CTA z reduces k in [z*kchunk, (z+1)*kchunk) and stores its raw partial tile into
+  // ws[z] (M x N, ld = M); dgemm_splitk_reduce_kernel adds the partials in z order
   if (skip != nullptr && *skip != 0) return;
   __shared__ double As[kKStep][kTile + 1];
   __shared__ double Bs[kKStep][kTile + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, tid = threadIdx.x;
   const long long m0 = (long long)blockIdx.x * kTile, n0 = (long long)blockIdx.y * kTile;
   double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  for (long long k0 = 0; k0 < K; k0 += kKStep) {
+  const long long kb = (ws != nullptr) ? (long long)blockIdx.z * kchunk : 0;
+  if (ws != nullptr) K = min(K, kb + kchunk);
+  for (long long k0 = kb; k0 < K; k0 += kKStep) {
     for (int e = tid; e < kKStep * kTile; e += 256) {
       int kk, mm;
       if (transA) {  // A stored K x M: consecutive threads walk k (contiguous)
@@ -71,11 +76,26 @@ __global__ void __launch_bounds__(256) dgemm_small_kernel(int transA, int transB
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const long long gm = m0 + tx + 16 * i, gn = n0 + ty + 16 * j;
-      if (gm < M && gn < N) {
+      if (gm < M && gn < N && ws != nullptr) {
+        ws[(long long)blockIdx.z * M * N + gm + gn * M] = acc[i][j];
+      } else if (gm < M && gn < N) {
         double* c = C + gm + gn * ldc;
         *c = (beta != 0.0) ? al * acc[i][j] + beta * (*c) : al * acc[i][j];
       }
     }
+}
+
+__global__ void dgemm_splitk_reduce_kernel(const double* __restrict__ ws, int splits, long long M, long long N, double alpha,
+                                           double beta, double* __restrict__ C, long long ldc,
+                                           const int* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long mn = M * N;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < mn; e += (long long)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int z = 0; z < splits; ++z) v += ws[(long long)z * mn + e];
+    double* c = C + e % M + (e / M) * ldc;
+    *c = (beta != 0.0) ? alpha * v + beta * (*c) : alpha * v;
+  }
 }
 
 struct LinArgs {
@@ -107,12 +127,22 @@ __global__ void transpose_kernel(const double* __restrict__ in, long long rows, 
   }
 }
 
-__global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* __restrict__ S, long long m, int n,
-                                                               double* __restrict__ V, double* __restrict__ sig,
-                                                               const int* __restrict__ skip) {
+__global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* S, long long m, int n, double* V,
+                                                               double* __restrict__ sig, const int* __restrict__ skip,
+                                                               int use_smem) {
   if (skip != nullptr && *skip != 0) return;
   __shared__ int s_rot;
+  extern __shared__ double jsm[];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  // small problems (the Rayleigh-Ritz / Gram matrices of the eigen-iteration, the coupling matrices H) are iterated in
+  // shared memory: every element access of a round is then a 30-cycle instead of a global / L2 round trip
+  double* const Sg = S;
+  double* const Vg = V;
+  if (use_smem) {
+    S = jsm;
+    V = jsm + m * n;
+    for (long long e = tid; e < m * n; e += nt) S[e] = Sg[e];
+  }
   for (long long e = tid; e < (long long)n * n; e += nt) V[e] = (e % (n + 1) == 0) ? 1.0 : 0.0;
   __syncthreads();
   const int ne = (n + 1) & ~1, npairs = ne / 2;
@@ -148,10 +178,14 @@ __global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* __restrict
         al = warp_sum(al);
         be = warp_sum(be);
         ga = warp_sum(ga);
-        if (fabs(ga) > tol * sqrt(al * be)) {
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        if (ga * ga > tol * tol * (al * be)) {
+          // tan(theta) = 2 ga / (tau + sign(tau) sqrt(tau^2 + 4 ga^2)), tau = be - al - the same rotation as
+          // sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = tau / (2 ga), without the two divisions and two
+          // square roots whose latency was most of a round (x * rsqrt(x), one reciprocal; see par2.cu)
+          const double tau = be - al, g2 = 2.0 * ga;
+          const double x2 = fma(tau, tau, g2 * g2);
+          const double t = g2 * __drcp_rn(tau + copysign(x2 * rsqrt(x2), tau));
+          const double cs = rsqrt(fma(t, t, 1.0)), sn = cs * t;
           for (long long j = lane; j < m; j += 32) {
             const double xv = x[j], yv = y[j];
             x[j] = cs * xv - sn * yv;
@@ -179,6 +213,11 @@ __global__ void __launch_bounds__(512) jacobi_onesided_kernel(double* __restrict
     for (long long j = lane; j < m; j += 32) al = fma(x[j], x[j], al);
     al = warp_sum(al);
     if (lane == 0) sig[c] = sqrt(al);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (long long e = tid; e < m * n; e += nt) Sg[e] = S[e];
+    for (long long e = tid; e < (long long)n * n; e += nt) Vg[e] = V[e];
   }
 }
 
@@ -268,9 +307,33 @@ int dgemm_small(int transA, int transB, long long M, long long N, long long K, d
                 cudaStream_t st, const int* skip) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((unsigned)ceil_div(M, kTile), (unsigned)ceil_div(N, kTile));
-  dgemm_small_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, alpha_dev, A, lda, B, ldb, beta, C, ldc, skip);
+  dgemm_small_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, alpha_dev, A, lda, B, ldb, beta, C, ldc, skip, 0,
+                                           nullptr);
   AO_CHECK_LAUNCH();
   return 1;
+}
+
+int dgemm_splitk_count(long long M, long long N, long long K) {
+  // enough CTAs for the whole GPU, at least 512 reduction steps each
+  const long long tiles = ceil_div(M, kTile) * ceil_div(N, kTile);
+  long long s = std::min<long long>(ceil_div(2 * 148, tiles), ceil_div(K, 512));
+  return (int)std::max<long long>(1, std::min<long long>(s, 256));
+}
+
+int dgemm_small_splitk(int transA, int transB, long long M, long long N, long long K, double alpha, const double* A,
+                       long long lda, const double* B, long long ldb, double beta, double* C, long long ldc, double* ws,
+                       cudaStream_t st, const int* skip) {
+  if (M <= 0 || N <= 0) return 0;
+  const int splits = dgemm_splitk_count(M, N, K);
+  if (splits <= 1 || ws == nullptr)
+    return dgemm_small(transA, transB, M, N, K, alpha, nullptr, A, lda, B, ldb, beta, C, ldc, st, skip);
+  const long long kchunk = ceil_div(ceil_div(K, splits), kKStep) * kKStep;
+  dim3 grid((unsigned)ceil_div(M, kTile), (unsigned)ceil_div(N, kTile), (unsigned)ceil_div(K, kchunk));
+  dgemm_small_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, 1.0, nullptr, A, lda, B, ldb, 0.0, C, ldc, skip, kchunk, ws);
+  AO_CHECK_LAUNCH();
+  dgemm_splitk_reduce_kernel<<<flat_grid(M * N), 256, 0, st>>>(ws, (int)grid.z, M, N, alpha, beta, C, ldc, skip);
+  AO_CHECK_LAUNCH();
+  return 2;
 }
 
 int lincomb(double* out, long long n, const LinTerm* terms, int nterms, cudaStream_t st, const int* skip) {
@@ -307,7 +370,10 @@ int quad_scale_rows(double* Y, long long rows, int cols, const double* lam, doub
 }
 
 int jacobi_onesided(double* S, long long m, int n, double* V, double* sig, cudaStream_t st, const int* skip) {
-  jacobi_onesided_kernel<<<1, 512, 0, st>>>(S, m, n, V, sig, skip);
+  const size_t bytes = ((size_t)m * n + (size_t)n * n) * sizeof(double);
+  const int use_smem = (bytes <= 200 * 1024) ? 1 : 0;
+  if (use_smem) ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_onesided_kernel), bytes);
+  jacobi_onesided_kernel<<<1, 512, use_smem ? bytes : 0, st>>>(S, m, n, V, sig, skip, use_smem);
   AO_CHECK_LAUNCH();
   return 1;
 }

@@ -14,6 +14,14 @@ int dgemm_small(int transA, int transB, long long M, long long N, long long K, d
                 const double* A, long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
                 cudaStream_t st, const int* skip);
 
+// The same product for a LONG reduction and a small result (e.g. V'W with V, W of 4096 x 80): the reduction range is
+// split over CTAs (dgemm_splitk_count(M, N, K) parts) into `ws` (>= count * M * N doubles) and the partial tiles are
+// added in a fixed order - two launches, bit-reproducible.  Falls back to dgemm_small when one part is enough.
+int dgemm_splitk_count(long long M, long long N, long long K);
+int dgemm_small_splitk(int transA, int transB, long long M, long long N, long long K, double alpha, const double* A,
+                       long long lda, const double* B, long long ldb, double beta, double* C, long long ldc, double* ws,
+                       cudaStream_t st, const int* skip);
+
 // out[i] = sum_t coef[t] * (coef_dev[t] ? *coef_dev[t] : 1) * x[t][i],  i < n   (up to 5 terms; out may alias any x[t])
 struct LinTerm {
   const double* x;

@@ -554,10 +554,11 @@ EigInfo top_eigvecs(const double* Y, long long n, int r, double* U, double* thet
   const size_t nb = (size_t)n * Rb, bb = (size_t)Rb * Rb;
   double* buf = nullptr;
   int* order_dev = nullptr;
-  AO_CUDA(cudaMalloc(&buf, (4 * nb + 3 * bb + 3 * (size_t)Rb) * sizeof(double)));
+  const size_t wsd = (size_t)dgemm_splitk_count(Rb, Rb, n) * bb;   // split-K partials of the block x block products
+  AO_CUDA(cudaMalloc(&buf, (4 * nb + 3 * bb + 3 * (size_t)Rb + wsd) * sizeof(double)));
   AO_CUDA(cudaMalloc(&order_dev, sizeof(int) * (size_t)r));
   double *V = buf, *W = V + nb, *Z = W + nb, *Ur = Z + nb, *H = Ur + nb, *Q = H + bb, *G = Q + bb, *sig = G + bb,
-         *ev = sig + Rb, *res = ev + Rb;
+         *ev = sig + Rb, *res = ev + Rb, *ws = res + Rb;
   std::vector<double> h_sig(Rb), h_res(Rb);
   std::vector<int> order(Rb);
   int L = 0;
@@ -567,7 +568,7 @@ EigInfo top_eigvecs(const double* Y, long long n, int r, double* U, double* thet
     auto orthonormalise = [&](double* src) {
       for (int pass = 0; pass < 2; ++pass) {
         const double* in = (pass == 0) ? src : V;
-        L += dgemm_small(1, 0, Rb, Rb, n, 1.0, nullptr, in, n, in, n, 0.0, G, Rb, st, nullptr);
+        L += dgemm_small_splitk(1, 0, Rb, Rb, n, 1.0, in, n, in, n, 0.0, G, Rb, ws, st, nullptr);
         symmetrize_kernel<<<blocks_for((long long)bb), 256, 0, st>>>(G, Rb);
         L += 1 + jacobi_onesided(G, Rb, Rb, Q, ev, st);
         L += dgemm_small(0, 0, n, Rb, Rb, 1.0, nullptr, in, n, Q, Rb, 0.0, W, n, st, nullptr);
@@ -589,7 +590,7 @@ EigInfo top_eigvecs(const double* Y, long long n, int r, double* U, double* thet
     for (int it = 1; it <= maxit; ++it) {
       info.iterations = it;
       L += dgemm_small(0, 0, n, Rb, n, 1.0, nullptr, Y, n, V, n, 0.0, W, n, st, nullptr);        // W = Y V
-      L += dgemm_small(1, 0, Rb, Rb, n, 1.0, nullptr, V, n, W, n, 0.0, H, Rb, st, nullptr);      // H = V' Y V
+      L += dgemm_small_splitk(1, 0, Rb, Rb, n, 1.0, V, n, W, n, 0.0, H, Rb, ws, st, nullptr);    // H = V' Y V
       symmetrize_kernel<<<blocks_for((long long)bb), 256, 0, st>>>(H, Rb);
       L += 1 + jacobi_onesided(H, Rb, Rb, Q, sig, st);                                           // H = Q diag(sig) Q'
       L += dgemm_small(0, 0, n, Rb, Rb, 1.0, nullptr, W, n, Q, Rb, 0.0, Z, n, st, nullptr);      // Z = Y (V Q)
