@@ -583,6 +583,7 @@ void Engine::construct(const aoadmm_problem* prob, const aoadmm_dist* dist, void
       has_missing_ = true;
     }
     if (o.order == 2 && o.mask == nullptr && o.dims[0] >= 1 && o.dims[1] >= 1 &&
+        ceil_div(o.dims[1], 32) <= 65535 &&   // grid.y of the transpose
         (size_t)o.dims[0] * (size_t)o.dims[1] * 8 <= ((size_t)2 << 30)) {
       // second copy of a (small) matrix, transposed; a failed allocation just keeps the single-copy path
       o.ldT = round_up(o.dims[1], 2);
